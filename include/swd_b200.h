@@ -1,0 +1,140 @@
+/*
+ * swd_b200.h — C-ABI of the B200-native batched window decoder (libswd_b200.so).
+ *
+ * Drop-in boundary for the hot path of gongaa/SlidingWindowDecoder: one handle
+ * replaces one Cython decoder object of the reference and decodes a BATCH of
+ * syndromes of the same window on one B200.  Plain pointers and sizes only; no
+ * torch / numpy types.  Every entry point returns an int status (0 = OK, <0 =
+ * error, see swd_strerror) and never aborts the process (the reference's C
+ * layer may exit(1)/abort(), mod2sparse.c:94-97, mod2sparse_extra.cpp:139).
+ *
+ * Reference interfaces replaced (file:line under the reference's src/):
+ *   swd_create            <- bp_history_decoder.__cinit__  bp_guessing_decoder.pyx:6-46
+ *                            bpgdg_decoder.__cinit__       bp_guessing_decoder.pyx:161-219
+ *                            bpgd_decoder.__cinit__        bp_guessing_decoder.pyx:474-499
+ *                            osd_window.__cinit__          osd_window.pyx:8-126
+ *                            (numpy2mod2sparse / spmatrix2mod2sparse, mod2sparse.pyx:6-32)
+ *   swd_decode_batch_*    <- bpgdg_decoder.decode          bp_guessing_decoder.pyx:221-236
+ *                            bpgd_decoder.decode           bp_guessing_decoder.pyx:501-514
+ *                            osd_window.decode             osd_window.pyx:158-199
+ *                            which in turn replace BPGD_main_thread::do_work (bpgd.cpp:591-688),
+ *                            BPGD::{reset,min_sum_log,select_vn,peel,vn_set_value,get_pm}
+ *                            (bpgd.cpp:13-351), index_sort (bpgd.cpp:384-389),
+ *                            mod2sparse_decomp_osd + LU_forward_backward_solve
+ *                            (mod2sparse_extra.cpp:78-376)
+ *   swd_destroy           <- __dealloc__                   bp_guessing_decoder.pyx:142-154,444-469
+ *   swd_window_*          <- the per-window bookkeeping of guessing.py:141-227 / osd.py:134-179
+ *                            (commit first F rounds, syndrome update, flagged / logical counters)
+ */
+#ifndef SWD_B200_H
+#define SWD_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWD_OK               0
+#define SWD_ERR_INVALID     -1   /* bad argument (NULL, negative size, length mismatch)            */
+#define SWD_ERR_UNSUPPORTED -2   /* graph exceeds a kernel limit (see DESIGN.md "limits")           */
+#define SWD_ERR_CUDA        -3   /* CUDA runtime error; text via swd_last_error()                   */
+#define SWD_ERR_NOMEM       -4
+
+/* decoder kinds == the reference's three decoder classes */
+#define SWD_KIND_BPGDG       0   /* bpgdg_decoder  (GDG)                    */
+#define SWD_KIND_BPGD        1   /* bpgd_decoder   (plain guided decimation) */
+#define SWD_KIND_OSD_WINDOW  2   /* osd_window     (BP + shortening + OSD)   */
+
+#define SWD_OSD_0  0
+#define SWD_OSD_E  1
+#define SWD_OSD_CS 2
+
+/* kwargs of the reference constructors, same meaning and defaults
+ * (bp_guessing_decoder.pyx:7-9,162-171,475-478; osd_window.pyx:10-16). */
+typedef struct swd_config {
+    int    kind;
+    int    device;                /* CUDA device ordinal                                         */
+    /* BP on the full window ("max_iter" / "pre_max_iter") */
+    int    max_iter;
+    double ms_scaling_factor;
+    /* GDG / GD */
+    int    max_iter_per_step;
+    int    max_step;
+    int    max_tree_depth;
+    int    max_side_depth;
+    int    max_tree_branch_step;
+    int    max_side_branch_step;
+    double gdg_factor;            /* gdg_factor, or gd_factor for SWD_KIND_BPGD                   */
+    int    new_n;                 /* <= 0 : min(n, 2m)                                            */
+    int    multi_thread;          /* 1: bpgd.cpp branch tree; 0: single-thread schedule (pyx:254) */
+    int    low_error_mode;
+    /* osd_window */
+    int    post_max_iter;
+    int    osd_method;            /* SWD_OSD_*                                                    */
+    int    osd_order;
+} swd_config;
+
+typedef struct swd_decoder swd_decoder;
+
+/* Work counters accumulated since creation / last reset (for roofline accounting). */
+typedef struct swd_counters {
+    uint64_t shots;               /* syndromes decoded                                           */
+    uint64_t pre_bp_edge_iters;   /* edges x iterations executed by the full-window BP kernel    */
+    uint64_t path_edge_iters;     /* active edges x iterations executed inside GDG/GD/post-BP    */
+    uint64_t gdg_shots;           /* shots that went past the pre-BP                             */
+    uint64_t osd_shots;           /* shots that reached OSD                                      */
+    uint64_t kernel_launches;     /* kernels launched by this library                            */
+    uint64_t paths_run;           /* branch paths that executed at least one BP call             */
+    uint64_t bp_calls;            /* min_sum_log-equivalent calls over all branch paths          */
+} swd_counters;
+
+/* pcm as CSC: colptr[n+1], rowidx[nnz] (any order inside a column; sorted internally, as
+ * mod2sparse_insert keeps them).  channel_llr[n] = log((1-p)/p) computed by the caller with libm
+ * (bp_guessing_decoder.pyx:46).  All arrays are HOST pointers and are copied. */
+int  swd_create(const swd_config *cfg, int m, int n, const int32_t *colptr, const int32_t *rowidx,
+                const double *channel_llr, swd_decoder **out);
+void swd_destroy(swd_decoder *d);
+
+/* Decode B syndromes. synd[B*m], corr[B*n] one byte per bit (0/1), converge[B];
+ * min_pm[B] optional (NULL ok).  _host: host pointers, H2D/D2H copies inside the call,
+ * synchronous.  _device: device pointers, asynchronous on `stream` (a cudaStream_t). */
+int  swd_decode_batch_host(swd_decoder *d, const uint8_t *synd, int64_t B,
+                           uint8_t *corr, uint8_t *converge, double *min_pm);
+int  swd_decode_batch_device(swd_decoder *d, const uint8_t *d_synd, int64_t B,
+                             uint8_t *d_corr, uint8_t *d_converge, double *d_min_pm, void *stream);
+
+/* osd_window read-only properties of the LAST batch (osd_window.pyx:487-517), host copies.
+ * Any pointer may be NULL.  bp_dec/osd0/osdw: [B*n]; log_prob_ratios: [B*n*4]; bp_iteration: [B]. */
+int  swd_osd_last_outputs(swd_decoder *d, int64_t B, uint8_t *bp_dec, uint8_t *osd0, uint8_t *osdw,
+                          double *log_prob_ratios, int32_t *bp_iteration);
+
+int  swd_get_counters(swd_decoder *d, swd_counters *out);
+int  swd_reset_counters(swd_decoder *d);
+int  swd_rank(swd_decoder *d);          /* GF(2) rank of the pcm (mod2sparse_rank), -1 if n/a      */
+int  swd_new_n(swd_decoder *d);
+
+/* ---- sliding-window bookkeeping on the device (guessing.py:204-227, osd.py:170-179) ------------
+ * A "window plan" holds the full detector matrix chk (num_det x num_col, CSC) and the observable
+ * matrix obs (num_obs x num_col, CSC).  All shot data is one byte per bit, row-major, on device. */
+typedef struct swd_window swd_window;
+int  swd_window_create(int device, int num_det, int num_col, const int32_t *chk_colptr, const int32_t *chk_rowidx,
+                       int num_obs, const int32_t *obs_colptr, const int32_t *obs_rowidx, swd_window **out);
+void swd_window_destroy(swd_window *w);
+/* copy syndrome columns [row0,row0+m) of d_det[B,num_det] into d_synd[B,m]  (detector_win = new_det_data[:, a0:b0]) */
+int  swd_window_extract(swd_window *w, const uint8_t *d_det, int64_t B, int row0, int m, uint8_t *d_synd, void *stream);
+/* commit: for every shot XOR chk[:, col0+j] into d_det and obs[:, col0+j] into d_obs for each j < ncommit with
+ * d_corr[b, j] == 1 (d_corr has row stride n_win); i.e. new_det = det + e_hat @ chk.T restricted to the commit. */
+int  swd_window_commit(swd_window *w, const uint8_t *d_corr, int64_t B, int n_win, int col0, int ncommit,
+                       uint8_t *d_det, uint8_t *d_obs, void *stream);
+/* counts over shots: flagged = any(det residual), logical = flagged or any(obs residual). out[0]=flagged, out[1]=failed */
+int  swd_window_count_failures(swd_window *w, const uint8_t *d_det, const uint8_t *d_obs, int64_t B,
+                               unsigned long long *d_out2, void *stream);
+
+const char *swd_strerror(int status);
+const char *swd_last_error(void);
+const char *swd_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

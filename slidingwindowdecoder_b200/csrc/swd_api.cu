@@ -1,0 +1,538 @@
+// swd_api.cu — host side of libswd_b200.so: the C-ABI declared in include/swd_b200.h.
+// Builds the flat graph, sizes the per-batch workspace, launches the kernel pipeline.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include <string>
+#include <mutex>
+
+#include "../../include/swd_b200.h"
+#include "swd_kernels.cuh"
+#include "swd_osd.cuh"
+#include "swd_window.cuh"
+
+static thread_local std::string g_last_error;
+static void set_err(const std::string &s) { g_last_error = s; }
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            set_err(std::string(#call) + ": " + cudaGetErrorString(e_));                                  \
+            return SWD_ERR_CUDA;                                                                          \
+        }                                                                                                 \
+    } while (0)
+
+static inline int r16(int x) { return (x + 15) & ~15; }
+static inline int r32up(int x) { return (x + 31) & ~31; }
+
+typedef void (*path_fn_t)(Workspace, SubLayout, PathSmem, GdgDev, int);
+static path_fn_t pick_path_kernel(int dmax, int T) {
+    if (dmax == 8) {
+        if (T <= 128) return path_kernel<4, 8, 128>;
+        if (T <= 512) return path_kernel<4, 8, 512>;
+        return path_kernel<4, 8, 1024>;
+    }
+    if (T <= 128) return path_kernel<4, 16, 128>;
+    return path_kernel<4, 16, 1024>;
+}
+
+struct swd_decoder {
+    swd_config cfg;
+    path_fn_t path_fn = nullptr;
+    int m = 0, n = 0, nnz = 0, nn = 0, max_col_deg = 0, max_row_deg = 0, es_max = 0, rank = -1;
+    int device = 0, num_sm = 0;
+    GraphDev g{};
+    void *d_graph[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    SubLayout L{};
+    PathSmem PS{};
+    PreSmem PRE{};
+    SortSmem SS{};
+    OsdSmem OS{};
+    GdgDev P{};
+    int T1 = 0, T2 = 0, T3 = 0, T5 = 0, dmax = 8;
+    int grid1 = 0, grid2 = 0, grid3 = 0, grid5 = 0;
+    // workspace
+    long long cap = 0;            // shots per chunk
+    Workspace ws{};
+    double *hscratch = nullptr;
+    OsdWork ow{};
+    void *ws_block = nullptr;
+    // staging for the host entry point
+    u8 *d_synd = nullptr, *d_corr = nullptr, *d_conv = nullptr; double *d_pm = nullptr;
+    u8 *h_pin = nullptr; size_t h_pin_bytes = 0;
+    long long stage_cap = 0;
+    cudaStream_t stream = nullptr;
+    // accumulated counters
+    swd_counters ctr{};
+    long long last_B = 0;
+};
+
+extern "C" const char *swd_version(void) { return "swd_b200 0.1 (sm_100a)"; }
+extern "C" const char *swd_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char *swd_strerror(int s) {
+    switch (s) {
+        case SWD_OK: return "ok";
+        case SWD_ERR_INVALID: return "invalid argument";
+        case SWD_ERR_UNSUPPORTED: return "unsupported configuration";
+        case SWD_ERR_CUDA: return "CUDA error";
+        case SWD_ERR_NOMEM: return "out of memory";
+    }
+    return "unknown";
+}
+
+template <typename T>
+static int upload(const std::vector<T> &v, void **out) {
+    CK(cudaMalloc(out, std::max<size_t>(16, v.size() * sizeof(T))));
+    CK(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return SWD_OK;
+}
+
+// GF(2) rank of the pcm (what mod2sparse_rank returns, mod2sparse_extra.cpp:32-76), dense bit-packed.
+static int host_rank(int m, int n, const std::vector<int> &cp, const std::vector<int> &cr) {
+    const int W = (m + 63) / 64;
+    std::vector<std::vector<uint64_t>> basis;
+    std::vector<int> prow;
+    std::vector<uint64_t> v(W);
+    for (int c = 0; c < n && (int)basis.size() < std::min(m, n); c++) {
+        std::fill(v.begin(), v.end(), 0);
+        for (int e = cp[c]; e < cp[c + 1]; e++) v[cr[e] >> 6] ^= 1ull << (cr[e] & 63);
+        for (size_t i = 0; i < basis.size(); i++)
+            if ((v[prow[i] >> 6] >> (prow[i] & 63)) & 1) for (int w = 0; w < W; w++) v[w] ^= basis[i][w];
+        int pr = -1;
+        for (int w = 0; w < W && pr < 0; w++) if (v[w]) pr = w * 64 + __builtin_ctzll(v[w]);
+        if (pr >= 0) { basis.push_back(v); prow.push_back(pr); }
+    }
+    return (int)basis.size();
+}
+
+static int setup_kernels(swd_decoder *d);
+static int alloc_workspace(swd_decoder *d, long long want_cap);
+
+extern "C" int swd_create(const swd_config *cfg, int m, int n, const int32_t *colptr, const int32_t *rowidx,
+                          const double *channel_llr, swd_decoder **out) {
+    if (!cfg || !colptr || !rowidx || !channel_llr || !out || m <= 0 || n <= 0) { set_err("swd_create: null/empty argument"); return SWD_ERR_INVALID; }
+    if (cfg->kind < 0 || cfg->kind > 2) { set_err("swd_create: bad kind"); return SWD_ERR_INVALID; }
+    const int nnz = colptr[n];
+    if (colptr[0] != 0 || nnz < 0) { set_err("swd_create: bad colptr"); return SWD_ERR_INVALID; }
+    if (n > 65534 || m > 65534 || nnz > 65535) { set_err("swd_create: graph too large for 16-bit indices"); return SWD_ERR_UNSUPPORTED; }
+    swd_decoder *d = new swd_decoder();
+    d->cfg = *cfg; d->m = m; d->n = n; d->nnz = nnz; d->device = cfg->device;
+    // ---- flat graph: CSC with ascending rows, CSR with ascending columns (mod2sparse.c:358-432)
+    std::vector<int> cp(colptr, colptr + n + 1), cr(nnz), rp(m + 1, 0), rc(nnz), cpos(nnz);
+    for (int c = 0; c < n; c++) {
+        if (cp[c + 1] < cp[c]) { delete d; set_err("swd_create: colptr not monotone"); return SWD_ERR_INVALID; }
+        std::vector<int> rows(rowidx + cp[c], rowidx + cp[c + 1]);
+        std::sort(rows.begin(), rows.end());
+        for (size_t k = 0; k < rows.size(); k++) {
+            if (rows[k] < 0 || rows[k] >= m || (k && rows[k] == rows[k - 1])) { delete d; set_err("swd_create: bad row index"); return SWD_ERR_INVALID; }
+            cr[cp[c] + k] = rows[k]; rp[rows[k] + 1]++;
+        }
+        d->max_col_deg = std::max(d->max_col_deg, (int)rows.size());
+    }
+    for (int r = 0; r < m; r++) { d->max_row_deg = std::max(d->max_row_deg, rp[r + 1]); rp[r + 1] += rp[r]; }
+    {
+        std::vector<int> fill(rp.begin(), rp.end() - 1);
+        for (int c = 0; c < n; c++) for (int e = cp[c]; e < cp[c + 1]; e++) { int p = fill[cr[e]]++; rc[p] = c; cpos[e] = p; }
+    }
+    if (d->max_col_deg > 16) { delete d; set_err("swd_create: column weight > 16 unsupported"); return SWD_ERR_UNSUPPORTED; }
+    if (d->max_row_deg > 255) { delete d; set_err("swd_create: row weight > 255 unsupported"); return SWD_ERR_UNSUPPORTED; }
+    d->dmax = d->max_col_deg <= 8 ? 8 : 16;
+    d->nn = (cfg->new_n <= 0) ? std::min(n, 2 * m) : std::min(cfg->new_n, n);
+    {   // worst-case edge count of a shortened graph: the nn heaviest columns
+        std::vector<int> deg(n);
+        for (int c = 0; c < n; c++) deg[c] = cp[c + 1] - cp[c];
+        std::sort(deg.begin(), deg.end(), std::greater<int>());
+        long long s = 0; for (int j = 0; j < d->nn; j++) s += deg[j];
+        d->es_max = (int)s;
+    }
+    if (cfg->kind == SWD_KIND_OSD_WINDOW) {
+        d->rank = host_rank(m, n, cp, cr);
+        int method = cfg->osd_method, order = cfg->osd_order;
+        if (method == SWD_OSD_0) order = 0;
+        if (order < 0 || order > d->nn - d->rank) {          // osd_window.pyx:88-92
+            delete d; set_err("swd_create: osd_order out of range 0..new_n-rank"); return SWD_ERR_INVALID;
+        }
+        if (method == SWD_OSD_E && order > 20) { delete d; set_err("swd_create: osd_e order > 20 unsupported"); return SWD_ERR_UNSUPPORTED; }
+        d->cfg.osd_order = order;
+    }
+    if (cudaSetDevice(d->device) != cudaSuccess) { delete d; set_err("cudaSetDevice failed"); return SWD_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, d->device) != cudaSuccess) { delete d; set_err("cudaGetDeviceProperties failed"); return SWD_ERR_CUDA; }
+    d->num_sm = prop.multiProcessorCount;
+    std::vector<u16> cr16(cr.begin(), cr.end()), rc16(rc.begin(), rc.end()), cpos16(cpos.begin(), cpos.end());
+    std::vector<double> llr(channel_llr, channel_llr + n);
+    int st;
+    if ((st = upload(rp, &d->d_graph[0])) || (st = upload(rc16, &d->d_graph[1])) || (st = upload(cp, &d->d_graph[2])) ||
+        (st = upload(cr16, &d->d_graph[3])) || (st = upload(cpos16, &d->d_graph[4])) || (st = upload(llr, &d->d_graph[5]))) {
+        swd_destroy(d); return st;
+    }
+    d->g.m = m; d->g.n = n; d->g.nnz = nnz;
+    d->g.rp = (const int *)d->d_graph[0]; d->g.rc = (const u16 *)d->d_graph[1]; d->g.cp = (const int *)d->d_graph[2];
+    d->g.cr = (const u16 *)d->d_graph[3]; d->g.cpos = (const u16 *)d->d_graph[4]; d->g.llr = (const double *)d->d_graph[5];
+    if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) { swd_destroy(d); set_err("stream create failed"); return SWD_ERR_CUDA; }
+    if ((st = setup_kernels(d)) != SWD_OK) { swd_destroy(d); return st; }
+    *out = d;
+    return SWD_OK;
+}
+
+extern "C" void swd_destroy(swd_decoder *d) {
+    if (!d) return;
+    cudaSetDevice(d->device);
+    for (auto &p : d->d_graph) if (p) cudaFree(p);
+    if (d->ws_block) cudaFree(d->ws_block);
+    if (d->hscratch) cudaFree(d->hscratch);
+    if (d->d_synd) cudaFree(d->d_synd);
+    if (d->d_corr) cudaFree(d->d_corr);
+    if (d->d_conv) cudaFree(d->d_conv);
+    if (d->d_pm) cudaFree(d->d_pm);
+    if (d->h_pin) cudaFreeHost(d->h_pin);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+}
+
+template <typename K>
+static int occupancy(K kernel, int threads, size_t smem, int *out) {
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem));
+    *out = nb;
+    return SWD_OK;
+}
+
+static int setup_kernels(swd_decoder *d) {
+    const int m = d->m, n = d->n, nn = d->nn, es = std::max(d->es_max, 1);
+    const swd_config &c = d->cfg;
+    // ---- GDG parameters
+    GdgDev &P = d->P;
+    P.kind = c.kind; P.multi_thread = c.multi_thread; P.low_error = (c.kind == SWD_KIND_BPGD) ? 0 : c.low_error_mode;
+    P.num_iter = c.max_iter_per_step; P.max_step = c.max_step; P.T = c.max_tree_depth; P.S = c.max_side_depth;
+    P.tree_step = c.max_tree_branch_step; P.side_step = c.max_side_branch_step; P.factor = c.gdg_factor;
+    P.post_max_iter = c.post_max_iter;
+    if (c.kind == SWD_KIND_BPGDG && c.multi_thread) {
+        if (P.T < 0 || P.T > 10) { set_err("max_tree_depth out of range"); return SWD_ERR_UNSUPPORTED; }
+        P.n_tree = (1 << P.T) - 1; P.n_side = std::max(0, P.S - P.T); P.n_rec = 1 + P.n_tree + P.n_side;
+    } else { P.n_tree = 0; P.n_side = 0; P.n_rec = 1; }
+    if (c.kind == SWD_KIND_OSD_WINDOW) { P.factor = c.ms_scaling_factor; P.low_error = 0; }
+    P.rec_stride = r16((int)sizeof(RecHeader) + 4 * ((nn + 31) / 32));
+    P.side_stride = r16((int)sizeof(SideHeader) + nn + 2 * m);
+    // ---- blob layout
+    SubLayout &L = d->L;
+    L.nn = nn; L.m = m; L.es_max = es;
+    int o = 16;
+    L.off_prior = o; o += 8 * nn; o = r16(o);
+    L.off_col = o; o += 2 * nn; o = r16(o);
+    L.off_voff = o; o += 2 * (nn + 1); o = r16(o);
+    L.off_coff = o; o += 2 * (m + 1); o = r16(o);
+    L.off_synd = o; o += m; o = r16(o);
+    L.off_vnmask = o; o += nn; o = r16(o);
+    L.off_cnmask = o; o += m; o = r16(o);
+    L.off_cndeg = o; o += m; o = r16(o);
+    L.fixed_bytes = o;
+    L.off_vrow = o; o += r16(2 * es);
+    L.off_vpos = o; o += r16(2 * es);
+    L.off_cvn = o; o += r16(2 * es);
+    L.blob_bytes = o;
+    // ---- K1
+    d->T1 = std::min(256, std::max(64, r32up((n + 3) / 4)));
+    if (const char *e = getenv("SWD_T1")) d->T1 = atoi(e);
+    PreSmem &S1 = d->PRE;
+    o = 0; S1.off_msg = o; o += 8 * std::max(d->nnz, 1); o = r16(o);
+    S1.off_upar = o; o += 4 * m; o = r16(o);
+    S1.off_synd = o; o += m; o = r16(o);
+    S1.off_dec = o; o += n; o = r16(o);
+    S1.off_misc = o; o += 64; S1.total = o;
+    if (S1.total > 227 * 1024) { set_err("window graph does not fit in shared memory (nnz too large)"); return SWD_ERR_UNSUPPORTED; }
+    int occ = 0, st;
+    if (d->dmax == 8) st = occupancy(pre_bp_kernel<8>, d->T1, S1.total, &occ); else st = occupancy(pre_bp_kernel<16>, d->T1, S1.total, &occ);
+    if (st) return st;
+    if (occ < 1) { set_err("pre_bp_kernel does not fit"); return SWD_ERR_UNSUPPORTED; }
+    d->grid1 = d->num_sm * occ;
+    // ---- K2
+    SortSmem &S2 = d->SS;
+    int np2 = 64; while (np2 < n) np2 <<= 1;
+    S2.np2 = np2;
+    d->T2 = std::min(1024, std::max(128, np2 / 8));
+    o = 0; S2.off_key = o; o += 8 * np2; S2.off_idx = o; o += 2 * np2; o = r16(o);
+    S2.off_posof = o; o += 2 * n; o = r16(o);
+    S2.off_blob = o; o += L.blob_bytes;
+    S2.off_u32a = o; o += 4 * (nn + 1); o = r16(o);
+    S2.off_u32b = o; o += 4 * (m + 1); o = r16(o);
+    S2.off_wt = o; o += 4 * 64;
+    S2.off_error = o; o += nn; o = r16(o);
+    S2.off_misc = o; o += 64; S2.total = o;
+    if (S2.total > 227 * 1024) { set_err("sort/reset kernel does not fit in shared memory"); return SWD_ERR_UNSUPPORTED; }
+    if ((st = occupancy(sort_reset_kernel, d->T2, S2.total, &occ))) return st;
+    if (occ < 1) { set_err("sort_reset_kernel does not fit"); return SWD_ERR_UNSUPPORTED; }
+    d->grid2 = d->num_sm * occ;
+    // ---- K3
+    d->T3 = std::max(32, std::max(r32up((nn + 3) / 4), r32up((m + SWD_CPT - 1) / SWD_CPT)));
+    if (d->T3 > 1024) { set_err("new_n > 4096 unsupported"); return SWD_ERR_UNSUPPORTED; }
+    PathSmem &S3 = d->PS;
+    o = 0; S3.off_msg = o; o += 8 * es; o = r16(o);
+    S3.off_vnmask = o; o += nn; o = r16(o);
+    S3.off_error = o; o += nn; o = r16(o);
+    S3.off_dec = o; o += nn; o = r16(o);
+    S3.off_cnmask = o; o += m; o = r16(o);
+    S3.off_cndeg = o; o += m; o = r16(o);
+    S3.off_flip = o; o += m; o = r16(o);
+    S3.off_upar = o; o += 4 * m; o = r16(o);
+    S3.off_bvn = o; o += nn; o = r16(o);
+    S3.off_bcn = o; o += m; o = r16(o);
+    S3.off_bdeg = o; o += m; o = r16(o);
+    S3.off_red = o; o += 64 * 8 + 64 * 4; o = r16(o);
+    S3.off_misc = o; o += 64;
+    S3.off_bar = o; o += 16;
+    S3.total = o;
+    const size_t smem3 = (size_t)L.blob_bytes + S3.total;
+    if (smem3 > 227 * 1024) { set_err("shortened graph does not fit in shared memory"); return SWD_ERR_UNSUPPORTED; }
+    d->path_fn = pick_path_kernel(d->dmax, d->T3);
+    if ((st = occupancy(d->path_fn, d->T3, smem3, &occ))) return st;
+    if (occ < 1) { set_err("path_kernel does not fit"); return SWD_ERR_UNSUPPORTED; }
+    d->grid3 = d->num_sm * occ;
+    // ---- K5 (OSD)
+    if (c.kind == SWD_KIND_OSD_WINDOW) {
+        if ((st = osd_setup(d->m, d->n, d->nn, d->rank, d->cfg.osd_method, d->cfg.osd_order, d->num_sm, &d->OS, &d->T5, &d->grid5))) {
+            set_err("osd kernel does not fit in shared memory"); return st;
+        }
+    }
+    return SWD_OK;
+}
+
+static int alloc_workspace(swd_decoder *d, long long want) {
+    if (want <= d->cap) return SWD_OK;
+    CK(cudaSetDevice(d->device));
+    size_t budget = (size_t)8 << 30;
+    if (const char *e = getenv("SWD_WS_BYTES")) budget = (size_t)atoll(e);
+    const int n = d->n;
+    const bool osd = d->cfg.kind == SWD_KIND_OSD_WINDOW;
+    size_t per = (size_t)n * 8 + d->L.blob_bytes + (size_t)d->P.n_rec * d->P.rec_stride + (size_t)d->P.n_side * d->P.side_stride + 4 + 64;
+    if (osd) per += (size_t)n * 32 + osd_bytes_per_shot(d->m, n);
+    long long cap = std::max<long long>(1, std::min<long long>(want, (long long)(budget / per)));
+    if (cap <= d->cap) return SWD_OK;
+    if (d->ws_block) { cudaFree(d->ws_block); d->ws_block = nullptr; d->cap = 0; }
+    auto a256 = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t o = 0;
+    size_t o_cnt = o; o += a256(64 * sizeof(int));
+    size_t o_stats = o; o += a256(16 * sizeof(u64));
+    size_t o_list = o; o += a256((size_t)cap * 4);
+    size_t o_sum = o; o += a256((size_t)cap * n * 8);
+    size_t o_hist = o; if (osd) o += a256((size_t)cap * n * 32);
+    size_t o_blob = o; o += a256((size_t)cap * d->L.blob_bytes);
+    size_t o_rec = o; o += a256((size_t)cap * d->P.n_rec * d->P.rec_stride);
+    size_t o_side = o; o += a256((size_t)cap * std::max(1, d->P.n_side) * d->P.side_stride);
+    size_t o_osd = o; if (osd) o += a256((size_t)cap * osd_bytes_per_shot(d->m, n));
+    cudaError_t e = cudaMalloc(&d->ws_block, o);
+    if (e != cudaSuccess) { set_err("workspace cudaMalloc failed"); return SWD_ERR_NOMEM; }
+    CK(cudaMemset(d->ws_block, 0, o_list));
+    unsigned char *b = (unsigned char *)d->ws_block;
+    d->ws.counters = (int *)(b + o_cnt); d->ws.stats = (u64 *)(b + o_stats); d->ws.gdg_list = (int *)(b + o_list);
+    d->ws.sum = (double *)(b + o_sum); d->ws.hist = osd ? (double *)(b + o_hist) : nullptr;
+    d->ws.blob = b + o_blob; d->ws.rec = b + o_rec; d->ws.side = b + o_side;
+    if (osd) osd_bind(&d->ow, b + o_osd, cap, d->m, n);
+    if (!d->hscratch) CK(cudaMalloc(&d->hscratch, (size_t)d->grid1 * 4 * n * sizeof(double)));
+    d->cap = cap;
+    return SWD_OK;
+}
+
+static int pull_stats(swd_decoder *d, cudaStream_t s) {
+    u64 h[16];
+    CK(cudaMemcpyAsync(h, d->ws.stats, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    d->ctr.pre_bp_edge_iters = h[0]; d->ctr.path_edge_iters = h[1]; d->ctr.paths_run = h[2]; d->ctr.bp_calls = h[3];
+    d->ctr.osd_shots = h[4]; d->ctr.gdg_shots = h[5];
+    return SWD_OK;
+}
+
+// one chunk (B <= cap), everything asynchronous on `s`
+static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_corr, u8 *d_conv, double *d_pm, cudaStream_t s,
+                        long long chunk_base) {
+    const swd_config &c = d->cfg;
+    CK(cudaMemsetAsync(d->ws.counters, 0, 64 * sizeof(int), s));
+    const int g1 = (int)std::min<long long>(B, d->grid1);
+    const int full_hist = (c.kind == SWD_KIND_OSD_WINDOW) ? 1 : 0;
+    int *iter_out = (c.kind == SWD_KIND_OSD_WINDOW) ? d->ow.bp_iter + chunk_base : nullptr;
+    if (d->dmax == 8)
+        pre_bp_kernel<8><<<g1, d->T1, d->PRE.total, s>>>(d->g, d_synd, B, c.max_iter, c.ms_scaling_factor, d_corr, d_conv, d->ws,
+                                                        d->hscratch, full_hist, d->PRE, iter_out);
+    else
+        pre_bp_kernel<16><<<g1, d->T1, d->PRE.total, s>>>(d->g, d_synd, B, c.max_iter, c.ms_scaling_factor, d_corr, d_conv, d->ws,
+                                                         d->hscratch, full_hist, d->PRE, iter_out);
+    d->ctr.kernel_launches++;
+    if (d_pm) {
+        const double fillv = (c.kind == SWD_KIND_OSD_WINDOW) ? 0.0 : SWD_MAX_PM;
+        fill_pm_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(d_pm, B, fillv);
+        d->ctr.kernel_launches++;
+    }
+    if (c.kind == SWD_KIND_BPGD && c.max_iter <= -1) return SWD_OK;   // pyx:506
+    const int g2 = (int)std::min<long long>(B, d->grid2);
+    sort_reset_kernel<<<g2, d->T2, d->SS.total, s>>>(d->g, d_synd, d->ws, d->L, d->P, d->SS, d_corr);
+    d->ctr.kernel_launches++;
+    const size_t smem3 = (size_t)d->L.blob_bytes + d->PS.total;
+    const int g3 = d->grid3;
+    const int phases = (c.kind == SWD_KIND_BPGDG && c.multi_thread && d->P.n_side > 0) ? 2 : 1;
+    if (c.kind == SWD_KIND_OSD_WINDOW) {
+        int st = osd_launch(d->g, d_synd, d->ws, d->L, d->PS, d->P, d->OS, d->ow, d->dmax, d->T3, g3, smem3, d->T5, d->grid5,
+                            c.osd_method, c.osd_order, d->rank, d_corr, d_conv, d_pm, chunk_base, s, &d->ctr.kernel_launches);
+        if (st) { set_err("osd launch failed"); return st; }
+    } else {
+        for (int ph = 0; ph < phases; ph++) {
+            d->path_fn<<<g3, d->T3, smem3, s>>>(d->ws, d->L, d->PS, d->P, ph);
+            d->ctr.kernel_launches++;
+        }
+        select_kernel<<<std::max(1, std::min<int>((int)B, d->num_sm * 8)), 128, 0, s>>>(d->ws, d->L, d->P, d->n, d_corr, d_conv, d_pm);
+        d->ctr.kernel_launches++;
+    }
+    CK(cudaGetLastError());
+    return SWD_OK;
+}
+
+extern "C" int swd_decode_batch_device(swd_decoder *d, const uint8_t *d_synd, int64_t B, uint8_t *d_corr, uint8_t *d_conv,
+                                       double *d_pm, void *stream) {
+    if (!d || B < 0 || (B > 0 && (!d_synd || !d_corr || !d_conv))) { set_err("decode: null argument"); return SWD_ERR_INVALID; }
+    if (B == 0) return SWD_OK;
+    CK(cudaSetDevice(d->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int st = alloc_workspace(d, B);
+    if (st) return st;
+    if (d->cfg.kind == SWD_KIND_OSD_WINDOW) { st = osd_reserve_outputs(&d->ow, B, d->n); if (st) { set_err("osd output alloc failed"); return st; } }
+    for (long long b0 = 0; b0 < B; b0 += d->cap) {
+        const long long nb = std::min<long long>(d->cap, B - b0);
+        st = launch_chunk(d, d_synd + b0 * d->m, nb, d_corr + b0 * d->n, d_conv + b0, d_pm ? d_pm + b0 : nullptr, s, b0);
+        if (st) return st;
+        // fold the per-chunk GDG count into the running statistics (device side, no sync)
+        accumulate_count_kernel<<<1, 1, 0, s>>>(d->ws.counters, d->ws.stats);
+        d->ctr.kernel_launches++;
+    }
+    d->ctr.shots += (uint64_t)B;
+    d->last_B = B;
+    return SWD_OK;
+}
+
+extern "C" int swd_decode_batch_host(swd_decoder *d, const uint8_t *synd, int64_t B, uint8_t *corr, uint8_t *conv, double *pm) {
+    if (!d || B < 0 || (B > 0 && (!synd || !corr || !conv))) { set_err("decode: null argument"); return SWD_ERR_INVALID; }
+    if (B == 0) return SWD_OK;
+    CK(cudaSetDevice(d->device));
+    if (B > d->stage_cap) {
+        if (d->d_synd) { cudaFree(d->d_synd); cudaFree(d->d_corr); cudaFree(d->d_conv); cudaFree(d->d_pm); d->d_synd = nullptr; }
+        CK(cudaMalloc(&d->d_synd, (size_t)B * d->m));
+        CK(cudaMalloc(&d->d_corr, (size_t)B * d->n));
+        CK(cudaMalloc(&d->d_conv, (size_t)B));
+        CK(cudaMalloc(&d->d_pm, (size_t)B * 8));
+        d->stage_cap = B;
+    }
+    cudaStream_t s = d->stream;
+    CK(cudaMemcpyAsync(d->d_synd, synd, (size_t)B * d->m, cudaMemcpyHostToDevice, s));
+    int st = swd_decode_batch_device(d, d->d_synd, B, d->d_corr, d->d_conv, d->d_pm, s);
+    if (st) return st;
+    CK(cudaMemcpyAsync(corr, d->d_corr, (size_t)B * d->n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(conv, d->d_conv, (size_t)B, cudaMemcpyDeviceToHost, s));
+    if (pm) CK(cudaMemcpyAsync(pm, d->d_pm, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SWD_OK;
+}
+
+extern "C" int swd_osd_last_outputs(swd_decoder *d, int64_t B, uint8_t *bp_dec, uint8_t *osd0, uint8_t *osdw,
+                                    double *lpr, int32_t *bp_iteration) {
+    if (!d || d->cfg.kind != SWD_KIND_OSD_WINDOW) { set_err("not an osd_window decoder"); return SWD_ERR_INVALID; }
+    if (B > d->last_B) { set_err("B exceeds last batch"); return SWD_ERR_INVALID; }
+    CK(cudaSetDevice(d->device));
+    CK(cudaDeviceSynchronize());
+    const size_t n = d->n;
+    if (bp_dec) CK(cudaMemcpy(bp_dec, d->ow.bp_dec, (size_t)B * n, cudaMemcpyDeviceToHost));
+    if (osd0) CK(cudaMemcpy(osd0, d->ow.osd0, (size_t)B * n, cudaMemcpyDeviceToHost));
+    if (osdw) CK(cudaMemcpy(osdw, d->ow.osdw, (size_t)B * n, cudaMemcpyDeviceToHost));
+    if (lpr) CK(cudaMemcpy(lpr, d->ow.lpr, (size_t)B * n * 32, cudaMemcpyDeviceToHost));
+    if (bp_iteration) CK(cudaMemcpy(bp_iteration, d->ow.bp_iter, (size_t)B * 4, cudaMemcpyDeviceToHost));
+    return SWD_OK;
+}
+
+extern "C" int swd_get_counters(swd_decoder *d, swd_counters *out) {
+    if (!d || !out) return SWD_ERR_INVALID;
+    CK(cudaSetDevice(d->device));
+    if (d->ws.stats) { CK(cudaDeviceSynchronize()); int st = pull_stats(d, d->stream); if (st) return st; }
+    *out = d->ctr;
+    return SWD_OK;
+}
+extern "C" int swd_reset_counters(swd_decoder *d) {
+    if (!d) return SWD_ERR_INVALID;
+    CK(cudaSetDevice(d->device));
+    memset(&d->ctr, 0, sizeof(d->ctr));
+    if (d->ws.stats) { CK(cudaDeviceSynchronize()); CK(cudaMemset(d->ws.stats, 0, 16 * sizeof(u64))); }
+    return SWD_OK;
+}
+extern "C" int swd_rank(swd_decoder *d) { return d ? d->rank : -1; }
+extern "C" int swd_new_n(swd_decoder *d) { return d ? d->nn : -1; }
+
+// ------------------------------------------------------------------------------------------------
+// sliding-window bookkeeping
+// ------------------------------------------------------------------------------------------------
+struct swd_window {
+    int device, num_det, num_col, num_obs;
+    int *chk_cp = nullptr, *chk_ri = nullptr, *obs_cp = nullptr, *obs_ri = nullptr;
+};
+
+extern "C" int swd_window_create(int device, int num_det, int num_col, const int32_t *chk_cp, const int32_t *chk_ri, int num_obs,
+                                 const int32_t *obs_cp, const int32_t *obs_ri, swd_window **out) {
+    if (!chk_cp || !chk_ri || !out || num_det <= 0 || num_col <= 0 || num_obs < 0 || (num_obs > 0 && (!obs_cp || !obs_ri))) {
+        set_err("swd_window_create: bad argument"); return SWD_ERR_INVALID;
+    }
+    CK(cudaSetDevice(device));
+    swd_window *w = new swd_window();
+    w->device = device; w->num_det = num_det; w->num_col = num_col; w->num_obs = num_obs;
+    std::vector<int> a(chk_cp, chk_cp + num_col + 1), b(chk_ri, chk_ri + chk_cp[num_col]);
+    int st;
+    if ((st = upload(a, (void **)&w->chk_cp)) || (st = upload(b, (void **)&w->chk_ri))) { swd_window_destroy(w); return st; }
+    if (num_obs > 0) {
+        std::vector<int> c(obs_cp, obs_cp + num_col + 1), e(obs_ri, obs_ri + obs_cp[num_col]);
+        if ((st = upload(c, (void **)&w->obs_cp)) || (st = upload(e, (void **)&w->obs_ri))) { swd_window_destroy(w); return st; }
+    }
+    *out = w;
+    return SWD_OK;
+}
+extern "C" void swd_window_destroy(swd_window *w) {
+    if (!w) return;
+    cudaSetDevice(w->device);
+    if (w->chk_cp) cudaFree(w->chk_cp);
+    if (w->chk_ri) cudaFree(w->chk_ri);
+    if (w->obs_cp) cudaFree(w->obs_cp);
+    if (w->obs_ri) cudaFree(w->obs_ri);
+    delete w;
+}
+extern "C" int swd_window_extract(swd_window *w, const uint8_t *d_det, int64_t B, int row0, int m, uint8_t *d_synd, void *stream) {
+    if (!w || !d_det || !d_synd || B < 0 || row0 < 0 || m <= 0 || row0 + m > w->num_det) { set_err("swd_window_extract: bad argument"); return SWD_ERR_INVALID; }
+    if (B == 0) return SWD_OK;
+    CK(cudaSetDevice(w->device));
+    const long long total = (long long)B * m;
+    window_extract_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 1 << 20), 256, 0, (cudaStream_t)stream>>>(
+        d_det, B, w->num_det, row0, m, d_synd);
+    CK(cudaGetLastError());
+    return SWD_OK;
+}
+extern "C" int swd_window_commit(swd_window *w, const uint8_t *d_corr, int64_t B, int n_win, int col0, int ncommit, uint8_t *d_det,
+                                 uint8_t *d_obs, void *stream) {
+    if (!w || !d_corr || !d_det || B < 0 || col0 < 0 || ncommit < 0 || ncommit > n_win || col0 + ncommit > w->num_col) {
+        set_err("swd_window_commit: bad argument"); return SWD_ERR_INVALID;
+    }
+    if (B == 0 || ncommit == 0) return SWD_OK;
+    CK(cudaSetDevice(w->device));
+    const int wpb = 8;
+    window_commit_kernel<<<(unsigned)std::min<long long>((B + wpb - 1) / wpb, 1 << 20), wpb * 32, 0, (cudaStream_t)stream>>>(
+        d_corr, B, n_win, col0, ncommit, w->chk_cp, w->chk_ri, w->num_det, d_det, w->obs_cp, w->obs_ri, w->num_obs, d_obs);
+    CK(cudaGetLastError());
+    return SWD_OK;
+}
+extern "C" int swd_window_count_failures(swd_window *w, const uint8_t *d_det, const uint8_t *d_obs, int64_t B,
+                                         unsigned long long *d_out2, void *stream) {
+    if (!w || !d_det || !d_out2 || B < 0) { set_err("swd_window_count_failures: bad argument"); return SWD_ERR_INVALID; }
+    CK(cudaSetDevice(w->device));
+    CK(cudaMemsetAsync(d_out2, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream));
+    if (B == 0) return SWD_OK;
+    const int wpb = 8;
+    window_count_kernel<<<(unsigned)std::min<long long>((B + wpb - 1) / wpb, 1 << 20), wpb * 32, 0, (cudaStream_t)stream>>>(
+        d_det, w->num_det, d_obs, w->num_obs, B, d_out2);
+    CK(cudaGetLastError());
+    return SWD_OK;
+}

@@ -1,0 +1,482 @@
+// swd_device.cuh — device-side building blocks of the B200 window decoder.
+//
+// Semantics follow the reference's BPGD class (src/include/bpgd.cpp) but none of its
+// structure: the Tanner graph is flat CSR/CSC, a branch path is executed by one CTA,
+// messages live in ONE shared-memory array that alternately holds bit-to-check and
+// check-to-bit values, decided variables are marked by a NaN in their message slots,
+// and the posterior history ring lives in registers of the thread that owns the VN.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef uint16_t u16;
+typedef uint8_t  u8;
+typedef int8_t   i8;
+typedef uint32_t u32;
+typedef unsigned long long u64;
+
+#define SWD_BIG     1e308       /* empty-min sentinel, bpgd.cpp:106 */
+#define SWD_CLIP    50.0        /* bpgd.cpp:120-121 */
+#define SWD_MAX_PM  10000.0     /* bpgd.cpp:11 */
+#define FULLMASK    0xffffffffu
+#define SWD_CPT     4           /* checks owned per thread in path kernels: m <= SWD_CPT * blockDim */
+
+// ----------------------------------------------------------------------------------------------
+// layouts (byte offsets), computed once on the host
+// ----------------------------------------------------------------------------------------------
+struct SubLayout {              // per-slot "sub-graph blob": shortened graph + reset snapshot
+    int nn, m, es_max;
+    int off_prior;              // double[nn]
+    int off_col;                // u16[nn]     original column of sub-VN j (sorted order)
+    int off_voff;               // u16[nn+1]
+    int off_coff;               // u16[m+1]
+    int off_synd;               // u8[m]
+    int off_vnmask;             // i8[nn]      state after reset (bpgd.cpp:199-239)
+    int off_cnmask;             // i8[m]
+    int off_cndeg;              // u8[m]
+    int fixed_bytes;            // multiple of 16: header + all of the above
+    int off_vrow, off_vpos, off_cvn;   // u16[es_max] each, 16-byte aligned
+    int blob_bytes;             // multiple of 16
+};
+struct BlobHeader { int es; int status; int bad_rows; int shot; };   // 16 bytes at offset 0
+
+struct PathSmem {               // dynamic shared memory of path_kernel, offsets after the blob image
+    int off_msg;                // double[es_max]
+    int off_vnmask, off_error, off_dec;       // i8[nn]
+    int off_cnmask;             // i8[m]
+    int off_cndeg, off_flip;    // u8[m]
+    int off_upar;               // u32[m]
+    int off_bvn, off_bcn, off_bdeg;           // backup snapshot (tree paths)
+    int off_red;                // reduction scratch: 64 doubles + 64 ints
+    int off_misc;               // ints: broadcast slots
+    int off_bar;                // mbarrier (8 bytes)
+    int total;
+};
+
+struct GraphDev {               // static window graph (device pointers)
+    int m, n, nnz;
+    const int *rp;              // [m+1]  CSR row pointer
+    const u16 *rc;              // [nnz]  CSR column index
+    const int *cp;              // [n+1]  CSC column pointer
+    const u16 *cr;              // [nnz]  CSC row index (ascending)
+    const u16 *cpos;            // [nnz]  CSC entry -> CSR position
+    const double *llr;          // [n]
+};
+
+struct GdgDev {                 // parameters of the decimation tree
+    int num_iter, max_step, T, S, tree_step, side_step, low_error, n_tree, n_side, n_rec;
+    double factor;
+    int rec_stride;             // bytes per result record
+    int side_stride;            // bytes per side snapshot
+    int kind;                   // SWD_KIND_*
+    int multi_thread;
+    int post_max_iter;
+};
+
+struct Workspace {              // per-batch device buffers
+    int *counters;              // [0] gdg_count, [1..] tickets
+    int *gdg_list;              // [cap] shot id per slot
+    double *sum;                // [cap][n]      posterior-history sums (sort keys)
+    double *hist;               // [cap][n][4]   pre-BP history (osd_window only) or NULL
+    u8 *blob;                   // [cap][blob_bytes]
+    u8 *rec;                    // [cap][n_rec][rec_stride]
+    u8 *side;                   // [cap][n_side][side_stride]
+    u64 *stats;                 // device counters: [0] pre edge-iters [1] path edge-iters [2] paths [3] bp calls [4] osd shots
+};
+
+// ----------------------------------------------------------------------------------------------
+// small helpers
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u64 *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 phase) {
+    u32 ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// TMA 1-D bulk copy global -> shared (SASS: UBLKCP); dst/src 16-byte aligned, bytes % 16 == 0
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ double dnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// lexicographic (value, index) minimum across the CTA. Result broadcast to all threads.
+// red_d[>=32], red_i[>=32] shared scratch.  Contains __syncthreads().
+__device__ __forceinline__ void block_argmin(double &v, int &idx, double *red_d, int *red_i) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(FULLMASK, v, o);
+        int oi = __shfl_xor_sync(FULLMASK, idx, o);
+        if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    __syncthreads();                    // scratch may still be read from a previous call
+    if (lane == 0) { red_d[wid] = v; red_i[wid] = idx; }
+    __syncthreads();
+    double bv = red_d[0]; int bi = red_i[0];
+    for (int w = 1; w < nw; w++) {
+        double ov = red_d[w]; int oi = red_i[w];
+        if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    v = bv; idx = bi;
+}
+
+// exclusive scan over a[0..L] in shared memory (L+1 entries; a[L] should be 0 on entry and
+// receives the total).  wt: >= 33 u32 of shared scratch.  Contains __syncthreads().
+__device__ __forceinline__ void block_excl_scan(u32 *a, int L1, u32 *wt) {
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = (T + 31) >> 5;
+    const int per = (L1 + T - 1) / T;
+    int s = tid * per, e = s + per; if (e > L1) e = L1; if (s > L1) s = L1;
+    u32 sum = 0;
+    for (int i = s; i < e; i++) sum += a[i];
+    u32 incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wt[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        u32 v = lane < nw ? wt[lane] : 0, iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(FULLMASK, iv, o); if (lane >= o) iv += t; }
+        wt[lane] = iv - v;
+    }
+    __syncthreads();
+    u32 base = wt[wid] + incl - sum;
+    for (int i = s; i < e; i++) { u32 t = a[i]; a[i] = base; base += t; }
+    __syncthreads();
+}
+
+// stable ascending argsort of (key, idx) pairs held in shared memory (bitonic network on NP2
+// elements; ties broken by idx, which makes it equal to std::stable_sort with operator<,
+// bpgd.cpp:384-389).  Contains __syncthreads().
+__device__ __forceinline__ void block_bitonic_sort(double *key, u16 *idx, int NP2) {
+    const int T = blockDim.x, tid = threadIdx.x;
+    for (int k = 2; k <= NP2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (NP2 >> 1); t += T) {
+                int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                int hi = lo | j;
+                bool asc = ((lo & k) == 0);
+                double a = key[lo], b = key[hi];
+                u16 ia = idx[lo], ib = idx[hi];
+                bool gt = (b < a) || (!(a < b) && ib < ia);      // (a,ia) > (b,ib)
+                if (gt == asc) { key[lo] = b; key[hi] = a; idx[lo] = ib; idx[hi] = ia; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// branch-path context (all pointers into shared memory)
+// ----------------------------------------------------------------------------------------------
+struct Ctx {
+    int m, nn, es;
+    int bad_rows;
+    double factor;
+    int low_error;
+    int A, A_sum, C, D;                 // bpgd.hpp:15 thresholds (ints)
+    double *msg;
+    const double *prior;
+    const u16 *voff, *vrow, *vpos, *coff, *cvn;
+    const u8 *synd;
+    i8 *vn_mask, *error, *cn_mask, *dec;
+    u8 *cn_deg, *flip;
+    u32 *upar;
+    double *red_d; int *red_i; int *misc;
+};
+
+// BPGD::vn_set_value (bpgd.cpp:51-80) executed by ONE warp; lane k handles the k-th check of vn.
+template <bool HASMSG>
+__device__ __forceinline__ int set_warp(Ctx &c, int vn, int val, int lane) {
+    int cur = c.vn_mask[vn];
+    if (cur >= 0) return (cur == val) ? 0 : -1;
+    __syncwarp();
+    if (lane == 0) { c.vn_mask[vn] = (i8)val; c.error[vn] = (i8)val; }
+    const int e0 = c.voff[vn], d = c.voff[vn + 1] - e0;
+    int fail = 0;
+    if (lane < d) {
+        const int r = c.vrow[e0 + lane];
+        if (HASMSG) c.msg[c.vpos[e0 + lane]] = dnan();
+        int cm = c.cn_mask[r], dg = c.cn_deg[r];
+        if (cm < 0 || dg == 0) fail = 1;
+        else {
+            dg -= 1;
+            if (val) cm ^= 1;
+            c.cn_deg[r] = (u8)dg;
+            if (dg == 0) { if (cm != 0) fail = 1; else cm = -1; }
+            c.cn_mask[r] = (i8)cm;
+        }
+    }
+    fail = __any_sync(FULLMASK, fail);
+    __syncwarp();
+    return fail ? -1 : 0;
+}
+
+// BPGD::peel (bpgd.cpp:13-49) executed by ONE warp in exactly the reference's sweep order:
+// ballots find the next degree<=1 active check at or after the sweep position.
+template <bool HASMSG>
+__device__ __forceinline__ int peel_warp(Ctx &c, int lane) {
+    for (;;) {
+        bool clean = true;
+        int cn = 0;
+        while (cn < c.m) {
+            int r = cn + lane;
+            bool cand = false;
+            if (r < c.m) cand = (c.cn_mask[r] >= 0) && (c.cn_deg[r] < 2);
+            u32 b = __ballot_sync(FULLMASK, cand);
+            if (!b) { cn += 32; continue; }
+            r = cn + __ffs(b) - 1;
+            if (c.cn_deg[r] == 0) {                 // bpgd.cpp:22-26
+                __syncwarp();
+                if (lane == 0) c.cn_mask[r] = -1;
+                __syncwarp();
+                cn = r + 1; continue;
+            }
+            clean = false;
+            const int p0 = c.coff[r], p1 = c.coff[r + 1];
+            int vn = -1;
+            for (int pb = p0; pb < p1 && vn < 0; pb += 32) {
+                int p = pb + lane, j = -1;
+                bool und = false;
+                if (p < p1) { j = c.cvn[p]; und = c.vn_mask[j] < 0; }
+                u32 ub = __ballot_sync(FULLMASK, und);
+                if (ub) vn = __shfl_sync(FULLMASK, j, __ffs(ub) - 1);
+            }
+            if (vn < 0) return -1;
+            const int val = c.cn_mask[r];
+            if (set_warp<HASMSG>(c, vn, val, lane) < 0) return -1;
+            cn = r + 1;
+        }
+        if (clean) return 0;
+    }
+}
+
+// BPGD::get_pm (bpgd.cpp:250-256): ordered fp64 sum over j ascending; every lane of the calling
+// warp computes the same value.
+__device__ __forceinline__ double pm_warp(const Ctx &c, int lane) {
+    double pm = 0.0;
+    for (int base = 0; base < c.nn; base += 32) {
+        int j = base + lane;
+        u32 b = __ballot_sync(FULLMASK, j < c.nn && c.error[j] != 0);
+        while (b) { int k = __ffs(b) - 1; pm += c.prior[base + k]; b &= b - 1; }
+    }
+    return pm;
+}
+
+// BPGD::init (bpgd.cpp:82-95) + NaN marking of decided VNs.  Whole CTA; caller syncs.
+template <int VPT>
+__device__ __forceinline__ void init_msgs(Ctx &c) {
+    const int T = blockDim.x, tid = threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < VPT; i++) {
+        const int j = tid + i * T;
+        if (j < c.nn) {
+            const int e0 = c.voff[j], e1 = c.voff[j + 1];
+            const double v = (c.vn_mask[j] < 0) ? c.prior[j] : dnan();
+            for (int e = e0; e < e1; e++) c.msg[c.vpos[e]] = v;
+        }
+    }
+}
+
+// BPGD::min_sum_log (bpgd.cpp:97-197) on the shortened graph, whole CTA.
+// h[i][s]: posterior history of VN (tid + i*T), slot s = iteration % 4.  Returns 1 on convergence.
+template <int VPT, int DMAX>
+__device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter, u64 &edge_iters) {
+    const int T = blockDim.x, tid = threadIdx.x;
+    const double fpos = c.factor, fneg = -c.factor;
+    for (int it = 0; it < num_iter; it++) {
+        // ---- check pass: min1/min2/argmin/parity, then overwrite b2c by c2b in place
+        for (int r = tid; r < c.m; r += T) {
+            c.upar[r] = 0;
+            const int cm = c.cn_mask[r];
+            if (cm < 0) continue;
+            const int p0 = c.coff[r], p1 = c.coff[r + 1];
+            double m1 = SWD_BIG, m2 = SWD_BIG; int arg = -1, par = cm;
+            for (int p = p0; p < p1; p++) {
+                const double b = c.msg[p];
+                if (b != b) continue;                       // decided VN
+                const double a = fmin(fabs(b), SWD_CLIP);
+                if (a < m1) { m2 = m1; m1 = a; arg = p; } else if (a < m2) m2 = a;
+                par ^= (b <= 0.0);
+            }
+            for (int p = p0; p < p1; p++) {
+                const double b = c.msg[p];
+                if (b != b) continue;
+                const double mag = (p == arg) ? m2 : m1;
+                c.msg[p] = mag * ((par ^ (int)(b <= 0.0)) ? fneg : fpos);
+            }
+        }
+        __syncthreads();
+        // ---- variable pass: ordered prefix / suffix sums (bpgd.cpp:151-182)
+#pragma unroll
+        for (int i = 0; i < VPT; i++) {
+            const int j = tid + i * T;
+            if (j < c.nn && c.vn_mask[j] < 0) {
+                const int e0 = c.voff[j], d = c.voff[j + 1] - e0;
+                double cc[DMAX], pre[DMAX]; int pp[DMAX];
+                double t = c.prior[j];
+#pragma unroll
+                for (int k = 0; k < DMAX; k++) if (k < d) { pp[k] = c.vpos[e0 + k]; cc[k] = c.msg[pp[k]]; }
+#pragma unroll
+                for (int k = 0; k < DMAX; k++) if (k < d) { pre[k] = t; t += cc[k]; }
+                switch (it & 3) { case 0: h[i][0] = t; break; case 1: h[i][1] = t; break; case 2: h[i][2] = t; break; default: h[i][3] = t; }
+                const int hard = (t <= 0.0);
+                c.error[j] = (i8)hard;
+                if (hard) for (int k = 0; k < d; k++) atomicXor(&c.upar[c.vrow[e0 + k]], 1u);
+                double s = 0.0;
+#pragma unroll
+                for (int k = DMAX - 1; k >= 0; k--) if (k < d) { c.msg[pp[k]] = pre[k] + s; s += cc[k]; }
+                edge_iters += d;
+            }
+        }
+        __syncthreads();
+        // ---- H*error == syndrome (bpgd.cpp:185-194): decided VNs are folded into cn_mask
+        int mism = c.bad_rows;
+        for (int r = tid; r < c.m; r += T) {
+            const int cm = c.cn_mask[r];
+            const int f = (cm < 0) ? 0 : (c.upar[r] != (u32)cm);
+            c.flip[r] = (u8)f;
+            mism |= f;
+        }
+        if (!__syncthreads_or(mism)) return 1;
+    }
+    return 0;
+}
+
+// BPGD::select_vn (bpgd.cpp:288-351), whole CTA.  Returns favor (0/1) or -1; guess = -1 if no
+// candidate.  The scan's aggressive decimations are classified in parallel (classification of a
+// VN never depends on earlier decimations of the same scan) and applied per check; a contradiction
+// is resolved to the first failing VN in scan order so that `error` matches the reference.
+template <int VPT>
+__device__ __forceinline__ int select_vn(Ctx &c, const double (&h)[VPT][4], int depth, int &guess) {
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double best = SWD_MAX_PM, bestn = SWD_MAX_PM; int bi = 0x7fffffff, bni = 0x7fffffff;
+    int any_dec = 0;
+    if (tid == 0) c.misc[0] = 0x7fffffff;                    // failpos
+#pragma unroll
+    for (int i = 0; i < VPT; i++) {
+        const int j = tid + i * T;
+        if (j < c.nn) {
+            int action = -1;
+            if (c.vn_mask[j] < 0) {
+                const int e0 = c.voff[j], d = c.voff[j + 1] - e0;
+                if (d > 2) {
+                    int nf = 0;
+                    for (int k = 0; k < d; k++) nf += c.flip[c.vrow[e0 + k]];
+                    bool geC = true, geD = true, leA = true, neg = true; double sum = 0.0;
+#pragma unroll
+                    for (int s = 0; s < 4; s++) {
+                        const double l = h[i][s]; sum += l;
+                        if (l < (double)c.C) geC = false;
+                        if (l < (double)c.D) geD = false;
+                        if (l > (double)c.A) leA = false;
+                        if (l > 0.0) neg = false;
+                    }
+                    if (!c.low_error && geC && depth < 4) action = 0;
+                    else if (!c.low_error && nf >= 3 && geD) action = 0;
+                    else if (!c.low_error && leA && sum < (double)c.A_sum) action = 1;
+                    else {
+                        if (sum < best) { best = sum; bi = j; }
+                        if (neg && sum < bestn) { bestn = sum; bni = j; }
+                    }
+                }
+            }
+            c.dec[j] = (i8)action;
+            any_dec |= (action >= 0);
+        }
+    }
+    any_dec = __syncthreads_or(any_dec);
+    if (any_dec) {
+        // per check: how many of its undecided VNs were decimated, with which parity, last scan index
+        int ndg[SWD_CPT], nmk[SWD_CPT];                      // SWD_CPT checks per thread (m <= SWD_CPT*T)
+#pragma unroll
+        for (int q = 0; q < SWD_CPT; q++) {
+            const int r = tid + q * T;
+            ndg[q] = -1; nmk[q] = 0;
+            if (r >= c.m) continue;
+            const int cm = c.cn_mask[r];
+            if (cm < 0) continue;
+            int cnt = 0, par = 0, last = -1;
+            for (int p = c.coff[r]; p < c.coff[r + 1]; p++) {
+                const int j = c.cvn[p];
+                const int a = c.dec[j];
+                if (a >= 0) { cnt++; par ^= a; last = max(last, j); }
+            }
+            if (cnt) {
+                const int nd = (int)c.cn_deg[r] - cnt, nm = cm ^ par;
+                if (nd == 0 && nm != 0) atomicMin(&c.misc[0], last);
+                ndg[q] = nd; nmk[q] = (nd == 0) ? -1 : nm;
+            }
+        }
+        __syncthreads();
+        const int failpos = c.misc[0];
+        if (failpos != 0x7fffffff) {                         // contradiction: branch is dead
+#pragma unroll
+            for (int i = 0; i < VPT; i++) {
+                const int j = tid + i * T;
+                if (j < c.nn && c.dec[j] >= 0 && j <= failpos) { c.vn_mask[j] = c.dec[j]; c.error[j] = c.dec[j]; }
+            }
+            __syncthreads();
+            guess = -1;
+            return -1;
+        }
+#pragma unroll
+        for (int q = 0; q < SWD_CPT; q++) {
+            const int r = tid + q * T;
+            if (r < c.m && ndg[q] >= 0) { c.cn_deg[r] = (u8)ndg[q]; c.cn_mask[r] = (i8)nmk[q]; }
+        }
+#pragma unroll
+        for (int i = 0; i < VPT; i++) {
+            const int j = tid + i * T;
+            if (j < c.nn && c.dec[j] >= 0) {
+                c.vn_mask[j] = c.dec[j]; c.error[j] = c.dec[j];
+                for (int e = c.voff[j]; e < c.voff[j + 1]; e++) c.msg[c.vpos[e]] = dnan();
+            }
+        }
+    }
+    block_argmin(best, bi, c.red_d, c.red_i);                // contains the barriers that publish the updates
+    block_argmin(bestn, bni, c.red_d, c.red_i);
+    if (wid == 0) {
+        int st = peel_warp<true>(c, lane);
+        if (lane == 0) c.misc[1] = st;
+    }
+    __syncthreads();
+    if (c.misc[1] < 0) { guess = -1; return -1; }
+    if (bni != 0x7fffffff) { guess = bni; return 1; }
+    guess = (bi == 0x7fffffff) ? -1 : bi;
+    return (best > 0.0) ? 0 : 1;
+}
+
+// vn_set_value(guess, value) followed by peel (bpgd.cpp:485-486, :665), whole CTA. 0 ok / -1.
+__device__ __forceinline__ int set_and_peel(Ctx &c, int vn, int val) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (wid == 0) {
+        int st = set_warp<true>(c, vn, val, lane);
+        if (st == 0) st = peel_warp<true>(c, lane);
+        if (lane == 0) c.misc[1] = st;
+    }
+    __syncthreads();
+    return c.misc[1];
+}

@@ -1,0 +1,499 @@
+// swd_kernels.cuh — the kernels of the GDG / GD / post-BP pipeline.
+//
+//   pre_bp_kernel      full-window min-sum (bp_guessing_decoder.pyx:48-139), one CTA per shot,
+//                      messages in shared memory, early exit, appends non-converged shots to the
+//                      GDG list together with their posterior-history sums
+//   sort_reset_kernel  index_sort (bpgd.cpp:384-389) + BPGD::reset (bpgd.cpp:199-239): builds the
+//                      shortened graph of one shot ("blob") and its post-reset state
+//   path_kernel        one CTA per (shot, branch path): main / tree(+backup) / side branches of
+//                      BPGD_main_thread::do_work (bpgd.cpp:435-688), bpgd_decoder.gd (pyx:517-560)
+//   select_kernel      min path-metric selection + scatter through `cols` (pyx:246-251)
+#pragma once
+#include "swd_device.cuh"
+
+#define SWD_KIND_BPGDG       0
+#define SWD_KIND_BPGD        1
+#define SWD_KIND_OSD_WINDOW  2
+
+// ----------------------------------------------------------------------------------------------
+// K1: full-window BP
+// ----------------------------------------------------------------------------------------------
+struct PreSmem { int off_msg, off_upar, off_synd, off_dec, off_misc, total; };
+
+template <int DMAX>
+__global__ void __launch_bounds__(512)
+pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter, double alpha,
+              u8 *__restrict__ dec_out, u8 *__restrict__ conv_out, Workspace ws, double *hscratch,
+              int full_hist, PreSmem S, int *iter_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double *msg = (double *)(smem + S.off_msg);
+    u32 *upar = (u32 *)(smem + S.off_upar);
+    u8 *s_synd = smem + S.off_synd;
+    u8 *s_dec = smem + S.off_dec;
+    int *misc = (int *)(smem + S.off_misc);
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int m = g.m, n = g.n;
+    double *hs = hscratch + (size_t)blockIdx.x * 4 * n;
+    const double fpos = alpha, fneg = -alpha;
+    u64 edge_iters = 0;
+
+    for (long long shot = blockIdx.x; shot < B; shot += gridDim.x) {
+        for (int r = tid; r < m; r += T) s_synd[r] = synd[shot * m + r];
+        for (int v = tid; v < n; v += T) {                    // pyx:55-60
+            const int e0 = g.cp[v], e1 = g.cp[v + 1];
+            const double l = g.llr[v];
+            for (int e = e0; e < e1; e++) msg[g.cpos[e]] = l;
+            s_dec[v] = 0;
+        }
+        __syncthreads();
+        int conv = 0, it = 0;
+        for (; it < max_iter; it++) {
+            for (int r = tid; r < m; r += T) {
+                upar[r] = 0;
+                const int p0 = g.rp[r], p1 = g.rp[r + 1];
+                double m1 = SWD_BIG, m2 = SWD_BIG; int arg = -1, par = s_synd[r];
+                for (int p = p0; p < p1; p++) {
+                    const double b = msg[p];
+                    const double a = fmin(fabs(b), SWD_CLIP);
+                    if (a < m1) { m2 = m1; m1 = a; arg = p; } else if (a < m2) m2 = a;
+                    par ^= (b <= 0.0);
+                }
+                for (int p = p0; p < p1; p++) {
+                    const double b = msg[p];
+                    const double mag = (p == arg) ? m2 : m1;
+                    msg[p] = mag * ((par ^ (int)(b <= 0.0)) ? fneg : fpos);
+                }
+            }
+            __syncthreads();
+            const bool keep = full_hist || (it >= max_iter - 4);
+            for (int v = tid; v < n; v += T) {
+                const int e0 = g.cp[v], d = g.cp[v + 1] - e0;
+                double cc[DMAX], pre[DMAX]; int pp[DMAX];
+                double t = g.llr[v];
+#pragma unroll
+                for (int k = 0; k < DMAX; k++) if (k < d) { pp[k] = g.cpos[e0 + k]; cc[k] = msg[pp[k]]; }
+#pragma unroll
+                for (int k = 0; k < DMAX; k++) if (k < d) { pre[k] = t; t += cc[k]; }
+                if (keep) hs[(size_t)(it & 3) * n + v] = t;
+                const int hard = (t <= 0.0);
+                s_dec[v] = (u8)hard;
+                if (hard) for (int k = 0; k < d; k++) atomicXor(&upar[g.cr[e0 + k]], 1u);
+                double s = 0.0;
+#pragma unroll
+                for (int k = DMAX - 1; k >= 0; k--) if (k < d) { msg[pp[k]] = pre[k] + s; s += cc[k]; }
+            }
+            edge_iters += 1;
+            __syncthreads();
+            int mism = 0;
+            for (int r = tid; r < m; r += T) mism |= (upar[r] != (u32)s_synd[r]);
+            if (!__syncthreads_or(mism)) { conv = 1; it++; break; }
+        }
+        for (int v = tid; v < n; v += T) dec_out[shot * n + v] = s_dec[v];
+        if (tid == 0) {
+            conv_out[shot] = (u8)conv;
+            if (iter_out) iter_out[shot] = it;
+            if (!conv) { int slot = atomicAdd(&ws.counters[0], 1); ws.gdg_list[slot] = (int)shot; misc[0] = slot; }
+        }
+        __syncthreads();
+        if (!conv) {
+            const int slot = misc[0];
+            for (int v = tid; v < n; v += T) {
+                double h4[4];
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    // slots never written in this call are 0 (fresh ring); with full_hist all executed
+                    // iterations were stored, otherwise only the last four.
+                    bool written = (s < max_iter);
+                    h4[s] = written ? hs[(size_t)s * n + v] : 0.0;
+                }
+                ws.sum[(size_t)slot * n + v] = ((h4[0] + h4[1]) + h4[2]) + h4[3];
+                if (ws.hist) {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) ws.hist[((size_t)slot * n + v) * 4 + s] = h4[s];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && edge_iters) atomicAdd(&ws.stats[0], edge_iters * (u64)g.nnz);
+}
+
+// ----------------------------------------------------------------------------------------------
+// K2: sort + reset
+// ----------------------------------------------------------------------------------------------
+struct SortSmem { int off_key, off_idx, off_posof, off_blob, off_u32a, off_u32b, off_wt, off_error, off_misc, total; int np2; };
+
+__global__ void __launch_bounds__(1024)
+sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayout L, GdgDev P, SortSmem S,
+                  u8 *__restrict__ dec_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double *key = (double *)(smem + S.off_key);
+    u16 *idx = (u16 *)(smem + S.off_idx);
+    u16 *posof = (u16 *)(smem + S.off_posof);
+    unsigned char *blob = smem + S.off_blob;
+    u32 *ua = (u32 *)(smem + S.off_u32a);         // [nn+1]
+    u32 *ub = (u32 *)(smem + S.off_u32b);         // [m+1]
+    u32 *wt = (u32 *)(smem + S.off_wt);
+    i8 *s_error = (i8 *)(smem + S.off_error);
+    int *misc = (int *)(smem + S.off_misc);
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int m = g.m, n = g.n, nn = L.nn, NP2 = S.np2;
+
+    BlobHeader *hdr = (BlobHeader *)blob;
+    double *prior = (double *)(blob + L.off_prior);
+    u16 *col = (u16 *)(blob + L.off_col);
+    u16 *voff = (u16 *)(blob + L.off_voff);
+    u16 *coff = (u16 *)(blob + L.off_coff);
+    u8 *s_synd = blob + L.off_synd;
+    i8 *vn_mask = (i8 *)(blob + L.off_vnmask);
+    i8 *cn_mask = (i8 *)(blob + L.off_cnmask);
+    u8 *cn_deg = blob + L.off_cndeg;
+    u16 *vrow = (u16 *)(blob + L.off_vrow);
+    u16 *vpos = (u16 *)(blob + L.off_vpos);
+    u16 *cvn = (u16 *)(blob + L.off_cvn);
+
+    const int count = ws.counters[0];
+    for (int slot = blockIdx.x; slot < count; slot += gridDim.x) {
+        const int shot = ws.gdg_list[slot];
+        const double inf = __longlong_as_double(0x7ff0000000000000LL);
+        for (int i = tid; i < NP2; i += T) {
+            key[i] = (i < n) ? ws.sum[(size_t)slot * n + i] : inf;
+            idx[i] = (i < n) ? (u16)i : (u16)0xffff;
+        }
+        __syncthreads();
+        block_bitonic_sort(key, idx, NP2);
+        for (int j = tid; j < n; j += T) posof[idx[j]] = (u16)j;
+        for (int j = tid; j < nn; j += T) {
+            const int c = idx[j];
+            col[j] = (u16)c; prior[j] = g.llr[c];
+            ua[j] = (u32)(g.cp[c + 1] - g.cp[c]);
+            vn_mask[j] = -1; s_error[j] = 0;
+        }
+        if (tid == 0) ua[nn] = 0;
+        __syncthreads();
+        block_excl_scan(ua, nn + 1, wt);
+        const int es = (int)ua[nn];
+        for (int j = tid; j <= nn; j += T) voff[j] = (u16)ua[j];
+        for (int j = tid; j < nn; j += T) {
+            const int c = col[j], e0 = g.cp[c], d = g.cp[c + 1] - e0, o = (int)ua[j];
+            for (int k = 0; k < d; k++) vrow[o + k] = g.cr[e0 + k];
+        }
+        for (int r = tid; r < m; r += T) {
+            int cnt = 0;
+            for (int q = g.rp[r]; q < g.rp[r + 1]; q++) cnt += (posof[g.rc[q]] < nn);
+            ub[r] = (u32)cnt;
+        }
+        if (tid == 0) ub[m] = 0;
+        __syncthreads();
+        block_excl_scan(ub, m + 1, wt);
+        int bad = 0;
+        for (int r = tid; r < m; r += T) {
+            int p = (int)ub[r];
+            const int d = (int)ub[r + 1] - p;
+            coff[r] = (u16)p;
+            for (int q = g.rp[r]; q < g.rp[r + 1]; q++) {
+                const int j = posof[g.rc[q]];
+                if (j < nn) {
+                    cvn[p] = (u16)j;
+                    for (int e = voff[j]; e < voff[j + 1]; e++) if (vrow[e] == r) vpos[e] = (u16)p;
+                    p++;
+                }
+            }
+            const int s = synd[(size_t)shot * m + r];
+            s_synd[r] = (u8)s;
+            cn_deg[r] = (u8)d;
+            cn_mask[r] = (d == 0) ? (i8)-1 : (i8)s;          // bpgd.cpp:210-217
+            bad |= (d == 0 && s);
+        }
+        if (tid == 0) { coff[m] = (u16)ub[m]; misc[0] = 0x7fffffff; }
+        bad = __syncthreads_or(bad);
+
+        int status = 0;
+        if (P.kind == SWD_KIND_OSD_WINDOW && bad) {
+            // osd_window.pyx:178-181: decimating the dropped columns in sorted order hits a check whose
+            // every VN is dropped while its syndrome bit is 1; failure at the last of them in scan order.
+            for (int r = tid; r < m; r += T) {
+                if (ub[r + 1] == ub[r] && s_synd[r]) {
+                    int last = -1;
+                    for (int q = g.rp[r]; q < g.rp[r + 1]; q++) last = max(last, (int)posof[g.rc[q]]);
+                    atomicMin(&misc[0], last);
+                }
+            }
+            __syncthreads();
+            const int failpos = misc[0];
+            for (int j = nn + tid; j <= failpos && j < n; j += T) dec_out[(size_t)shot * n + idx[j]] = 0;
+            status = -2;
+        } else {
+            for (int j = nn + tid; j < n; j += T) dec_out[(size_t)shot * n + idx[j]] = 0;   // pyx:250-251 / :270-271
+            Ctx c;
+            c.m = m; c.nn = nn; c.es = es; c.msg = nullptr; c.prior = prior; c.voff = voff; c.vrow = vrow; c.vpos = vpos;
+            c.coff = coff; c.cvn = cvn; c.synd = s_synd; c.vn_mask = vn_mask; c.error = s_error; c.cn_mask = cn_mask;
+            c.cn_deg = cn_deg;
+            if (wid == 0) {
+                int st = peel_warp<false>(c, lane);                                          // bpgd.cpp:236
+                if (lane == 0) misc[1] = st;
+            }
+            __syncthreads();
+            status = misc[1];
+            if (status < 0 && P.kind == SWD_KIND_OSD_WINDOW) {
+                // osd_window.pyx:184-186: bp_decoding keeps the values peeled so far
+                for (int j = tid; j < nn; j += T) if (vn_mask[j] >= 0) dec_out[(size_t)shot * n + col[j]] = (u8)vn_mask[j];
+            }
+        }
+        if (tid == 0) { hdr->es = es; hdr->status = status; hdr->bad_rows = bad; hdr->shot = shot; }
+        __syncthreads();
+        // publish the blob (16-byte vectors): fixed part + the three es-sized arrays
+        {
+            uint4 *dst = (uint4 *)(ws.blob + (size_t)slot * L.blob_bytes);
+            const uint4 *src = (const uint4 *)blob;
+            const int nfix = L.fixed_bytes >> 4, nvar = (es * 2 + 15) >> 4;
+            for (int i = tid; i < nfix; i += T) dst[i] = src[i];
+            for (int i = tid; i < nvar; i += T) {
+                dst[(L.off_vrow >> 4) + i] = src[(L.off_vrow >> 4) + i];
+                dst[(L.off_vpos >> 4) + i] = src[(L.off_vpos >> 4) + i];
+                dst[(L.off_cvn >> 4) + i] = src[(L.off_cvn >> 4) + i];
+            }
+        }
+        // clear result records and side snapshots' valid flags
+        {
+            u32 *rec = (u32 *)(ws.rec + (size_t)slot * P.n_rec * P.rec_stride);
+            for (int i = tid; i < (P.n_rec * P.rec_stride) >> 2; i += T) rec[i] = 0;
+            for (int j = tid; j < P.n_side; j += T) *(int *)(ws.side + ((size_t)slot * P.n_side + j) * P.side_stride) = 0;
+        }
+        __syncthreads();
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K3: branch paths
+// ----------------------------------------------------------------------------------------------
+struct RecHeader { double pm; int status; int pad; };          // 16 bytes, followed by error bit words
+struct SideHeader { int valid, vn, value, depth; };            // 16 bytes, followed by vn_mask, cn_mask, cn_deg
+
+// write (status, pm, error bits) of the current path
+__device__ __forceinline__ void record_result(Ctx &c, u8 *rec, int converged) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (wid == 0) {
+        double pm = converged ? pm_warp(c, lane) : SWD_MAX_PM;
+        if (lane == 0) { RecHeader *h = (RecHeader *)rec; h->pm = pm; h->status = converged ? 1 : 2; }
+    }
+    u32 *bits = (u32 *)(rec + sizeof(RecHeader));
+    const int nwords = (c.nn + 31) >> 5;
+    for (int w = wid; w < nwords; w += nw) {
+        const int j = w * 32 + lane;
+        u32 b = __ballot_sync(FULLMASK, j < c.nn && c.error[j] != 0);
+        if (lane == 0) bits[w] = b;
+    }
+}
+
+template <int VPT, int DMAX, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+path_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int phase) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
+    unsigned char *blob = smem;
+    unsigned char *st = smem + L.blob_bytes;
+    Ctx c;
+    c.m = L.m; c.nn = L.nn; c.factor = P.factor; c.low_error = P.low_error;
+    c.prior = (const double *)(blob + L.off_prior);
+    c.voff = (const u16 *)(blob + L.off_voff); c.coff = (const u16 *)(blob + L.off_coff);
+    c.vrow = (const u16 *)(blob + L.off_vrow); c.vpos = (const u16 *)(blob + L.off_vpos); c.cvn = (const u16 *)(blob + L.off_cvn);
+    c.synd = blob + L.off_synd;
+    c.msg = (double *)(st + S.off_msg);
+    c.vn_mask = (i8 *)(st + S.off_vnmask); c.error = (i8 *)(st + S.off_error); c.dec = (i8 *)(st + S.off_dec);
+    c.cn_mask = (i8 *)(st + S.off_cnmask); c.cn_deg = st + S.off_cndeg; c.flip = st + S.off_flip;
+    c.upar = (u32 *)(st + S.off_upar);
+    c.red_d = (double *)(st + S.off_red); c.red_i = (int *)(c.red_d + 64); c.misc = (int *)(st + S.off_misc);
+    i8 *bvn = (i8 *)(st + S.off_bvn); i8 *bcn = (i8 *)(st + S.off_bcn); u8 *bdeg = st + S.off_bdeg;
+    u64 *bar = (u64 *)(st + S.off_bar);
+    const i8 *snap_vn = (const i8 *)(blob + L.off_vnmask), *snap_cn = (const i8 *)(blob + L.off_cnmask);
+    const u8 *snap_deg = blob + L.off_cndeg;
+
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    u32 mphase = 0;
+    const int count = ws.counters[0];
+    const int npaths = (phase == 0) ? ((P.kind == SWD_KIND_BPGDG && P.multi_thread) ? 1 + P.n_tree : 1) : P.n_side;
+    const long long total = (long long)npaths * count;
+    u64 edge_iters = 0, bp_calls = 0, paths_run = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) c.misc[2] = atomicAdd(&ws.counters[1 + phase], 1);
+        __syncthreads();
+        const long long item = c.misc[2];
+        if (item >= total) break;
+        const int path = (int)(item / count), slot = (int)(item % count);
+        const unsigned char *gblob = ws.blob + (size_t)slot * L.blob_bytes;
+        const BlobHeader gh = *(const BlobHeader *)gblob;
+        if (gh.status != 0) continue;
+        const SideHeader *sh = nullptr;
+        if (phase == 1) {
+            sh = (const SideHeader *)(ws.side + ((size_t)slot * P.n_side + path) * P.side_stride);
+            if (!sh->valid) continue;
+        }
+        // ---- stage the shot's shortened graph into shared memory with TMA bulk copies
+        if (tid == 0) {
+            fence_proxy_async();
+            const u32 vb = (u32)((gh.es * 2 + 15) & ~15);
+            mbar_expect_tx(bar, (u32)L.fixed_bytes + 3 * vb);
+            bulk_g2s(blob, gblob, (u32)L.fixed_bytes, bar);
+            if (vb) {
+                bulk_g2s(blob + L.off_vrow, gblob + L.off_vrow, vb, bar);
+                bulk_g2s(blob + L.off_vpos, gblob + L.off_vpos, vb, bar);
+                bulk_g2s(blob + L.off_cvn, gblob + L.off_cvn, vb, bar);
+            }
+        }
+        mbar_wait(bar, mphase);
+        mphase ^= 1;
+        c.es = gh.es; c.bad_rows = gh.bad_rows;
+        c.C = 30; c.D = 3;
+
+        // ---- load the start state
+        if (phase == 0) {
+            for (int j = tid; j < c.nn; j += T) { const i8 v = snap_vn[j]; c.vn_mask[j] = v; c.error[j] = v < 0 ? 0 : v; }
+            for (int r = tid; r < c.m; r += T) { c.cn_mask[r] = snap_cn[r]; c.cn_deg[r] = snap_deg[r]; c.flip[r] = 0; }
+        } else {
+            const i8 *svn = (const i8 *)(sh + 1); const i8 *scn = svn + c.nn; const u8 *sdg = (const u8 *)(scn + c.m);
+            for (int j = tid; j < c.nn; j += T) { const i8 v = svn[j]; c.vn_mask[j] = v; c.error[j] = v; }   // bpgd.cpp:541
+            for (int r = tid; r < c.m; r += T) { c.cn_mask[r] = scn[r]; c.cn_deg[r] = sdg[r]; c.flip[r] = 0; }
+        }
+        __syncthreads();
+        init_msgs<VPT>(c);
+        double h[VPT][4];
+#pragma unroll
+        for (int i = 0; i < VPT; i++) { h[i][0] = 0.0; h[i][1] = 0.0; h[i][2] = 0.0; h[i][3] = 0.0; }
+        __syncthreads();
+        paths_run++;
+
+        u8 *recbase = ws.rec + (size_t)slot * P.n_rec * P.rec_stride;
+
+        // ---- one interpreter loop for every kind of branch, so that bp_run / select_vn /
+        //      set_and_peel are instantiated once (registers, code size)
+        enum { R_MAIN = 0, R_TREE = 1, R_SIDE = 2, R_GD = 3 };
+        int role, limit, depth = 0, pend_vn = -1, pend_val = 0;
+        u8 *rec = recbase;
+        if (P.kind == SWD_KIND_BPGD) { role = R_GD; limit = P.max_step; }
+        else if (phase == 1) {                                  // side branch j (bpgd.cpp:527-570)
+            role = R_SIDE; limit = P.side_step; rec = recbase + (size_t)(1 + P.n_tree + path) * P.rec_stride;
+            c.A = 0; c.A_sum = -10; depth = sh->depth; pend_vn = sh->vn; pend_val = sh->value;
+        } else if (path == 0) { role = R_MAIN; limit = P.max_step; c.A = -3; c.A_sum = -16; }   // bpgd.cpp:623-683
+        else {                                                  // tree branch id (bpgd.cpp:435-525)
+            role = R_TREE; limit = P.tree_step + P.T + 1; rec = recbase + (size_t)path * P.rec_stride;
+            c.A = -3; c.A_sum = -16;
+        }
+        int stage = 0, steps = 0, on_side = 0, saved = 0, bvar = -1, bval = 0, conv = 0;
+        for (;;) {
+            bool stage_end = false;
+            if (pend_vn >= 0) {
+                const int r = set_and_peel(c, pend_vn, pend_val);
+                pend_vn = -1;
+                if (r < 0) stage_end = true;
+            }
+            if (!stage_end && steps >= limit) stage_end = true;
+            if (!stage_end) {
+                if (role == R_MAIN) c.A_sum = (depth == 0) ? -16 : -12;                          // :631
+                if (role == R_TREE && stage == 0 && depth > 0 && !on_side) c.A_sum = -12;         // :450
+                conv = bp_run<VPT, DMAX>(c, h, P.num_iter, edge_iters); bp_calls++;
+                steps++;
+                if (role == R_GD) {
+                    // bpgd_decoder.gd (pyx:540-553) with decimate_vn_reliable (bpgd.cpp:258-286)
+                    if (conv) break;
+                    double best = 0.0; int bi = 0x7fffffff;   // argmax |h[3]|, first wins
+#pragma unroll
+                    for (int i = 0; i < VPT; i++) {
+                        const int j = tid + i * T;
+                        if (j < c.nn && c.vn_mask[j] < 0) { const double a = -fabs(h[i][3]); if (a < best) { best = a; bi = j; } }
+                    }
+                    block_argmin(best, bi, c.red_d, c.red_i);
+                    if (bi == 0x7fffffff) break;
+#pragma unroll
+                    for (int i = 0; i < VPT; i++) if (tid + i * T == bi) c.misc[3] = (h[i][3] > 0.0) ? 0 : 1;
+                    __syncthreads();
+                    pend_vn = bi; pend_val = c.misc[3]; depth++;
+                    continue;
+                }
+                if (conv && role != R_MAIN) break;                                                // :452-459, :552-559
+                int guess = -1;
+                int favor = select_vn<VPT>(c, h, depth, guess);
+                if (conv) break;                                                                  // main: :633-649
+                if (favor == -1 || guess == -1) stage_end = true;
+                else {
+                    if (role == R_MAIN && depth >= P.T && depth < P.S) {                          // :651-664
+                        unsigned char *sp = ws.side + ((size_t)slot * P.n_side + (depth - P.T)) * P.side_stride;
+                        i8 *svn = (i8 *)(sp + sizeof(SideHeader)); i8 *scn = svn + c.nn; u8 *sdg = (u8 *)(scn + c.m);
+                        for (int j = tid; j < c.nn; j += T) svn[j] = c.vn_mask[j];
+                        for (int r = tid; r < c.m; r += T) { scn[r] = c.cn_mask[r]; sdg[r] = c.cn_deg[r]; }
+                        if (tid == 0) { SideHeader *q = (SideHeader *)sp; q->vn = guess; q->value = 1 - favor; q->depth = depth + 1; q->valid = 1; }
+                    }
+                    if (role == R_TREE && stage == 0) {
+                        if (depth < P.T) {                                                        // :464-470
+                            if ((path >> (P.T - 1 - depth)) & 1) { on_side = 1; c.A = 0; c.A_sum = -10; favor = 1 - favor; }
+                        } else if (depth == P.T) {                                                // :476-484
+                            for (int j = tid; j < c.nn; j += T) bvn[j] = c.vn_mask[j];
+                            for (int r = tid; r < c.m; r += T) { bcn[r] = c.cn_mask[r]; bdeg[r] = c.cn_deg[r]; }
+                            bvar = guess; bval = 1 - favor; saved = 1;
+                        }
+                    }
+                    pend_vn = guess; pend_val = favor; depth++;
+                    continue;
+                }
+            }
+            // ---- the current stage ended without convergence
+            if (role == R_TREE && stage == 0 && saved) {                                          // :490-503
+                __syncthreads();
+                for (int j = tid; j < c.nn; j += T) { const i8 v = bvn[j]; c.vn_mask[j] = v; c.error[j] = v; }
+                for (int r = tid; r < c.m; r += T) { c.cn_mask[r] = bcn[r]; c.cn_deg[r] = bdeg[r]; }
+                __syncthreads();
+                init_msgs<VPT>(c);
+                stage = 1; steps = 0; limit = P.tree_step; depth = P.T + 1; pend_vn = bvar; pend_val = bval;
+                continue;
+            }
+            break;
+        }
+        if (conv || role == R_MAIN || role == R_GD) record_result(c, rec, conv);
+    }
+    // ---- work counters
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) edge_iters += __shfl_xor_sync(FULLMASK, edge_iters, o);
+    if (lane == 0 && edge_iters) atomicAdd(&ws.stats[1], edge_iters);
+    if (tid == 0) { if (paths_run) atomicAdd(&ws.stats[2], paths_run); if (bp_calls) atomicAdd(&ws.stats[3], bp_calls); }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K4: pick the branch with the smallest path metric (first wins ties; order main, tree ids, sides)
+// ----------------------------------------------------------------------------------------------
+__global__ void select_kernel(Workspace ws, SubLayout L, GdgDev P, int n, u8 *__restrict__ dec_out,
+                              u8 *__restrict__ conv_out, double *__restrict__ pm_out) {
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int count = ws.counters[0];
+    for (int slot = blockIdx.x; slot < count; slot += gridDim.x) {
+        const unsigned char *gblob = ws.blob + (size_t)slot * L.blob_bytes;
+        const BlobHeader gh = *(const BlobHeader *)gblob;
+        const u16 *col = (const u16 *)(gblob + L.off_col);
+        const u8 *recbase = ws.rec + (size_t)slot * P.n_rec * P.rec_stride;
+        int best = -1; double pm = SWD_MAX_PM;
+        if (gh.status == 0) {
+            for (int r = 0; r < P.n_rec; r++) {
+                const RecHeader *h = (const RecHeader *)(recbase + (size_t)r * P.rec_stride);
+                if (h->status == 1 && h->pm < pm) { pm = h->pm; best = r; }
+            }
+        }
+        const int conv = (P.kind == SWD_KIND_BPGDG && P.multi_thread) ? (pm < 9999.0) : (best >= 0);   // pyx:247
+        const size_t row = (size_t)gh.shot * n;
+        if (gh.status == 0) {
+            const u32 *bits = (const u32 *)(recbase + (size_t)(best < 0 ? 0 : best) * P.rec_stride + sizeof(RecHeader));
+            for (int j = tid; j < L.nn; j += T) dec_out[row + col[j]] = (u8)((bits[j >> 5] >> (j & 31)) & 1u);
+        } else if (P.kind == SWD_KIND_BPGDG && P.multi_thread) {
+            for (int j = tid; j < L.nn; j += T) dec_out[row + col[j]] = 0;      // fresh min_pm_error
+        }
+        if (tid == 0) { conv_out[gh.shot] = (u8)conv; if (pm_out) pm_out[gh.shot] = pm; }
+    }
+}
+
+// min_pm for BP-converged shots is not defined by the GDG decoders; fill with MAX_PM.
+__global__ void fill_pm_kernel(double *pm_out, long long B, double v) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) pm_out[i] = v;
+}

@@ -1,0 +1,255 @@
+"""Drop-in decoder classes: the reference's Cython API on top of the B200 C-ABI.
+
+  bpgdg_decoder  <- src/bp_guessing_decoder.pyx:160-469
+  bpgd_decoder   <- src/bp_guessing_decoder.pyx:473-570
+  osd_window     <- src/osd_window.pyx:6-549
+
+Same constructor kwargs / defaults, `decode(syndrome) -> np.int64[n]`, `.converge`, and the
+osd_window read-only properties.  Added: `decode_batch(syndromes[B, m])`, which is what the
+sliding-window driver uses (one call per window for ALL shots).  All arithmetic runs in the CUDA
+library; there is no CPU path.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+from scipy.sparse import spmatrix, csc_matrix
+
+from . import _lib
+
+_OSD_METHODS = {"osd_0": 0, "0": 0, "osd0": 0,
+                "osd_e": 1, "1": 1, "osde": 1, "exhaustive": 1, "e": 1,
+                "osd_cs": 2, "2": 2, "osdcs": 2, "combination_sweep": 2, "cs": 2}
+
+
+def _libm_llr(channel_probs, n):
+    # log((1-p)/p) with libm's log, as bp_guessing_decoder.pyx:46 (numpy's vector log differs by ulps)
+    return np.array([math.log((1.0 - float(channel_probs[v])) / float(channel_probs[v])) for v in range(n)],
+                    dtype=np.float64)
+
+
+def _is_torch_cuda(x):
+    return type(x).__module__.startswith("torch") and hasattr(x, "is_cuda") and x.is_cuda
+
+
+class _window_decoder_base:
+    """Shared constructor checks (bp_guessing_decoder.pyx:6-46, osd_window.pyx:8-34) and batch plumbing."""
+
+    _kind = None
+
+    def _setup(self, parity_check_matrix, channel_probs, cfg, device):
+        if not (isinstance(parity_check_matrix, np.ndarray) or isinstance(parity_check_matrix, spmatrix)):
+            raise TypeError("The input matrix is of an invalid type. Please input a np.ndarray or "
+                            f"scipy.sparse.spmatrix object, not {type(parity_check_matrix)}")
+        self.m, self.n = parity_check_matrix.shape
+        if channel_probs is None:
+            raise TypeError("channel_probs is required")
+        if channel_probs[0] is not None and len(channel_probs) != self.n:
+            raise ValueError(f"The length of the channel probability vector must be eqaul to the block length n={self.n}.")
+        A = csc_matrix(parity_check_matrix)
+        A.eliminate_zeros()
+        A.sort_indices()
+        self._colptr = np.ascontiguousarray(A.indptr, dtype=np.int32)
+        self._rowidx = np.ascontiguousarray(A.indices, dtype=np.int32)
+        self.channel_llr = _libm_llr(channel_probs, self.n)
+        cfg.kind = self._kind
+        cfg.device = int(device)
+        self._cfg = cfg
+        self._device = int(device)
+        self._handle = C.c_void_p()
+        lib = _lib.load()
+        st = lib.swd_create(C.byref(cfg), self.m, self.n, self._colptr.ctypes.data_as(C.POINTER(C.c_int32)),
+                            self._rowidx.ctypes.data_as(C.POINTER(C.c_int32)),
+                            self.channel_llr.ctypes.data_as(C.POINTER(C.c_double)), C.byref(self._handle))
+        _lib.check(st, "swd_create")
+        self._lib = lib
+        self.new_n = lib.swd_new_n(self._handle)
+        self._converge = 0
+        self.min_pm_batch = None
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            self._lib.swd_destroy(h)
+            self._handle = C.c_void_p()
+
+    @property
+    def converge(self):
+        return self._converge
+
+    # ------------------------------------------------------------------ batched entry points
+    def decode_batch(self, syndromes, return_pm=False):
+        """syndromes: [B, m] of 0/1.  numpy in -> numpy out (host copies inside the call);
+        torch CUDA uint8 tensor in -> torch CUDA tensors out (asynchronous on the current stream).
+        Returns (corrections [B, n] uint8, converge [B] uint8[, min_pm [B] float64])."""
+        if _is_torch_cuda(syndromes):
+            return self._decode_batch_torch(syndromes, return_pm)
+        s = np.ascontiguousarray(np.asarray(syndromes), dtype=np.uint8)
+        if s.ndim != 2 or s.shape[1] != self.m:
+            raise ValueError(f"decode_batch expects syndromes of shape [B, {self.m}], got {s.shape}")
+        B = s.shape[0]
+        corr = np.empty((B, self.n), dtype=np.uint8)
+        conv = np.empty(B, dtype=np.uint8)
+        pm = np.empty(B, dtype=np.float64)
+        st = self._lib.swd_decode_batch_host(self._handle, s.ctypes.data, B, corr.ctypes.data, conv.ctypes.data, pm.ctypes.data)
+        _lib.check(st, "swd_decode_batch_host")
+        self._last_B = B
+        return (corr, conv, pm) if return_pm else (corr, conv)
+
+    def _decode_batch_torch(self, syndromes, return_pm):
+        import torch
+        s = syndromes
+        if s.dtype != torch.uint8:
+            s = s.to(torch.uint8)
+        s = s.contiguous()
+        if s.dim() != 2 or s.shape[1] != self.m:
+            raise ValueError(f"decode_batch expects syndromes of shape [B, {self.m}], got {tuple(s.shape)}")
+        if s.device.index != self._device:
+            raise ValueError(f"syndromes live on cuda:{s.device.index}, decoder on cuda:{self._device}")
+        B = s.shape[0]
+        corr = torch.empty((B, self.n), dtype=torch.uint8, device=s.device)
+        conv = torch.empty(B, dtype=torch.uint8, device=s.device)
+        pm = torch.empty(B, dtype=torch.float64, device=s.device)
+        stream = torch.cuda.current_stream(s.device).cuda_stream
+        st = self._lib.swd_decode_batch_device(self._handle, s.data_ptr(), B, corr.data_ptr(), conv.data_ptr(), pm.data_ptr(),
+                                               C.c_void_p(stream))
+        _lib.check(st, "swd_decode_batch_device")
+        self._last_B = B
+        self._keepalive = s
+        return (corr, conv, pm) if return_pm else (corr, conv)
+
+    def _decode_one(self, input_vector):
+        input_length = input_vector.shape[0]
+        if input_length != self.m:
+            raise ValueError(f"The input to the ldpc.bp_decoder.decode must be a syndrome (of length={self.m}). The inputted "
+                             f"vector has length={input_length}. Valid formats are `np.ndarray` or `scipy.sparse.spmatrix`.")
+        s = np.asarray(input_vector).reshape(1, self.m)
+        corr, conv, pm = self.decode_batch(s, return_pm=True)
+        self._converge = int(conv[0])
+        self._min_pm = float(pm[0])
+        return corr[0].astype(np.int64)
+
+    def counters(self):
+        c = _lib.SwdCounters()
+        _lib.check(self._lib.swd_get_counters(self._handle, C.byref(c)), "swd_get_counters")
+        return c.as_dict()
+
+    def reset_counters(self):
+        _lib.check(self._lib.swd_reset_counters(self._handle), "swd_reset_counters")
+
+
+class bpgdg_decoder(_window_decoder_base):
+    """BP + Guided Decimation Guessing (bp_guessing_decoder.pyx:160-469)."""
+    _kind = _lib.KIND_BPGDG
+
+    def __init__(self, parity_check_matrix, **kwargs):
+        cfg = _lib.SwdConfig()
+        cfg.max_iter = int(kwargs.get("max_iter", 50))
+        cfg.ms_scaling_factor = float(kwargs.get("ms_scaling_factor", 1.0))
+        cfg.max_iter_per_step = int(kwargs.get("max_iter_per_step", 6))
+        cfg.max_step = int(kwargs.get("max_step", 25))
+        cfg.max_tree_depth = int(kwargs.get("max_tree_depth", 3))
+        cfg.max_side_depth = int(kwargs.get("max_side_depth", 10))
+        cfg.max_tree_branch_step = int(kwargs.get("max_tree_branch_step", 10))
+        cfg.max_side_branch_step = int(kwargs.get("max_side_branch_step", 10))
+        cfg.gdg_factor = float(kwargs.get("gdg_factor", 1.0))
+        new_n = kwargs.get("new_n", None)
+        cfg.new_n = 0 if new_n is None else int(new_n)
+        cfg.multi_thread = int(bool(kwargs.get("multi_thread", False)))
+        cfg.low_error_mode = int(bool(kwargs.get("low_error_mode", False)))
+        self.multi_thread = bool(cfg.multi_thread)
+        self._setup(parity_check_matrix, kwargs.get("channel_probs"), cfg, kwargs.get("device", 0))
+
+    def decode(self, input_vector):
+        return self._decode_one(input_vector)
+
+
+class bpgd_decoder(_window_decoder_base):
+    """BP + guided decimation (bp_guessing_decoder.pyx:473-570)."""
+    _kind = _lib.KIND_BPGD
+
+    def __init__(self, parity_check_matrix, **kwargs):
+        cfg = _lib.SwdConfig()
+        cfg.max_iter = int(kwargs.get("max_iter", 50))
+        cfg.ms_scaling_factor = float(kwargs.get("ms_scaling_factor", 1.0))
+        cfg.max_iter_per_step = int(kwargs.get("max_iter_per_step", 6))
+        cfg.max_step = int(kwargs.get("max_step", 25))
+        cfg.gdg_factor = float(kwargs.get("gd_factor", 1.0))
+        new_n = kwargs.get("new_n", None)
+        cfg.new_n = 0 if new_n is None else int(new_n)
+        self._setup(parity_check_matrix, kwargs.get("channel_probs"), cfg, kwargs.get("device", 0))
+
+    def decode(self, input_vector):
+        return self._decode_one(input_vector)
+
+
+class osd_window(_window_decoder_base):
+    """BP on the window, shortening, BP on the shortened window, OSD (osd_window.pyx)."""
+    _kind = _lib.KIND_OSD_WINDOW
+
+    def __init__(self, parity_check_matrix, **kwargs):
+        cfg = _lib.SwdConfig()
+        cfg.max_iter = int(kwargs.get("pre_max_iter", 8))
+        cfg.post_max_iter = int(kwargs.get("post_max_iter", 100))
+        cfg.ms_scaling_factor = float(kwargs.get("ms_scaling_factor", 1.0))
+        new_n = kwargs.get("new_n", None)
+        cfg.new_n = 0 if new_n is None else int(new_n)
+        osd_method = kwargs.get("osd_method", "osd_0")
+        osd_order = kwargs.get("osd_order", 0)
+        key = str(osd_method).lower()
+        if key not in _OSD_METHODS:
+            raise ValueError(f"ERROR: OSD method '{osd_method}' invalid. Please choose from the following methods: "
+                             "'OSD_0', 'OSD_E' or 'OSD_CS'.")
+        cfg.osd_method = _OSD_METHODS[key]
+        cfg.osd_order = 0 if cfg.osd_method == 0 else int(osd_order)
+        self.osd_method, self.osd_order = cfg.osd_method, cfg.osd_order
+        try:
+            self._setup(parity_check_matrix, kwargs.get("channel_probs"), cfg, kwargs.get("device", 0))
+        except ValueError as e:
+            if "osd_order" in str(e):
+                raise ValueError("For this code, the OSD order should be set in the range 0<=osd_oder<=new_n-rank.") from e
+            raise
+        self.rank = self._lib.swd_rank(self._handle)
+        self._min_pm = 0.0
+        self._last_B = 0
+
+    def decode(self, input_vector):
+        return self._decode_one(input_vector)
+
+    def last_outputs(self, B=None):
+        """dict of the per-shot read-only properties of the last batch (host numpy arrays)."""
+        B = self._last_B if B is None else B
+        n = self.n
+        bp = np.empty((B, n), dtype=np.uint8)
+        o0 = np.empty((B, n), dtype=np.uint8)
+        ow = np.empty((B, n), dtype=np.uint8)
+        lpr = np.empty((B, n, 4), dtype=np.float64)
+        it = np.empty(B, dtype=np.int32)
+        st = self._lib.swd_osd_last_outputs(self._handle, B, bp.ctypes.data, o0.ctypes.data, ow.ctypes.data, lpr.ctypes.data,
+                                            it.ctypes.data)
+        _lib.check(st, "swd_osd_last_outputs")
+        return dict(bp_decoding=bp, osd0_decoding=o0, osdw_decoding=ow, log_prob_ratios=lpr, bp_iteration=it)
+
+    @property
+    def min_pm(self):
+        return self._min_pm
+
+    @property
+    def bp_iteration(self):
+        return int(self.last_outputs(1)["bp_iteration"][0])
+
+    @property
+    def bp_decoding(self):
+        return self.last_outputs(1)["bp_decoding"][0].astype(np.int64)
+
+    @property
+    def osd0_decoding(self):
+        return self.last_outputs(1)["osd0_decoding"][0].astype(np.int64)
+
+    @property
+    def osdw_decoding(self):
+        return self.last_outputs(1)["osdw_decoding"][0].astype(np.int64)
+
+    @property
+    def log_prob_ratios(self):
+        return self.last_outputs(1)["log_prob_ratios"][0].copy()
