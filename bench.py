@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: sliding-window GDG decoding throughput (decoded shots / s).
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on):
+  [[144,12,12]] gross code, circuit-level noise p = 0.003, 12 rounds, sliding window (W, F) = (3, 1)
+  -> 11 windows of 216 x (1656 | 1728 | 1656), GDG per window (bpgdg_decoder, max_iter=8, multi_thread tree).
+A "step" = one pass of the whole window pipeline over one batch of `--batch` synthetic shots per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+Under torchrun (N > 1) every rank decodes its own batch (weak scaling); the only collective is the
+all-reduce of the failure counters.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(N=144, p=0.003, rounds=12, W=3, F=1, method=1)
+GDG_KW = dict(max_iter=8, max_iter_per_step=6, max_step=25, max_tree_depth=3, max_side_depth=10,
+              max_tree_branch_step=10, max_side_branch_step=10, multi_thread=True, low_error_mode=False)
+WORKLOAD_NAME = "[[144,12,12]] circuit-level p=0.003, 12 rounds, sliding window W=3 F=1 (11 windows), GDG per window"
+
+
+def build_plan():
+    from slidingwindowdecoder_b200.codes import bb_code
+    from slidingwindowdecoder_b200.dem import bb_memory_circuit, detector_error_model, dem_to_check_matrices
+    from slidingwindowdecoder_b200.windows import build_windows
+    code, A, B = bb_code(WORKLOAD["N"])
+    circ = bb_memory_circuit(code, A, B, WORKLOAD["p"], WORKLOAD["rounds"], z_basis=True)
+    chk, obs, pri = dem_to_check_matrices(detector_error_model(circ))
+    return build_windows(chk, obs, pri, code.N, W=WORKLOAD["W"], F=WORKLOAD["F"], method=WORKLOAD["method"])
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+_CPU = {}
+
+
+def _cpu_init(plan_blob):
+    from oracle.oracle import Oracle
+    _CPU["plan"] = plan_blob
+    _CPU["orc"] = [Oracle(w.mat, w.prior) for w in plan_blob.windows]
+    _CPU["chkT"] = plan_blob.chk.T.tocsr()
+    _CPU["obsT"] = plan_blob.obs.T.tocsr()
+
+
+def _cpu_decode_shard(args):
+    """The reference's sliding-window loop (guessing.py:141-227) on a shard of shots with the C oracle."""
+    det, obs = args
+    plan = _CPU["plan"]
+    B = det.shape[0]
+    new_det = det.copy()
+    total = np.zeros((B, plan.chk.shape[1]), dtype=np.uint8)
+    for w, orc in zip(plan.windows, _CPU["orc"]):
+        dec, conv, _, _ = orc.bpgdg_batch(new_det[:, w.row0:w.row1], **GDG_KW)
+        total[:, w.col0:w.col0 + w.ncommit] = dec[:, :w.ncommit]
+        upd = np.asarray(total[:, w.col0:w.col0 + w.ncommit].astype(np.float32) @ _CPU["chkT"][w.col0:w.col0 + w.ncommit].astype(np.float32)) % 2
+        new_det = (new_det + upd.astype(np.uint8)) % 2
+    flagged = new_det.any(axis=1)
+    logical = ((obs + np.asarray(total.astype(np.float32) @ _CPU["obsT"].astype(np.float32)) % 2).astype(np.uint8) % 2).any(axis=1)
+    return int(flagged.sum()), int(np.logical_or(flagged, logical).sum())
+
+
+def sample_host(plan, shots, seed):
+    from slidingwindowdecoder_b200.sliding_window import sample_dem
+    det, obs, _ = sample_dem(plan.chk, plan.obs, plan.priors, shots, np.random.default_rng(seed))
+    return det, obs
+
+
+class CpuArm:
+    """Oracle port on all host cores (process-level sharding over shots: the 'all-core' CPU figure of BASELINE.md §3)."""
+
+    def __init__(self, plan):
+        import multiprocessing as mp
+        self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.plan = plan
+        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init, initargs=(plan,))
+
+    def run(self, det, obs):
+        B = det.shape[0]
+        nshard = min(B, self.cores * 4)
+        idx = np.array_split(np.arange(B), nshard)
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_decode_shard, [(det[i], obs[i]) for i in idx if len(i)])
+        dt = time.perf_counter() - t0
+        return dt, sum(r[0] for r in res), sum(r[1] for r in res)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def calibrate_cpu_sample(arm, plan, target_s):
+    det, obs = sample_host(plan, arm.cores * 4, 999)
+    dt, _, _ = arm.run(det, obs)
+    rate = det.shape[0] / max(dt, 1e-6)
+    return int(max(arm.cores * 4, min(20000, rate * target_s)))
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def gpu_sample(torch, plan, shots, seed, dev):
+    """Independent Bernoulli per DEM column on the device (what CompiledDemSampler draws, guessing.py:129-130)."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    pri = torch.from_numpy(plan.priors).to(dev, torch.float32)
+    chkT = torch.from_numpy(np.asarray(plan.chk.T.todense(), dtype=np.float32)).to(dev)
+    obsT = torch.from_numpy(np.asarray(plan.obs.T.todense(), dtype=np.float32)).to(dev)
+    dets, obss = [], []
+    for s0 in range(0, shots, 8192):
+        nb = min(8192, shots - s0)
+        err = (torch.rand((nb, pri.numel()), generator=g, device=dev) < pri).to(torch.float32)
+        dets.append(torch.remainder(err @ chkT, 2).to(torch.uint8))
+        obss.append(torch.remainder(err @ obsT, 2).to(torch.uint8))
+    return torch.cat(dets), torch.cat(obss)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    assert torch.cuda.is_available(), "bench.py needs CUDA (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from slidingwindowdecoder_b200.sliding_window import SlidingWindowDecoder
+    plan = build_plan()
+    swd = SlidingWindowDecoder(plan, decoder="gdg", device=local, **GDG_KW)
+    B, K, W = args.batch, args.steps, args.warmup
+    nsteps = K + W
+    torch.backends.cuda.matmul.allow_tf32 = False
+    det_all, obs_all = gpu_sample(torch, plan, B * nsteps, 1234 + rank, dev)
+    det_all = det_all.view(nsteps, B, -1); obs_all = obs_all.view(nsteps, B, -1)
+    h_det = torch.empty(det_all.shape, dtype=torch.uint8, pin_memory=True); h_det.copy_(det_all)
+    h_obs = torch.empty(obs_all.shape, dtype=torch.uint8, pin_memory=True); h_obs.copy_(obs_all)
+    h_counts = torch.zeros((nsteps, 2), dtype=torch.int64, pin_memory=True)
+    decs = swd.unique_decoders()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_resident(i):
+        det = det_all[i].clone(); obs = obs_all[i].clone()
+        return swd.decode_device(det, obs)["counts"]
+
+    def step_e2e(i):
+        det = h_det[i].to(dev, non_blocking=True); obs = h_obs[i].to(dev, non_blocking=True)
+        out = swd.decode_device(det, obs)
+        h_counts[i].copy_(out["counts"], non_blocking=True)
+        return out["counts"]
+
+    def timed(fn, profile):
+        for i in range(W):
+            fn(i)
+        for d in decs:
+            d.kernel_times() if profile else None
+            d.reset_counters()
+            d.set_profiling(profile)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        counts = torch.zeros(2, dtype=torch.int64, device=dev)
+        e0.record()
+        for i in range(W, W + K):
+            counts += fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)      # the path's only collective: failure counters
+        return ms, counts.cpu().numpy()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_res, counts_res = timed(step_resident, True)
+    ktimes = {}
+    ctr = {}
+    for d in decs:
+        for k, (t, ln) in d.kernel_times().items():
+            a = ktimes.setdefault(k, [0.0, 0]); a[0] += t; a[1] += ln
+        for k, v in d.counters().items():
+            ctr[k] = ctr.get(k, 0) + v
+        d.set_profiling(False)
+    ms_e2e, counts_e2e = timed(step_e2e, False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # per-window latency (p50) at the throughput batch and at batch 1
+    def window_latency(batch, reps):
+        lat = []
+        for r in range(reps):
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in plan.windows]
+            det = det_all[r % nsteps][:batch].clone(); obs = obs_all[r % nsteps][:batch].clone()
+            swd.decode_device(det, obs, window_events=ev)
+            torch.cuda.synchronize()
+            lat += [a.elapsed_time(b) for a, b in ev]
+        return float(np.median(lat)), float(np.percentile(lat, 99))
+    p50_b, p99_b = window_latency(B, 2)
+    p50_1, p99_1 = window_latency(1, 20)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    total_shots = world * B * K
+    value = total_shots / (ms_res / 1e3)
+    e2e = total_shots / (ms_e2e / 1e3)
+    # ---- roofline of the dominant kernel (path_kernel: GDG branch paths, both phases)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
+    path_ms = ktimes.get("path_main", [0, 0])[0] + ktimes.get("path_side", [0, 0])[0]
+    path_launches = ktimes.get("path_main", [0, 0])[1] + ktimes.get("path_side", [0, 0])[1]
+    # B_iter = 4 E w + 2 n_a w + (n_a + m_a)/8 with w = 8, summed over executed iterations
+    path_bytes = 32.0 * ctr["path_edge_iters"] + 16.0 * ctr["path_vn_iters"] + (ctr["path_vn_iters"] + ctr["path_cn_iters"]) / 8.0
+    pre_bytes = 32.0 * ctr["pre_bp_edge_iters"]
+    achieved = path_bytes / (path_ms / 1e3) / 1e9 if path_ms > 0 else 0.0
+    kernel_ms = {k: round(v[0], 3) for k, v in ktimes.items() if v[1]}
+    tot_k = sum(kernel_ms.values()) or 1.0
+    roofline = {"kernel": "path_kernel (GDG branch paths, phases main+side)", "bound": "hbm", "achieved": round(achieved, 1),
+                "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": round(path_bytes / max(1, path_launches)),
+                "avg_launch_ms": round(path_ms / max(1, path_launches), 4), "launches": path_launches,
+                "share_of_kernel_time": round(path_ms / tot_k, 4),
+                "note": "messages are held in shared memory, so algorithmic message bytes/s is compared with the HBM "
+                        "roof only to show on-chip residency; see smem_achieved_gbs for the binding on-chip roof",
+                "pre_bp_achieved_gbs": round(pre_bytes / (ktimes.get("pre_bp", [1e-9, 0])[0] / 1e3) / 1e9, 1) if ktimes.get("pre_bp", [0, 0])[0] else None,
+                "kernel_ms": kernel_ms}
+    # ---- CPU baseline on a bounded sample
+    if args.skip_cpu:
+        cpu_baseline = None
+    else:
+        arm = CpuArm(plan)
+        nsample = calibrate_cpu_sample(arm, plan, 12.0)
+        cdet, cobs = sample_host(plan, nsample, 4321)
+        dt, cflag, cfail = arm.run(cdet, cobs)
+        arm.close()
+        cpu_baseline = {"value": round(nsample / dt, 2), "unit": "shots/s", "cores": arm.cores, "kind": "port",
+                        "sample": f"{nsample} shots x 11 windows through the oracle port (C restatement, gcc -O2), "
+                                  f"one process per core, {dt:.1f} s; failed {cfail}/{nsample}"}
+    launches = ctr["kernel_launches"] + K * (2 * len(plan.windows) + 1)
+    line = {
+        "metric": "decoded shots/sec (sliding-window GDG)", "value": round(value, 1), "unit": "shots/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": round(ms_res / K, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAME, "shots_per_step_per_gpu": B, "decoder": "bpgdg_decoder(max_iter=8, multi_thread=True, defaults)",
+                   "inputs": "DEM samples (independent Bernoulli per column); distinct batch per step, "
+                             f"{(B * (det_all.shape[2] + obs_all.shape[2]) * nsteps) >> 20} MiB of syndromes in total (> L2), no L2 flush"},
+        "e2e": {"value": round(e2e, 1), "unit": "shots/s", "h2d_bytes_per_step": int(B * (det_all.shape[2] + obs_all.shape[2])),
+                "d2h_bytes_per_step": 16, "ms_per_step": round(ms_e2e / K, 3)},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "window_latency_ms": {"p50_at_batch": round(p50_b, 4), "p99_at_batch": round(p99_b, 4), "p50_batch1": round(p50_1, 4), "p99_batch1": round(p99_1, 4)},
+        "results": {"shots": int(total_shots), "flagged": int(counts_res[0]), "failed": int(counts_res[1]),
+                    "gdg_fraction": round(ctr["gdg_shots"] / max(1, ctr["shots"]), 4)},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    plan = build_plan()
+    arm = CpuArm(plan)
+    nsample = calibrate_cpu_sample(arm, plan, 8.0)
+    K, W = args.steps, args.warmup
+    K = max(1, min(K, 6)); W = max(0, min(W, 1))      # bounded: the whole run must end within minutes
+    times, fails, n = [], 0, 0
+    for i in range(W + K):
+        det, obs = sample_host(plan, nsample, 100 + i)
+        dt, fl, fa = arm.run(det, obs)
+        if i >= W:
+            times.append(dt); fails += fa; n += nsample
+    arm.close()
+    v = n / sum(times)
+    line = {"impl": "reference", "metric": "decoded shots/sec (sliding-window GDG)", "value": round(v, 2), "unit": "shots/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": K, "warmup": W, "ms_per_step": round(1e3 * sum(times) / K, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME, "shots_per_step": nsample},
+            "cpu_baseline": {"value": round(v, 2), "unit": "shots/s", "cores": arm.cores, "kind": "port",
+                             "sample": f"{nsample} shots x 11 windows per step, oracle port (C restatement), one process per core"},
+            "e2e": {"value": round(v, 2), "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "results": {"shots": n, "failed": fails}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=16384)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: do not time the CPU baseline")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

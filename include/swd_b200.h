@@ -86,7 +86,18 @@ typedef struct swd_counters {
     uint64_t kernel_launches;     /* kernels launched by this library                            */
     uint64_t paths_run;           /* branch paths that executed at least one BP call             */
     uint64_t bp_calls;            /* min_sum_log-equivalent calls over all branch paths          */
+    uint64_t path_vn_iters;       /* active variable nodes x iterations inside GDG/GD/post-BP    */
+    uint64_t path_cn_iters;       /* active check nodes x iterations inside GDG/GD/post-BP       */
 } swd_counters;
+
+/* Kernel classes for swd_get_kernel_times */
+#define SWD_K_PRE_BP     0
+#define SWD_K_SORT_RESET 1
+#define SWD_K_PATH_MAIN  2   /* path_kernel phase 0: main + tree branches (or the single GD / post-BP path) */
+#define SWD_K_PATH_SIDE  3   /* path_kernel phase 1: side branches                                         */
+#define SWD_K_SELECT     4
+#define SWD_K_OSD        5
+#define SWD_K_COUNT      8
 
 /* pcm as CSC: colptr[n+1], rowidx[nnz] (any order inside a column; sorted internally, as
  * mod2sparse_insert keeps them).  channel_llr[n] = log((1-p)/p) computed by the caller with libm
@@ -107,6 +118,12 @@ int  swd_decode_batch_device(swd_decoder *d, const uint8_t *d_synd, int64_t B,
  * Any pointer may be NULL.  bp_dec/osd0/osdw: [B*n]; log_prob_ratios: [B*n*4]; bp_iteration: [B]. */
 int  swd_osd_last_outputs(swd_decoder *d, int64_t B, uint8_t *bp_dec, uint8_t *osd0, uint8_t *osdw,
                           double *log_prob_ratios, int32_t *bp_iteration);
+
+/* Per-kernel device timing.  When enabled, every kernel launch is bracketed by a pair of CUDA events
+ * on the launching stream; swd_get_kernel_times synchronises, sums the elapsed times per kernel class
+ * into ms[SWD_K_COUNT] / launches[SWD_K_COUNT] (accumulated since the last call) and recycles the events. */
+int  swd_set_profiling(swd_decoder *d, int enable);
+int  swd_get_kernel_times(swd_decoder *d, double *ms, uint64_t *launches);
 
 int  swd_get_counters(swd_decoder *d, swd_counters *out);
 int  swd_reset_counters(swd_decoder *d);

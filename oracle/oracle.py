@@ -203,3 +203,26 @@ class Oracle:
                                           self.rank, _p(dec, C.c_int8), _p(conv, C.c_int8), _p(pm, C.c_double),
                                           C.byref(st))
         return dec, conv, pm, st
+
+
+def sliding_window_reference(plan, det, obs, decode_window):
+    """The reference's window loop (guessing.py:141-227) in dense numpy, for tests.
+    decode_window(window, synd[B, m]) -> (corr[B, n_win], conv[B]).
+    Returns dict(flagged[B] bool, failed[B] bool, total_e_hat[B, num_col], window_unconverged list)."""
+    chk = np.asarray(plan.chk.todense()).astype(np.int64)
+    ob = np.asarray(plan.obs.todense()).astype(np.int64)
+    det = np.asarray(det).astype(np.int64)
+    obs = np.asarray(obs).astype(np.int64)
+    B = det.shape[0]
+    total = np.zeros((B, chk.shape[1]), dtype=np.int64)
+    new_det = det.copy()
+    unconv = []
+    for w in plan.windows:
+        synd = new_det[:, w.row0:w.row1]
+        corr, conv = decode_window(w, synd)
+        total[:, w.col0:w.col0 + w.ncommit] = np.asarray(corr)[:, :w.ncommit]
+        unconv.append(int(B - np.asarray(conv).astype(np.int64).sum()))
+        new_det = (det + total @ chk.T) % 2
+    flagged = new_det.any(axis=1)
+    logical = ((obs + total @ ob.T) % 2).any(axis=1)
+    return dict(flagged=flagged, failed=np.logical_or(flagged, logical), total_e_hat=total, window_unconverged=unconv)

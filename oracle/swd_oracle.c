@@ -368,6 +368,11 @@ typedef struct {
 
 typedef struct { double pm; int8_t *err; int n; } best_t;
 static void best_offer(best_t *b, double pm, const int8_t *err) {
+    if (getenv("ORC_TRACE")) {
+        int wt = 0; unsigned hsh = 0;
+        for (int i = 0; i < b->n; i++) if (err[i]) { wt++; hsh = hsh * 31u + (unsigned)i; }
+        fprintf(stderr, "[orc] offer pm=%.17g wt=%d hash=%08x %s\n", pm, wt, hsh, pm < b->pm ? "TAKEN" : "");
+    }
     if (pm < b->pm) { b->pm = pm; memcpy(b->err, err, b->n); }
 }
 

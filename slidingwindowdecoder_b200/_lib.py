@@ -22,17 +22,18 @@ class SwdConfig(C.Structure):
 
 class SwdCounters(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("shots", "pre_bp_edge_iters", "path_edge_iters", "gdg_shots", "osd_shots",
-                                          "kernel_launches", "paths_run", "bp_calls")]
+                                          "kernel_launches", "paths_run", "bp_calls", "path_vn_iters", "path_cn_iters")]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
 KIND_BPGDG, KIND_BPGD, KIND_OSD_WINDOW = 0, 1, 2
+KERNEL_CLASSES = ["pre_bp", "sort_reset", "path_main", "path_side", "select", "osd", "k6", "k7"]
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4
 
 EXPORTS = ["swd_create", "swd_destroy", "swd_decode_batch_host", "swd_decode_batch_device", "swd_osd_last_outputs",
-           "swd_get_counters", "swd_reset_counters", "swd_rank", "swd_new_n", "swd_window_create", "swd_window_destroy",
+           "swd_set_profiling", "swd_get_kernel_times", "swd_get_counters", "swd_reset_counters", "swd_rank", "swd_new_n", "swd_window_create", "swd_window_destroy",
            "swd_window_extract", "swd_window_commit", "swd_window_count_failures", "swd_strerror", "swd_last_error",
            "swd_version"]
 
@@ -61,6 +62,10 @@ def load():
     lib.swd_osd_last_outputs.restype = C.c_int
     lib.swd_get_counters.argtypes = [vp, C.POINTER(SwdCounters)]
     lib.swd_get_counters.restype = C.c_int
+    lib.swd_set_profiling.argtypes = [vp, C.c_int]
+    lib.swd_set_profiling.restype = C.c_int
+    lib.swd_get_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    lib.swd_get_kernel_times.restype = C.c_int
     lib.swd_reset_counters.argtypes = [vp]
     lib.swd_reset_counters.restype = C.c_int
     lib.swd_rank.argtypes = [vp]

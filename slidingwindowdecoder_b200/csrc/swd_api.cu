@@ -68,6 +68,25 @@ struct swd_decoder {
     // accumulated counters
     swd_counters ctr{};
     long long last_B = 0;
+    // optional per-kernel event timing
+    bool profiling = false;
+    struct EvPair { cudaEvent_t a, b; int k; };
+    std::vector<EvPair> ev_used;
+    std::vector<cudaEvent_t> ev_free;
+    cudaEvent_t ev_get() {
+        if (!ev_free.empty()) { cudaEvent_t e = ev_free.back(); ev_free.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+};
+
+struct KTimer {     // brackets one launch with events when profiling is on
+    swd_decoder *d; cudaStream_t s; int k; cudaEvent_t a = nullptr;
+    KTimer(swd_decoder *d_, cudaStream_t s_, int k_) : d(d_), s(s_), k(k_) {
+        if (d->profiling) { a = d->ev_get(); cudaEventRecord(a, s); }
+    }
+    ~KTimer() {
+        if (d->profiling) { cudaEvent_t b = d->ev_get(); cudaEventRecord(b, s); d->ev_used.push_back({a, b, k}); }
+    }
 };
 
 extern "C" const char *swd_version(void) { return "swd_b200 0.1 (sm_100a)"; }
@@ -189,13 +208,16 @@ extern "C" void swd_destroy(swd_decoder *d) {
     if (d->d_conv) cudaFree(d->d_conv);
     if (d->d_pm) cudaFree(d->d_pm);
     if (d->h_pin) cudaFreeHost(d->h_pin);
+    for (auto &e : d->ev_used) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (auto &e : d->ev_free) cudaEventDestroy(e);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
 }
 
 template <typename K>
 static int occupancy(K kernel, int threads, size_t smem, int *out) {
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // opt in to the full 227 KB once: several decoders with different footprints share each kernel
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem));
     *out = nb;
@@ -342,7 +364,7 @@ static int pull_stats(swd_decoder *d, cudaStream_t s) {
     CK(cudaMemcpyAsync(h, d->ws.stats, sizeof(h), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     d->ctr.pre_bp_edge_iters = h[0]; d->ctr.path_edge_iters = h[1]; d->ctr.paths_run = h[2]; d->ctr.bp_calls = h[3];
-    d->ctr.osd_shots = h[4]; d->ctr.gdg_shots = h[5];
+    d->ctr.osd_shots = h[4]; d->ctr.gdg_shots = h[5]; d->ctr.path_vn_iters = h[6]; d->ctr.path_cn_iters = h[7];
     return SWD_OK;
 }
 
@@ -354,12 +376,15 @@ static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_cor
     const int g1 = (int)std::min<long long>(B, d->grid1);
     const int full_hist = (c.kind == SWD_KIND_OSD_WINDOW) ? 1 : 0;
     int *iter_out = (c.kind == SWD_KIND_OSD_WINDOW) ? d->ow.bp_iter + chunk_base : nullptr;
+    {
+    KTimer kt(d, s, SWD_K_PRE_BP);
     if (d->dmax == 8)
         pre_bp_kernel<8><<<g1, d->T1, d->PRE.total, s>>>(d->g, d_synd, B, c.max_iter, c.ms_scaling_factor, d_corr, d_conv, d->ws,
                                                         d->hscratch, full_hist, d->PRE, iter_out);
     else
         pre_bp_kernel<16><<<g1, d->T1, d->PRE.total, s>>>(d->g, d_synd, B, c.max_iter, c.ms_scaling_factor, d_corr, d_conv, d->ws,
                                                          d->hscratch, full_hist, d->PRE, iter_out);
+    }
     d->ctr.kernel_launches++;
     if (d_pm) {
         const double fillv = (c.kind == SWD_KIND_OSD_WINDOW) ? 0.0 : SWD_MAX_PM;
@@ -368,7 +393,8 @@ static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_cor
     }
     if (c.kind == SWD_KIND_BPGD && c.max_iter <= -1) return SWD_OK;   // pyx:506
     const int g2 = (int)std::min<long long>(B, d->grid2);
-    sort_reset_kernel<<<g2, d->T2, d->SS.total, s>>>(d->g, d_synd, d->ws, d->L, d->P, d->SS, d_corr);
+    { KTimer kt(d, s, SWD_K_SORT_RESET);
+      sort_reset_kernel<<<g2, d->T2, d->SS.total, s>>>(d->g, d_synd, d->ws, d->L, d->P, d->SS, d_corr); }
     d->ctr.kernel_launches++;
     const size_t smem3 = (size_t)d->L.blob_bytes + d->PS.total;
     const int g3 = d->grid3;
@@ -379,10 +405,12 @@ static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_cor
         if (st) { set_err("osd launch failed"); return st; }
     } else {
         for (int ph = 0; ph < phases; ph++) {
+            KTimer kt(d, s, ph == 0 ? SWD_K_PATH_MAIN : SWD_K_PATH_SIDE);
             d->path_fn<<<g3, d->T3, smem3, s>>>(d->ws, d->L, d->PS, d->P, ph);
             d->ctr.kernel_launches++;
         }
-        select_kernel<<<std::max(1, std::min<int>((int)B, d->num_sm * 8)), 128, 0, s>>>(d->ws, d->L, d->P, d->n, d_corr, d_conv, d_pm);
+        { KTimer kt(d, s, SWD_K_SELECT);
+          select_kernel<<<std::max(1, std::min<int>((int)B, d->num_sm * 8)), 128, 0, s>>>(d->ws, d->L, d->P, d->n, d_corr, d_conv, d_pm); }
         d->ctr.kernel_launches++;
     }
     CK(cudaGetLastError());
@@ -446,6 +474,26 @@ extern "C" int swd_osd_last_outputs(swd_decoder *d, int64_t B, uint8_t *bp_dec, 
     if (osdw) CK(cudaMemcpy(osdw, d->ow.osdw, (size_t)B * n, cudaMemcpyDeviceToHost));
     if (lpr) CK(cudaMemcpy(lpr, d->ow.lpr, (size_t)B * n * 32, cudaMemcpyDeviceToHost));
     if (bp_iteration) CK(cudaMemcpy(bp_iteration, d->ow.bp_iter, (size_t)B * 4, cudaMemcpyDeviceToHost));
+    return SWD_OK;
+}
+
+extern "C" int swd_set_profiling(swd_decoder *d, int enable) {
+    if (!d) return SWD_ERR_INVALID;
+    d->profiling = enable != 0;
+    return SWD_OK;
+}
+extern "C" int swd_get_kernel_times(swd_decoder *d, double *ms, uint64_t *launches) {
+    if (!d || !ms || !launches) return SWD_ERR_INVALID;
+    CK(cudaSetDevice(d->device));
+    CK(cudaDeviceSynchronize());
+    for (int k = 0; k < SWD_K_COUNT; k++) { ms[k] = 0.0; launches[k] = 0; }
+    for (auto &e : d->ev_used) {
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, e.a, e.b));
+        ms[e.k] += t; launches[e.k]++;
+        d->ev_free.push_back(e.a); d->ev_free.push_back(e.b);
+    }
+    d->ev_used.clear();
     return SWD_OK;
 }
 

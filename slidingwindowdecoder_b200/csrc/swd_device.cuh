@@ -302,7 +302,7 @@ __device__ __forceinline__ void init_msgs(Ctx &c) {
 // BPGD::min_sum_log (bpgd.cpp:97-197) on the shortened graph, whole CTA.
 // h[i][s]: posterior history of VN (tid + i*T), slot s = iteration % 4.  Returns 1 on convergence.
 template <int VPT, int DMAX>
-__device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter, u64 &edge_iters) {
+__device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter, u64 &edge_iters, u32 &vn_iters, u32 &cn_iters) {
     const int T = blockDim.x, tid = threadIdx.x;
     const double fpos = c.factor, fneg = -c.factor;
     for (int it = 0; it < num_iter; it++) {
@@ -311,6 +311,7 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
             c.upar[r] = 0;
             const int cm = c.cn_mask[r];
             if (cm < 0) continue;
+            cn_iters++;
             const int p0 = c.coff[r], p1 = c.coff[r + 1];
             double m1 = SWD_BIG, m2 = SWD_BIG; int arg = -1, par = cm;
             for (int p = p0; p < p1; p++) {
@@ -347,7 +348,7 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
                 double s = 0.0;
 #pragma unroll
                 for (int k = DMAX - 1; k >= 0; k--) if (k < d) { c.msg[pp[k]] = pre[k] + s; s += cc[k]; }
-                edge_iters += d;
+                edge_iters += d; vn_iters++;
             }
         }
         __syncthreads();

@@ -317,6 +317,7 @@ path_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int phase) {
     const int npaths = (phase == 0) ? ((P.kind == SWD_KIND_BPGDG && P.multi_thread) ? 1 + P.n_tree : 1) : P.n_side;
     const long long total = (long long)npaths * count;
     u64 edge_iters = 0, bp_calls = 0, paths_run = 0;
+    u32 vn_iters = 0, cn_iters = 0;
 
     for (;;) {
         __syncthreads();
@@ -395,7 +396,7 @@ path_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int phase) {
             if (!stage_end) {
                 if (role == R_MAIN) c.A_sum = (depth == 0) ? -16 : -12;                          // :631
                 if (role == R_TREE && stage == 0 && depth > 0 && !on_side) c.A_sum = -12;         // :450
-                conv = bp_run<VPT, DMAX>(c, h, P.num_iter, edge_iters); bp_calls++;
+                conv = bp_run<VPT, DMAX>(c, h, P.num_iter, edge_iters, vn_iters, cn_iters); bp_calls++;
                 steps++;
                 if (role == R_GD) {
                     // bpgd_decoder.gd (pyx:540-553) with decimate_vn_reliable (bpgd.cpp:258-286)
@@ -458,6 +459,10 @@ path_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int phase) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) edge_iters += __shfl_xor_sync(FULLMASK, edge_iters, o);
     if (lane == 0 && edge_iters) atomicAdd(&ws.stats[1], edge_iters);
+    u64 vi = vn_iters, ci = cn_iters;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { vi += __shfl_xor_sync(FULLMASK, vi, o); ci += __shfl_xor_sync(FULLMASK, ci, o); }
+    if (lane == 0) { if (vi) atomicAdd(&ws.stats[6], vi); if (ci) atomicAdd(&ws.stats[7], ci); }
     if (tid == 0) { if (paths_run) atomicAdd(&ws.stats[2], paths_run); if (bp_calls) atomicAdd(&ws.stats[3], bp_calls); }
 }
 

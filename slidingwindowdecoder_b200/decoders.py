@@ -134,6 +134,16 @@ class _window_decoder_base:
         _lib.check(self._lib.swd_get_counters(self._handle, C.byref(c)), "swd_get_counters")
         return c.as_dict()
 
+    def set_profiling(self, enable=True):
+        _lib.check(self._lib.swd_set_profiling(self._handle, int(bool(enable))), "swd_set_profiling")
+
+    def kernel_times(self):
+        """{kernel class: (total ms, launches)} since the last call (needs set_profiling(True))."""
+        ms = (C.c_double * 8)()
+        ln = (C.c_uint64 * 8)()
+        _lib.check(self._lib.swd_get_kernel_times(self._handle, ms, ln), "swd_get_kernel_times")
+        return {k: (float(ms[i]), int(ln[i])) for i, k in enumerate(_lib.KERNEL_CLASSES)}
+
     def reset_counters(self):
         _lib.check(self._lib.swd_reset_counters(self._handle), "swd_reset_counters")
 

@@ -1,0 +1,127 @@
+"""Sliding-window driver: the per-window loop of the reference (guessing.py:141-227, osd.py:134-179)
+re-hosted for batched decoding on one B200.
+
+For every window: extract the window syndrome of ALL shots, decode them with one batched call,
+commit the first F rounds of the correction, update the remaining syndrome with the sparse
+equivalent of `new_det = (det + total_e_hat @ chk.T) % 2`, slide.  Shot data stays on the device
+between windows; PyTorch is used only to own device buffers and streams.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .decoders import bpgdg_decoder, osd_window
+from .windows import WindowPlan
+
+
+def sample_dem(chk, obs, priors, shots, rng):
+    """What stim's CompiledDemSampler draws (guessing.py:129-130): independent Bernoulli per DEM column.
+    -> (det [shots, num_det] uint8, obs [shots, num_obs] uint8, err [shots, num_col] uint8)"""
+    err = (rng.random((shots, len(priors))) < priors[None, :]).astype(np.uint8)
+    e = err.astype(np.float32)
+    det = (np.asarray(e @ chk.T.astype(np.float32)) % 2).astype(np.uint8)
+    ob = (np.asarray(e @ obs.T.astype(np.float32)) % 2).astype(np.uint8)
+    return det, ob, err
+
+
+class SlidingWindowDecoder:
+    """Holds one decoder per distinct window matrix (the reference rebuilds one per window,
+    guessing.py:160-174) and the device-side window bookkeeping."""
+
+    def __init__(self, plan: WindowPlan, decoder="gdg", device=0, last_window_kwargs=None, **decoder_kwargs):
+        import torch
+        self.torch = torch
+        self.plan = plan
+        self.device = int(device)
+        self.lib = _lib.load()
+        chk = plan.chk.tocsc(); chk.sort_indices()
+        obs = plan.obs.tocsc(); obs.sort_indices()
+        self.num_det, self.num_col = chk.shape
+        self.num_obs = obs.shape[0]
+        self._chk_cp = np.ascontiguousarray(chk.indptr, dtype=np.int32)
+        self._chk_ri = np.ascontiguousarray(chk.indices, dtype=np.int32)
+        self._obs_cp = np.ascontiguousarray(obs.indptr, dtype=np.int32)
+        self._obs_ri = np.ascontiguousarray(obs.indices, dtype=np.int32)
+        i32p = C.POINTER(C.c_int32)
+        self._win = C.c_void_p()
+        st = self.lib.swd_window_create(self.device, self.num_det, self.num_col, self._chk_cp.ctypes.data_as(i32p),
+                                        self._chk_ri.ctypes.data_as(i32p), self.num_obs, self._obs_cp.ctypes.data_as(i32p),
+                                        self._obs_ri.ctypes.data_as(i32p), C.byref(self._win))
+        _lib.check(st, "swd_window_create")
+        cls = {"gdg": bpgdg_decoder, "osd": osd_window}.get(decoder, decoder)
+        self.decoders = []
+        cache = []
+        for w in plan.windows:
+            kw = dict(decoder_kwargs)
+            if w.last and last_window_kwargs:
+                kw.update(last_window_kwargs)
+            found = None
+            for (m0, p0, kw0, d0) in cache:
+                if kw0 == kw and m0.shape == w.mat.shape and m0.nnz == w.mat.nnz and (m0 != w.mat).nnz == 0 and np.array_equal(p0, w.prior):
+                    found = d0
+                    break
+            if found is None:
+                found = cls(w.mat, channel_probs=w.prior, device=self.device, **kw)
+                cache.append((w.mat, w.prior, kw, found))
+            self.decoders.append(found)
+        self._counts = None
+
+    def __del__(self):
+        w = getattr(self, "_win", None)
+        if w is not None and w.value:
+            self.lib.swd_window_destroy(w)
+            self._win = C.c_void_p()
+
+    def unique_decoders(self):
+        seen, out = set(), []
+        for d in self.decoders:
+            if id(d) not in seen:
+                seen.add(id(d)); out.append(d)
+        return out
+
+    def decode_device(self, det, obs, return_corrections=False, window_events=None):
+        """det [B, num_det], obs [B, num_obs]: torch CUDA uint8 tensors, MODIFIED IN PLACE into the residual
+        syndrome / residual observables.  Returns dict with device tensors:
+          counts uint64[2] = (flagged shots, failed shots), window_unconverged int64[num_win]."""
+        torch = self.torch
+        B = det.shape[0]
+        stream = C.c_void_p(torch.cuda.current_stream(det.device).cuda_stream)
+        unconv = []
+        total = torch.zeros((B, self.num_col), dtype=torch.uint8, device=det.device) if return_corrections else None
+        for w, dec in zip(self.plan.windows, self.decoders):
+            m = w.row1 - w.row0
+            synd = torch.empty((B, m), dtype=torch.uint8, device=det.device)
+            _lib.check(self.lib.swd_window_extract(self._win, det.data_ptr(), B, w.row0, m, synd.data_ptr(), stream), "extract")
+            if window_events is not None:
+                window_events[w.index][0].record()
+            corr, conv = dec.decode_batch(synd)
+            if window_events is not None:
+                window_events[w.index][1].record()
+            n_win = corr.shape[1]
+            _lib.check(self.lib.swd_window_commit(self._win, corr.data_ptr(), B, n_win, w.col0, w.ncommit, det.data_ptr(),
+                                                  obs.data_ptr() if self.num_obs else None, stream), "commit")
+            unconv.append((B - conv.sum(dtype=torch.int64)))
+            if return_corrections:
+                total[:, w.col0:w.col0 + w.ncommit] = corr[:, :w.ncommit]
+        counts = torch.zeros(2, dtype=torch.int64, device=det.device)
+        _lib.check(self.lib.swd_window_count_failures(self._win, det.data_ptr(), obs.data_ptr() if self.num_obs else None, B,
+                                                      counts.data_ptr(), stream), "count")
+        out = dict(counts=counts, window_unconverged=torch.stack(unconv))
+        if return_corrections:
+            out["total_e_hat"] = total
+        return out
+
+    def decode(self, det_data, obs_data, return_corrections=False):
+        """Host entry point (numpy uint8 in, python ints out): H2D copy, all windows, D2H of the counters."""
+        torch = self.torch
+        dev = torch.device("cuda", self.device)
+        det = torch.from_numpy(np.ascontiguousarray(det_data, dtype=np.uint8)).to(dev, non_blocking=True)
+        obs = torch.from_numpy(np.ascontiguousarray(obs_data, dtype=np.uint8)).to(dev, non_blocking=True)
+        out = self.decode_device(det, obs, return_corrections)
+        counts = out["counts"].cpu().numpy()
+        res = dict(shots=int(det.shape[0]), flagged=int(counts[0]), failed=int(counts[1]),
+                   window_unconverged=out["window_unconverged"].cpu().numpy().tolist())
+        if return_corrections:
+            res["total_e_hat"] = out["total_e_hat"].cpu().numpy()
+        return res

@@ -1,0 +1,45 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def load_golden(name):
+    """-> dict with mat (csc), priors, synd [B, m] uint8, kwargs dict and the recorded reference outputs."""
+    from scipy.sparse import csc_matrix
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    m, n = (int(x) for x in z["shape"])
+    indptr, indices = z["indptr"], z["indices"]
+    mat = csc_matrix((np.ones(len(indices), dtype=np.uint8), indices, indptr), shape=(m, n))
+    out = {k: z[k] for k in z.files}
+    out["mat"] = mat
+    out["synd"] = np.unpackbits(z["synd"], axis=1)[:, :m]
+    out["kwargs"] = eval(str(z["kwargs"]), {"__builtins__": {}}, {"dict": dict, "True": True, "False": False, "None": None})
+    for k in ("dec", "bp_decoding", "osd0"):
+        if k in out:
+            out[k] = np.unpackbits(out[k], axis=1)[:, :n]
+    return out
+
+
+GOLDEN_GDG = ["c1_gdg_sim_mt1", "c1_gdg_default_mt1", "c1_gdg_sim_mt0", "c1_gdg_default_mt0",
+              "c2_w0_gdg_mt1", "c2_w1_gdg_mt1", "c2_w4_gdg_mt1", "c2_w0_gdg_mt0", "c2_w1_gdg_mt0", "c2_w4_gdg_mt0",
+              "c3_w0_gdg_mt1", "c3_w5_gdg_mt1", "c3_w10_gdg_mt1"]
+GOLDEN_OSD = ["c1_osdw_osd_00", "c1_osdw_osd_cs10", "c1_osdw_osd_e6", "c2_w0_osdw_cs10", "c2_w1_osdw_cs10",
+              "c2_w4_osdw_cs10", "c3_w5_osdw_cs10"]
+
+
+@pytest.fixture(scope="session")
+def oracle_mod():
+    from oracle import oracle
+    oracle.lib()
+    return oracle

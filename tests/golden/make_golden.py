@@ -1,0 +1,155 @@
+"""Generates tests/golden/*.npz from the REAL reference (gongaa/SlidingWindowDecoder).
+
+Run in the build container only (it needs /root/reference):
+    python tests/golden/make_golden.py
+It copies the reference to a scratch directory under /tmp, applies the two mechanical patches
+needed by Cython 3.3 / numpy 2 (np.int_t -> np.int64_t, long( -> int(), builds the Cython
+extensions there with /usr/bin/gcc, imports them and records decode() outputs on seeded inputs.
+Nothing of the reference is copied into this repository; only inputs and outputs are stored.
+Inputs are produced by this repository's own host code (codes.py / dem.py / windows.py), so each
+fixture carries the window matrix (CSC), the priors and the syndromes it was generated with.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+SCRATCH = "/tmp/refbuild/ref"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def build_reference():
+    if not os.path.exists(os.path.join(SCRATCH, "src")) or not any(f.endswith(".so") and "osd_window" in f for f in os.listdir(os.path.join(SCRATCH, "src"))):
+        os.makedirs(os.path.dirname(SCRATCH), exist_ok=True)
+        subprocess.run(f"rm -rf {SCRATCH} && cp -r /root/reference {SCRATCH} && chmod -R u+w {SCRATCH}", shell=True, check=True)
+        subprocess.run("rm -f src/bp_guessing_decoder.cpp src/osd_window.cpp src/bp4_osd.cpp src/mod2sparse.c && "
+                       "sed -i 's/np\\.int_t/np.int64_t/g' src/*.pyx src/*.pxd && sed -i 's/= long(/= int(/g' src/*.pyx && "
+                       "CC=/usr/bin/gcc CXX=/usr/bin/g++ LDSHARED='/usr/bin/g++ -shared' python3 setup.py build_ext --inplace > build.log 2>&1",
+                       shell=True, check=True, cwd=SCRATCH)
+    sys.path.insert(0, SCRATCH)
+
+
+def csc_of(mat):
+    from scipy.sparse import csc_matrix
+    A = csc_matrix(mat); A.sort_indices()
+    return A.shape, A.indptr.astype(np.int32), A.indices.astype(np.int32)
+
+
+def save(name, mat, priors, synd, kwargs, **outs):
+    shape, indptr, indices = csc_of(mat)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), shape=np.array(shape), indptr=indptr, indices=indices,
+                        priors=np.asarray(priors, dtype=np.float64), synd=np.packbits(np.asarray(synd, dtype=np.uint8), axis=1),
+                        kwargs=np.array(repr(kwargs)), **outs)
+    print("wrote", name, "shots", len(synd), {k: v.shape for k, v in outs.items()})
+
+
+def run_gdg(cls, mat, priors, synd, kwargs):
+    dec = cls(mat, channel_probs=priors, **kwargs)
+    out = np.zeros((len(synd), mat.shape[1]), dtype=np.uint8)
+    conv = np.zeros(len(synd), dtype=np.uint8)
+    for i, s in enumerate(synd):
+        out[i] = dec.decode(s)
+        conv[i] = int(dec.converge)
+    return np.packbits(out, axis=1), conv
+
+
+def run_osd(cls, mat, priors, synd, kwargs):
+    dec = cls(mat, channel_probs=priors, **kwargs)
+    n = mat.shape[1]
+    out = np.zeros((len(synd), n), dtype=np.uint8); bp = np.zeros_like(out); o0 = np.zeros_like(out)
+    conv = np.zeros(len(synd), dtype=np.uint8); pm = np.zeros(len(synd)); it = np.zeros(len(synd), dtype=np.int32)
+    lpr = np.zeros((len(synd), n, 4))
+    for i, s in enumerate(synd):
+        out[i] = dec.decode(s); conv[i] = int(dec.converge); pm[i] = dec.min_pm; it[i] = dec.bp_iteration
+        bp[i] = dec.bp_decoding
+        if not conv[i]:
+            o0[i] = dec.osd0_decoding
+        lpr[i] = dec.log_prob_ratios
+    return dict(dec=np.packbits(out, axis=1), conv=conv, min_pm=pm, bp_iteration=it, bp_decoding=np.packbits(bp, axis=1),
+                osd0=np.packbits(o0, axis=1), lpr_first8=lpr[:8])
+
+
+def main():
+    build_reference()
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 2)      # the reference prints "Error setting thread affinity" per thread on small hosts
+    from src.bp_guessing_decoder import bpgdg_decoder, bpgd_decoder
+    from src.osd_window import osd_window
+    from slidingwindowdecoder_b200.codes import bb_code
+    from slidingwindowdecoder_b200.dem import bb_memory_circuit, detector_error_model, dem_to_check_matrices
+    from slidingwindowdecoder_b200.windows import build_windows
+    from slidingwindowdecoder_b200.sliding_window import sample_dem
+
+    # ---- C1: [[72,12,6]] code capacity, p = 0.05 (non-uniform priors so that pm ties cannot occur)
+    code, A, B = bb_code(72)
+    H = code.hx
+    rng = np.random.default_rng(20261017)
+    shots = 1500
+    err = (rng.random((shots, code.N)) < 0.05).astype(np.int64)
+    synd = (err @ H.T % 2).astype(np.uint8)
+    priors = 0.05 * (1 + 0.3 * rng.random(code.N))
+    sim = dict(max_iter_per_step=6, gdg_factor=0.625, max_step=40, max_tree_depth=4, max_side_depth=20, max_tree_branch_step=30,
+               max_side_branch_step=20, low_error_mode=True, max_iter=24, ms_scaling_factor=0.625, new_n=72)
+    for mt in (True, False):
+        kw = dict(sim, multi_thread=mt)
+        d, c = run_gdg(bpgdg_decoder, H, priors, synd, kw)
+        save(f"c1_gdg_sim_mt{int(mt)}", H, priors, synd, kw, dec=d, conv=c)
+        kw = dict(max_iter=8, multi_thread=mt)
+        d, c = run_gdg(bpgdg_decoder, H, priors, synd, kw)
+        save(f"c1_gdg_default_mt{int(mt)}", H, priors, synd, kw, dec=d, conv=c)
+    kw = dict(max_iter=8, ms_scaling_factor=1.0, max_iter_per_step=6, max_step=25, gd_factor=1.0)
+    d, c = run_gdg(bpgd_decoder, H, priors, synd, kw)
+    save("c1_bpgd", H, priors, synd, kw, dec=d, conv=c)
+    for meth, order in (("osd_0", 0), ("osd_cs", 10), ("osd_e", 6)):
+        kw = dict(pre_max_iter=8, post_max_iter=50, ms_scaling_factor=0.8, osd_method=meth, osd_order=order)
+        save(f"c1_osdw_{meth}{order}", H, priors, synd, kw, **run_osd(osd_window, H, priors, synd, kw))
+    # uniform priors (the published configuration): converge flag only is exact (ties), keep for statistics
+    pri_u = np.ones(code.N) * 0.05
+    kw = dict(sim, multi_thread=False)
+    d, c = run_gdg(bpgdg_decoder, H, pri_u, synd, kw)
+    save("c1_gdg_sim_uniform_mt0", H, pri_u, synd, kw, dec=d, conv=c)
+
+    # ---- C2: [[72,12,6]] circuit level p = 0.003, 6 rounds, (3,1): windows 0 (first), 1 (middle), 4 (last)
+    circ = bb_memory_circuit(code, A, B, 0.003, 6, z_basis=True)
+    chk, obs, pri = dem_to_check_matrices(detector_error_model(circ))
+    plan = build_windows(chk, obs, pri, code.N, W=3, F=1, method=1)
+    det, ob, _ = sample_dem(plan.chk, plan.obs, plan.priors, 3000, np.random.default_rng(72))
+    for wi in (0, 1, len(plan.windows) - 1):
+        w = plan.windows[wi]
+        s = det[:, w.row0:w.row1]
+        keep = np.nonzero(s.any(axis=1))[0][:600]         # non-trivial syndromes
+        s = s[keep]
+        kw = dict(pre_max_iter=8, post_max_iter=200, ms_scaling_factor=1.0, osd_method="osd_cs", osd_order=10)
+        save(f"c2_w{wi}_osdw_cs10", w.mat, w.prior, s, kw, **run_osd(osd_window, w.mat, w.prior, s, kw))
+        kw = dict(max_iter=8, multi_thread=True)
+        d, c = run_gdg(bpgdg_decoder, w.mat, w.prior, s, kw)
+        save(f"c2_w{wi}_gdg_mt1", w.mat, w.prior, s, kw, dec=d, conv=c)
+        kw = dict(max_iter=8, multi_thread=False)
+        d, c = run_gdg(bpgdg_decoder, w.mat, w.prior, s, kw)
+        save(f"c2_w{wi}_gdg_mt0", w.mat, w.prior, s, kw, dec=d, conv=c)
+
+    # ---- C3: [[144,12,12]] circuit level p = 0.003, 12 rounds, (3,1): windows 0 and 5, GDG
+    code, A, B = bb_code(144)
+    circ = bb_memory_circuit(code, A, B, 0.003, 12, z_basis=True)
+    chk, obs, pri = dem_to_check_matrices(detector_error_model(circ))
+    plan = build_windows(chk, obs, pri, code.N, W=3, F=1, method=1)
+    det, ob, _ = sample_dem(plan.chk, plan.obs, plan.priors, 1500, np.random.default_rng(144))
+    for wi in (0, 5, len(plan.windows) - 1):
+        w = plan.windows[wi]
+        s = det[:, w.row0:w.row1]
+        keep = np.nonzero(s.any(axis=1))[0][:400]
+        s = s[keep]
+        kw = dict(max_iter=8, multi_thread=True)
+        d, c = run_gdg(bpgdg_decoder, w.mat, w.prior, s, kw)
+        save(f"c3_w{wi}_gdg_mt1", w.mat, w.prior, s, kw, dec=d, conv=c)
+    w = plan.windows[5]
+    s = det[:, w.row0:w.row1]; s = s[np.nonzero(s.any(axis=1))[0][:200]]
+    kw = dict(pre_max_iter=8, post_max_iter=100, ms_scaling_factor=1.0, osd_method="osd_cs", osd_order=10)
+    save("c3_w5_osdw_cs10", w.mat, w.prior, s, kw, **run_osd(osd_window, w.mat, w.prior, s, kw))
+
+
+if __name__ == "__main__":
+    main()

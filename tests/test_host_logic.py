@@ -1,0 +1,97 @@
+"""Host-side logic that needs no GPU: DEM builder known answers, window geometry, C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def dem144():
+    from slidingwindowdecoder_b200.codes import bb_code
+    from slidingwindowdecoder_b200.dem import bb_memory_circuit, detector_error_model, dem_to_check_matrices
+    code, A, B = bb_code(144)
+    chk, obs, pri = dem_to_check_matrices(detector_error_model(bb_memory_circuit(code, A, B, 0.003, 4, z_basis=True)))
+    return code, chk, obs, pri
+
+
+def test_dem_known_answers(dem144):
+    """Round Analysis.ipynb:15,322 and Sliding Window GDG.ipynb:485 (outputs of real stim)."""
+    from slidingwindowdecoder_b200.windows import build_windows
+    code, chk, obs, pri = dem144
+    assert chk.shape == (360, 3024)
+    rw = np.asarray(chk.sum(axis=1)).ravel()
+    cw = np.asarray(chk.sum(axis=0)).ravel()
+    assert (rw.max(), cw.max(), rw.min(), cw.min()) == (35, 6, 16, 2)
+    plan = build_windows(chk, obs, pri, code.N, W=3, F=1, method=1)
+    assert plan.anchors == [(0, 0), (72, 648), (144, 1368), (216, 2088), (288, 2808), (360, 3024)]
+    assert abs(plan.noisy_prior[0] - 0.027499817877069083) < 1e-16
+    assert [w.mat.shape for w in plan.windows] == [(216, 1656), (216, 1728), (216, 1656)]
+    assert [w.mat.nnz for w in plan.windows] == [5544, 5976, 5904]
+    assert [w.ncommit for w in plan.windows] == [648, 720, 1656]
+
+
+def test_dem_sampling_consistency(dem144):
+    from slidingwindowdecoder_b200.sliding_window import sample_dem
+    code, chk, obs, pri = dem144
+    det, ob, err = sample_dem(chk, obs, pri, 50, np.random.default_rng(3))
+    assert np.array_equal(det, np.asarray((chk @ err.T.astype(np.int64)).T % 2).astype(np.uint8))
+
+
+def test_bb_codes():
+    from slidingwindowdecoder_b200.codes import bb_code, gf2_rank
+    for N, K in ((72, 12), (144, 12)):
+        code, A, B = bb_code(N)
+        assert code.N == N and code.K == K
+        assert not ((code.hx @ code.lz.T) % 2).any() and not ((code.hz @ code.lx.T) % 2).any()
+        assert gf2_rank(np.vstack([code.hz, code.lz])) == code.rank_hz + K
+
+
+def test_cabi_exports_every_declared_symbol():
+    from slidingwindowdecoder_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "swd_b200.h")).read()
+    declared = set(re.findall(r"\b(swd_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/swd_b200.h but not exported"
+    assert set(_lib.EXPORTS) == declared
+    assert b"sm_100a" in lib.swd_version()
+    assert lib.swd_strerror(-2) == b"unsupported configuration"
+
+
+def test_config_struct_matches_header():
+    from slidingwindowdecoder_b200 import _lib
+    # field order of swd_config in the header == ctypes mirror
+    header = open(os.path.join(ROOT, "include", "swd_b200.h")).read()
+    body = header[header.index("typedef struct swd_config {"):header.index("} swd_config;")]
+    names = re.findall(r"^\s*(?:int|double)\s+([a-z_]+);", body, flags=re.M)
+    assert names == [f for f, _ in _lib.SwdConfig._fields_]
+    body = header[header.index("typedef struct swd_counters {"):header.index("} swd_counters;")]
+    names = re.findall(r"^\s*uint64_t\s+([a-z_]+);", body, flags=re.M)
+    assert names == [f for f, _ in _lib.SwdCounters._fields_]
+
+
+def test_constructor_argument_errors_need_no_gpu():
+    from slidingwindowdecoder_b200 import bpgdg_decoder, osd_window
+    H = np.eye(4, dtype=np.uint8)
+    with pytest.raises(TypeError):
+        bpgdg_decoder([[1, 0], [0, 1]], channel_probs=[0.1, 0.1])
+    with pytest.raises(ValueError):
+        bpgdg_decoder(H, channel_probs=[0.1] * 3)
+    with pytest.raises(ValueError):
+        osd_window(H, channel_probs=[0.1] * 4, osd_method="nonsense")
+
+
+def test_oracle_header_says_test_infrastructure():
+    for f in ("swd_oracle.h", "swd_oracle.c", "oracle.py"):
+        assert "TEST INFRASTRUCTURE ONLY" in open(os.path.join(ROOT, "oracle", f)).read()
+    # the product package never references the oracle
+    pkg = os.path.join(ROOT, "slidingwindowdecoder_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                assert "oracle" not in open(os.path.join(dirpath, fn)).read().lower(), fn
