@@ -210,6 +210,7 @@ extern "C" void swd_destroy(swd_decoder *d) {
     if (d->h_pin) cudaFreeHost(d->h_pin);
     for (auto &e : d->ev_used) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto &e : d->ev_free) cudaEventDestroy(e);
+    osd_free_outputs(&d->ow);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
 }
@@ -376,14 +377,15 @@ static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_cor
     const int g1 = (int)std::min<long long>(B, d->grid1);
     const int full_hist = (c.kind == SWD_KIND_OSD_WINDOW) ? 1 : 0;
     int *iter_out = (c.kind == SWD_KIND_OSD_WINDOW) ? d->ow.bp_iter + chunk_base : nullptr;
+    double *lpr_out = (c.kind == SWD_KIND_OSD_WINDOW) ? d->ow.lpr + (size_t)chunk_base * d->n * 4 : nullptr;
     {
     KTimer kt(d, s, SWD_K_PRE_BP);
     if (d->dmax == 8)
         pre_bp_kernel<8><<<g1, d->T1, d->PRE.total, s>>>(d->g, d_synd, B, c.max_iter, c.ms_scaling_factor, d_corr, d_conv, d->ws,
-                                                        d->hscratch, full_hist, d->PRE, iter_out);
+                                                        d->hscratch, full_hist, d->PRE, iter_out, lpr_out);
     else
         pre_bp_kernel<16><<<g1, d->T1, d->PRE.total, s>>>(d->g, d_synd, B, c.max_iter, c.ms_scaling_factor, d_corr, d_conv, d->ws,
-                                                         d->hscratch, full_hist, d->PRE, iter_out);
+                                                         d->hscratch, full_hist, d->PRE, iter_out, lpr_out);
     }
     d->ctr.kernel_launches++;
     if (d_pm) {
@@ -400,8 +402,10 @@ static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_cor
     const int g3 = d->grid3;
     const int phases = (c.kind == SWD_KIND_BPGDG && c.multi_thread && d->P.n_side > 0) ? 2 : 1;
     if (c.kind == SWD_KIND_OSD_WINDOW) {
+        KTimer kt(d, s, SWD_K_OSD);
         int st = osd_launch(d->g, d_synd, d->ws, d->L, d->PS, d->P, d->OS, d->ow, d->dmax, d->T3, g3, smem3, d->T5, d->grid5,
-                            c.osd_method, c.osd_order, d->rank, d_corr, d_conv, d_pm, chunk_base, s, &d->ctr.kernel_launches);
+                            c.osd_method, c.osd_order, d->rank, d_corr, d_conv, d_pm, B, chunk_base, s, &d->ctr.kernel_launches,
+                            d->ow.need_osd + d->cap);
         if (st) { set_err("osd launch failed"); return st; }
     } else {
         for (int ph = 0; ph < phases; ph++) {

@@ -302,7 +302,8 @@ __device__ __forceinline__ void init_msgs(Ctx &c) {
 // BPGD::min_sum_log (bpgd.cpp:97-197) on the shortened graph, whole CTA.
 // h[i][s]: posterior history of VN (tid + i*T), slot s = iteration % 4.  Returns 1 on convergence.
 template <int VPT, int DMAX>
-__device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter, u64 &edge_iters, u32 &vn_iters, u32 &cn_iters) {
+__device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter, u64 &edge_iters, u32 &vn_iters, u32 &cn_iters,
+                                      int *iters_done = nullptr) {
     const int T = blockDim.x, tid = threadIdx.x;
     const double fpos = c.factor, fneg = -c.factor;
     for (int it = 0; it < num_iter; it++) {
@@ -360,8 +361,9 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
             c.flip[r] = (u8)f;
             mism |= f;
         }
-        if (!__syncthreads_or(mism)) return 1;
+        if (!__syncthreads_or(mism)) { if (iters_done) *iters_done = it + 1; return 1; }
     }
+    if (iters_done) *iters_done = num_iter > 0 ? num_iter : 0;
     return 0;
 }
 

@@ -24,7 +24,7 @@ template <int DMAX>
 __global__ void __launch_bounds__(512)
 pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter, double alpha,
               u8 *__restrict__ dec_out, u8 *__restrict__ conv_out, Workspace ws, double *hscratch,
-              int full_hist, PreSmem S, int *iter_out) {
+              int full_hist, PreSmem S, int *iter_out, double *lpr_out) {
     extern __shared__ __align__(16) unsigned char smem[];
     double *msg = (double *)(smem + S.off_msg);
     u32 *upar = (u32 *)(smem + S.off_upar);
@@ -95,21 +95,27 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
             if (!conv) { int slot = atomicAdd(&ws.counters[0], 1); ws.gdg_list[slot] = (int)shot; misc[0] = slot; }
         }
         __syncthreads();
-        if (!conv) {
+        if (!conv || lpr_out) {
             const int slot = misc[0];
             for (int v = tid; v < n; v += T) {
                 double h4[4];
 #pragma unroll
                 for (int s = 0; s < 4; s++) {
-                    // slots never written in this call are 0 (fresh ring); with full_hist all executed
-                    // iterations were stored, otherwise only the last four.
-                    bool written = (s < max_iter);
+                    // slots never written in this call are 0 (fresh ring); `it` iterations were executed
+                    // (with full_hist all of them were stored, otherwise only the last four of max_iter).
+                    const bool written = (s < it);
                     h4[s] = written ? hs[(size_t)s * n + v] : 0.0;
                 }
-                ws.sum[(size_t)slot * n + v] = ((h4[0] + h4[1]) + h4[2]) + h4[3];
-                if (ws.hist) {
+                if (!conv) {
+                    ws.sum[(size_t)slot * n + v] = ((h4[0] + h4[1]) + h4[2]) + h4[3];
+                    if (ws.hist) {
 #pragma unroll
-                    for (int s = 0; s < 4; s++) ws.hist[((size_t)slot * n + v) * 4 + s] = h4[s];
+                        for (int s = 0; s < 4; s++) ws.hist[((size_t)slot * n + v) * 4 + s] = h4[s];
+                    }
+                }
+                if (lpr_out) {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) lpr_out[((size_t)shot * n + v) * 4 + s] = h4[s];
                 }
             }
         }
@@ -163,6 +169,8 @@ sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayo
         __syncthreads();
         block_bitonic_sort(key, idx, NP2);
         for (int j = tid; j < n; j += T) posof[idx[j]] = (u16)j;
+        if (P.kind == SWD_KIND_OSD_WINDOW)          // decided-0 key of the dropped columns (osd_window.pyx:208-209)
+            for (int j = nn + tid; j < n; j += T) ws.sum[(size_t)slot * n + idx[j]] = 1000.0;
         for (int j = tid; j < nn; j += T) {
             const int c = idx[j];
             col[j] = (u16)c; prior[j] = g.llr[c];

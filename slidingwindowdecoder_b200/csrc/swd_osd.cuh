@@ -1,12 +1,480 @@
-// swd_osd.cuh — osd_window post-BP + bit-packed GF(2) OSD (placeholder until the kernels land).
+// swd_osd.cuh — window OSD on the device (osd_window.pyx:201-284 + mod2sparse_extra.cpp:78-376).
+//
+// The reference runs a sparse LU with fill-in on linked lists, then k + w(w-1)/2 (CS) or 2^w (E)
+// triangular re-solves.  Here one CTA per shot keeps the m x m row-transform T bit-packed in shared
+// memory (64-bit words, column-major), scans the columns in LLR order, and for each new column c
+// computes the reduced column v = T h_c as the XOR of <= 16 words-vectors, picks the first free row
+// as pivot and applies the rank-1 update T += (v - e_i) (e_i^T T).  The syndrome rides along as an
+// extra column, so OSD-0 is read off directly; every higher-order candidate is y0 ^ v_t1 ^ v_t2 ...
+// and its path metric is an ordered fp64 sum (ascending column index, as the reference).
 #pragma once
 #include "swd_kernels.cuh"
-struct OsdSmem { int total; };
-struct OsdWork { u8 *bp_dec = nullptr, *osd0 = nullptr, *osdw = nullptr; double *lpr = nullptr; int *bp_iter = nullptr; long long out_cap = 0; };
-static inline size_t osd_bytes_per_shot(int m, int n) { return 0; }
-static inline void osd_bind(OsdWork *, unsigned char *, long long, int, int) {}
-static inline int osd_reserve_outputs(OsdWork *, long long, int) { return -2; }
-static inline int osd_setup(int, int, int, int, int, int, int, OsdSmem *, int *, int *) { return -2; }
-static inline int osd_launch(const GraphDev &, const u8 *, const Workspace &, const SubLayout &, const PathSmem &, const GdgDev &,
-                             const OsdSmem &, const OsdWork &, int, int, int, size_t, int, int, int, int, int, u8 *, u8 *, double *,
-                             long long, cudaStream_t, uint64_t *) { return -2; }
+
+#define SWD_OSD_0  0
+#define SWD_OSD_E  1
+#define SWD_OSD_CS 2
+
+struct OsdSmem {
+    int np2, W64, k;
+    int off_key, off_idx, off_tcol, off_vt, off_colinfo, off_ent, off_vbuf, off_piv, off_scan, off_wt, off_red, off_misc, off_ybest;
+    int total;
+};
+
+struct OsdWork {
+    // outputs of the last batch (device), for the osd_window read-only properties
+    u8 *bp_dec = nullptr, *osd0 = nullptr, *osdw = nullptr;
+    double *lpr = nullptr;
+    int *bp_iter = nullptr;
+    long long out_cap = 0;
+    // per-chunk scratch (inside the workspace block)
+    u8 *need_osd = nullptr;         // [cap] 1 if slot must run OSD
+};
+
+static inline size_t osd_bytes_per_shot(int m, int n) { return 2; }   // need_osd[cap] + in_list[cap]
+static inline void osd_bind(OsdWork *ow, unsigned char *base, long long cap, int m, int n) { ow->need_osd = base; }
+
+static inline int osd_reserve_outputs(OsdWork *ow, long long B, int n) {
+    if (B <= ow->out_cap) return 0;
+    if (ow->bp_dec) { cudaFree(ow->bp_dec); cudaFree(ow->osd0); cudaFree(ow->osdw); cudaFree(ow->lpr); cudaFree(ow->bp_iter); ow->bp_dec = nullptr; }
+    if (cudaMalloc(&ow->bp_dec, (size_t)B * n) != cudaSuccess) return -4;
+    if (cudaMalloc(&ow->osd0, (size_t)B * n) != cudaSuccess) return -4;
+    if (cudaMalloc(&ow->osdw, (size_t)B * n) != cudaSuccess) return -4;
+    if (cudaMalloc(&ow->lpr, (size_t)B * n * 32) != cudaSuccess) return -4;
+    if (cudaMalloc(&ow->bp_iter, (size_t)B * 4) != cudaSuccess) return -4;
+    cudaMemset(ow->osd0, 0, (size_t)B * n); cudaMemset(ow->osdw, 0, (size_t)B * n); cudaMemset(ow->bp_dec, 0, (size_t)B * n);
+    ow->out_cap = B;
+    return 0;
+}
+static inline void osd_free_outputs(OsdWork *ow) {
+    if (ow->bp_dec) { cudaFree(ow->bp_dec); cudaFree(ow->osd0); cudaFree(ow->osdw); cudaFree(ow->lpr); cudaFree(ow->bp_iter); ow->bp_dec = nullptr; }
+}
+
+// ----------------------------------------------------------------------------------------------
+// post-BP on the shortened graph (osd_window.pyx:187-192): one CTA per non-converged shot
+// ----------------------------------------------------------------------------------------------
+template <int VPT, int DMAX, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+post_bp_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int n, OsdWork ow, long long chunk_base) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
+    unsigned char *blob = smem;
+    unsigned char *st = smem + L.blob_bytes;
+    Ctx c;
+    c.m = L.m; c.nn = L.nn; c.factor = P.factor; c.low_error = 0;
+    c.prior = (const double *)(blob + L.off_prior);
+    c.voff = (const u16 *)(blob + L.off_voff); c.coff = (const u16 *)(blob + L.off_coff);
+    c.vrow = (const u16 *)(blob + L.off_vrow); c.vpos = (const u16 *)(blob + L.off_vpos); c.cvn = (const u16 *)(blob + L.off_cvn);
+    c.synd = blob + L.off_synd;
+    c.msg = (double *)(st + S.off_msg);
+    c.vn_mask = (i8 *)(st + S.off_vnmask); c.error = (i8 *)(st + S.off_error); c.dec = (i8 *)(st + S.off_dec);
+    c.cn_mask = (i8 *)(st + S.off_cnmask); c.cn_deg = st + S.off_cndeg; c.flip = st + S.off_flip;
+    c.upar = (u32 *)(st + S.off_upar);
+    c.red_d = (double *)(st + S.off_red); c.red_i = (int *)(c.red_d + 64); c.misc = (int *)(st + S.off_misc);
+    u64 *bar = (u64 *)(st + S.off_bar);
+    const u16 *col = (const u16 *)(blob + L.off_col);
+    const i8 *snap_vn = (const i8 *)(blob + L.off_vnmask), *snap_cn = (const i8 *)(blob + L.off_cnmask);
+    const u8 *snap_deg = blob + L.off_cndeg;
+    c.A = 0; c.A_sum = 0; c.C = 0; c.D = 0;
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    u32 mphase = 0;
+    const int count = ws.counters[0];
+    u64 edge_iters = 0, bp_calls = 0, paths_run = 0; u32 vn_iters = 0, cn_iters = 0;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) c.misc[2] = atomicAdd(&ws.counters[1], 1);
+        __syncthreads();
+        const int slot = c.misc[2];
+        if (slot >= count) break;
+        const unsigned char *gblob = ws.blob + (size_t)slot * L.blob_bytes;
+        const BlobHeader gh = *(const BlobHeader *)gblob;
+        if (tid == 0) ow.need_osd[slot] = 0;
+        if (gh.status != 0) continue;
+        if (tid == 0) {
+            fence_proxy_async();
+            const u32 vb = (u32)((gh.es * 2 + 15) & ~15);
+            mbar_expect_tx(bar, (u32)L.fixed_bytes + 3 * vb);
+            bulk_g2s(blob, gblob, (u32)L.fixed_bytes, bar);
+            if (vb) {
+                bulk_g2s(blob + L.off_vrow, gblob + L.off_vrow, vb, bar);
+                bulk_g2s(blob + L.off_vpos, gblob + L.off_vpos, vb, bar);
+                bulk_g2s(blob + L.off_cvn, gblob + L.off_cvn, vb, bar);
+            }
+        }
+        mbar_wait(bar, mphase);
+        mphase ^= 1;
+        c.es = gh.es; c.bad_rows = gh.bad_rows;
+        for (int j = tid; j < c.nn; j += T) { const i8 v = snap_vn[j]; c.vn_mask[j] = v; c.error[j] = v < 0 ? 0 : v; }
+        for (int r = tid; r < c.m; r += T) { c.cn_mask[r] = snap_cn[r]; c.cn_deg[r] = snap_deg[r]; c.flip[r] = 0; }
+        __syncthreads();
+        init_msgs<VPT>(c);                                                  // bp_init, osd_window.pyx:370-379
+        // the history ring continues from the pre-BP (osd_window.pyx:458 re-uses log_prob_ratios)
+        double h[VPT][4];
+        const double *hg = ws.hist + (size_t)slot * n * 4;
+#pragma unroll
+        for (int i = 0; i < VPT; i++) {
+            const int j = tid + i * T;
+#pragma unroll
+            for (int s = 0; s < 4; s++) h[i][s] = (j < c.nn) ? hg[(size_t)col[j] * 4 + s] : 0.0;
+        }
+        __syncthreads();
+        paths_run++;
+        int iters = 0;
+        const int conv = bp_run<VPT, DMAX>(c, h, P.post_max_iter, edge_iters, vn_iters, cn_iters, &iters); bp_calls++;
+        const long long shot = gh.shot;
+        // outputs: bp_decoding, log_prob_ratios, bp_iteration; sort keys for OSD (osd_window.pyx:205-213)
+        double *key = ws.sum + (size_t)slot * n;
+        double *lpr = ow.lpr + ((size_t)(chunk_base + shot) * n) * 4;
+        u8 *bpd = ow.bp_dec + (size_t)(chunk_base + shot) * n;
+        for (int v = tid; v < n; v += T) bpd[v] = 0;                        // dropped columns were decimated to 0
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < VPT; i++) {
+            const int j = tid + i * T;
+            if (j < c.nn) {
+                const int cj = col[j];
+                const int vm = c.vn_mask[j];
+                double k;
+                if (vm == 1) k = -1000.0; else if (vm == 0) k = 1000.0;
+                else {
+                    k = ((h[i][0] + h[i][1]) + h[i][2]) + h[i][3];
+#pragma unroll
+                    for (int s = 0; s < 4; s++) lpr[(size_t)cj * 4 + s] = h[i][s];
+                }
+                key[cj] = k;
+                bpd[cj] = (u8)(c.error[j] != 0);
+            }
+        }
+        if (tid == 0) { ow.bp_iter[chunk_base + shot] += iters; ow.need_osd[slot] = conv ? 0 : 1; }
+        record_result(c, ws.rec + (size_t)slot * P.n_rec * P.rec_stride, conv);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) edge_iters += __shfl_xor_sync(FULLMASK, edge_iters, o);
+    if (lane == 0 && edge_iters) atomicAdd(&ws.stats[1], edge_iters);
+    u64 vi = vn_iters, ci = cn_iters;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { vi += __shfl_xor_sync(FULLMASK, vi, o); ci += __shfl_xor_sync(FULLMASK, ci, o); }
+    if (lane == 0) { if (vi) atomicAdd(&ws.stats[6], vi); if (ci) atomicAdd(&ws.stats[7], ci); }
+    if (tid == 0) { if (paths_run) atomicAdd(&ws.stats[2], paths_run); if (bp_calls) atomicAdd(&ws.stats[3], bp_calls); }
+}
+
+// ----------------------------------------------------------------------------------------------
+// OSD: one CTA per shot that needs it
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+osd_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayout L, GdgDev P, OsdSmem S, OsdWork ow,
+           int method, int order_w, int rank, u8 *__restrict__ dec_out, double *__restrict__ pm_out, long long chunk_base) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double *key = (double *)(smem + S.off_key);
+    u16 *idx = (u16 *)(smem + S.off_idx);               // after the sort: scan order of the columns
+    u64 *tcol = (u64 *)(smem + S.off_tcol);             // [(m+1)][W64]; column m carries T*syndrome
+    u64 *vt = (u64 *)(smem + S.off_vt);                 // [k][W64] reduced non-pivot columns
+    u16 *colinfo = (u16 *)(smem + S.off_colinfo);       // per column: 0xffff none | pivot row | 0x8000 + T index
+    u32 *ent = (u32 *)(smem + S.off_ent);               // [nn'] (col << 16 | info), ascending col
+    u64 *vbuf = (u64 *)(smem + S.off_vbuf);             // [W64]
+    u64 *pivmask = (u64 *)(smem + S.off_piv);           // [W64]
+    u32 *scan = (u32 *)(smem + S.off_scan);             // [n+1]
+    u32 *wt = (u32 *)(smem + S.off_wt);
+    double *red_d = (double *)(smem + S.off_red); int *red_i = (int *)(red_d + 64);
+    int *misc = (int *)(smem + S.off_misc);
+    u64 *ybest = (u64 *)(smem + S.off_ybest);           // [W64]
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int m = g.m, n = g.n, nn = L.nn, W64 = S.W64, NP2 = S.np2, k = S.k;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const int count = ws.counters[0];
+    u64 osd_shots = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) misc[2] = atomicAdd(&ws.counters[3], 1);
+        __syncthreads();
+        const int slot = misc[2];
+        if (slot >= count) break;
+        if (!ow.need_osd[slot]) continue;
+        const int shot = ws.gdg_list[slot];
+        osd_shots++;
+        // ---- order the columns (osd_window.pyx:205-215)
+        for (int i = tid; i < NP2; i += T) {
+            key[i] = (i < n) ? ws.sum[(size_t)slot * n + i] : inf;
+            idx[i] = (i < n) ? (u16)i : (u16)0xffff;
+        }
+        for (int i = tid; i < (m + 1) * W64; i += T) tcol[i] = 0;
+        for (int i = tid; i < n; i += T) colinfo[i] = 0xffff;
+        for (int i = tid; i < W64; i += T) pivmask[i] = 0;
+        __syncthreads();
+        for (int r = tid; r < m; r += T) {
+            tcol[r * W64 + (r >> 6)] = 1ull << (r & 63);
+            if (synd[(size_t)shot * m + r]) atomicOr(&tcol[m * W64 + (r >> 6)], 1ull << (r & 63));
+        }
+        block_bitonic_sort(key, idx, NP2);
+        if (tid == 0) { misc[0] = 0; }
+        __syncthreads();
+        // ---- greedy independent columns in scan order, Gauss-Jordan on T (mod2sparse_extra.cpp:113-376)
+        int found = 0;
+        for (int pos = 0; pos < n && found < rank; pos++) {
+            const int cidx = idx[pos];
+            if (tid < W64) {
+                u64 v = 0;
+                for (int e = g.cp[cidx]; e < g.cp[cidx + 1]; e++) v ^= tcol[(int)g.cr[e] * W64 + tid];
+                vbuf[tid] = v;
+            }
+            __syncthreads();
+            if (wid == 0) {
+                int pr = -1;
+                for (int wb = 0; wb < W64 && pr < 0; wb += 32) {
+                    const int w = wb + lane;
+                    const u64 free_bits = (w < W64) ? (vbuf[w] & ~pivmask[w]) : 0ull;
+                    const u32 b = __ballot_sync(FULLMASK, free_bits != 0);
+                    if (b) {
+                        const int fl = __ffs(b) - 1;
+                        const u64 fb = __shfl_sync(FULLMASK, free_bits, fl);
+                        pr = (wb + fl) * 64 + (__ffsll((long long)fb) - 1);
+                    }
+                }
+                if (lane == 0) {
+                    misc[1] = pr;
+                    if (pr >= 0) { pivmask[pr >> 6] |= 1ull << (pr & 63); colinfo[cidx] = (u16)pr; }
+                }
+            }
+            __syncthreads();
+            const int pr = misc[1];
+            if (pr < 0) continue;
+            found++;
+            const int pw = pr >> 6; const u64 pb = 1ull << (pr & 63);
+            for (int r = tid; r <= m; r += T) {
+                if (tcol[r * W64 + pw] & pb) {
+                    for (int w = 0; w < W64; w++) {
+                        u64 x = vbuf[w];
+                        if (w == pw) x &= ~pb;
+                        tcol[r * W64 + w] ^= x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- the non-pivot columns that may be flipped: first k of order[0..nn) \ pivots (osd_window.pyx:243-258)
+        if (wid == 0) {
+            int cnt = 0;
+            for (int base = 0; base < nn && cnt < k; base += 32) {
+                const int pos = base + lane;
+                int cidx = -1; bool np_ = false;
+                if (pos < nn) { cidx = idx[pos]; np_ = (colinfo[cidx] == 0xffff); }
+                const u32 b = __ballot_sync(FULLMASK, np_);
+                const int my = cnt + __popc(b & ((1u << lane) - 1));
+                if (np_ && my < k) colinfo[cidx] = (u16)(0x8000 | my);
+                cnt += __popc(b);
+            }
+        }
+        __syncthreads();
+        // ---- entries (pivot or flippable column) in ascending column index
+        for (int cI = tid; cI < n; cI += T) scan[cI] = (colinfo[cI] != 0xffff) ? 1u : 0u;
+        if (tid == 0) scan[n] = 0;
+        __syncthreads();
+        block_excl_scan(scan, n + 1, wt);
+        const int nent = (int)scan[n];
+        for (int cI = tid; cI < n; cI += T) if (colinfo[cI] != 0xffff) ent[scan[cI]] = ((u32)cI << 16) | colinfo[cI];
+        // reduced flippable columns vt[t] = T h_t
+        for (int cI = tid; cI < n; cI += T) {
+            const u16 ci = colinfo[cI];
+            if (ci != 0xffff && (ci & 0x8000)) {
+                const int t = ci & 0x7fff;
+                for (int w = 0; w < W64; w++) {
+                    u64 v = 0;
+                    for (int e = g.cp[cI]; e < g.cp[cI + 1]; e++) v ^= tcol[(int)g.cr[e] * W64 + w];
+                    vt[t * W64 + w] = v;
+                }
+            }
+        }
+        __syncthreads();
+        const u64 *y0 = tcol + m * W64;
+        // ---- candidates: id 0 = OSD-0; CS: singles 1..k, then pairs i<j<w; E: patterns 0..2^w-1 as id+... (see below)
+        long long ncand;
+        if (order_w <= 0 || method == SWD_OSD_0) ncand = 1;
+        else if (method == SWD_OSD_CS) ncand = 1 + (long long)k + (long long)order_w * (order_w - 1) / 2;
+        else ncand = 1 + (1ll << order_w);
+        double best = inf; int besti = 0x7fffffff;
+        double pm0 = 0.0;
+        for (long long cand = tid; cand < ncand; cand += T) {
+            // flipped T indices of this candidate
+            int t1 = -1, t2 = -1; u32 emask = 0;
+            if (cand > 0) {
+                const long long l = cand - 1;
+                if (method == SWD_OSD_CS) {
+                    if (l < k) t1 = (int)l;
+                    else {
+                        long long q = l - k; int i = 0;
+                        while (q >= order_w - 1 - i) { q -= order_w - 1 - i; i++; }
+                        t1 = i; t2 = i + 1 + (int)q;
+                    }
+                } else emask = (u32)l;
+            }
+            double pm = 0.0;
+            for (int q = 0; q < nent; q++) {
+                const u32 en = ent[q];
+                const int info = en & 0xffff, cI = en >> 16;
+                bool on;
+                if (info & 0x8000) {
+                    const int t = info & 0x7fff;
+                    on = (t == t1) || (t == t2) || (t < 32 && ((emask >> t) & 1u));
+                } else {
+                    const int w = info >> 6;
+                    u64 y = y0[w];
+                    if (t1 >= 0) y ^= vt[t1 * W64 + w];
+                    if (t2 >= 0) y ^= vt[t2 * W64 + w];
+                    if (emask) { u32 e2 = emask; while (e2) { const int t = __ffs(e2) - 1; e2 &= e2 - 1; y ^= vt[t * W64 + w]; } }
+                    on = (y >> (info & 63)) & 1ull;
+                }
+                if (on) pm += g.llr[cI];
+            }
+            if (cand == 0) pm0 = pm;
+            else if (pm < best) { best = pm; besti = (int)cand; }       // candidates visited in ascending id per thread
+        }
+        // OSD-0 path metric broadcast, then strict-min over higher-order candidates (first wins)
+        if (tid == 0) red_d[63] = pm0;
+        block_argmin(best, besti, red_d, red_i);
+        pm0 = red_d[63];
+        const bool use_w = (besti != 0x7fffffff) && (best < pm0);         // osd_window.pyx:276
+        // ---- materialise osd0 and osdw
+        int t1 = -1, t2 = -1; u32 emask = 0;
+        if (use_w) {
+            const long long l = (long long)besti - 1;
+            if (method == SWD_OSD_CS) {
+                if (l < k) t1 = (int)l;
+                else { long long q = l - k; int i = 0; while (q >= order_w - 1 - i) { q -= order_w - 1 - i; i++; } t1 = i; t2 = i + 1 + (int)q; }
+            } else emask = (u32)l;
+        }
+        if (tid < W64) {
+            u64 y = y0[tid];
+            if (t1 >= 0) y ^= vt[t1 * W64 + tid];
+            if (t2 >= 0) y ^= vt[t2 * W64 + tid];
+            u32 e2 = emask; while (e2) { const int t = __ffs(e2) - 1; e2 &= e2 - 1; y ^= vt[t * W64 + tid]; }
+            ybest[tid] = y;
+        }
+        __syncthreads();
+        const size_t row = (size_t)(shot) * n, orow = (size_t)(chunk_base + shot) * n;
+        for (int cI = tid; cI < n; cI += T) {
+            const u16 info = colinfo[cI];
+            u8 b0 = 0, bw = 0;
+            if (info != 0xffff) {
+                if (info & 0x8000) { const int t = info & 0x7fff; bw = (u8)((t == t1) || (t == t2) || (t < 32 && ((emask >> t) & 1u))); }
+                else { b0 = (u8)((y0[info >> 6] >> (info & 63)) & 1ull); bw = (u8)((ybest[info >> 6] >> (info & 63)) & 1ull); }
+            }
+            dec_out[row + cI] = bw;
+            ow.osd0[orow + cI] = b0;
+            ow.osdw[orow + cI] = bw;
+        }
+        if (tid == 0 && pm_out) pm_out[shot] = use_w ? best : pm0;
+    }
+    if (tid == 0 && osd_shots) atomicAdd(&ws.stats[4], osd_shots);
+}
+
+// ----------------------------------------------------------------------------------------------
+// finish: scatter post-BP results of converged shots, converge flags (BP only, osd_window.pyx:189)
+// ----------------------------------------------------------------------------------------------
+__global__ void osd_finish_kernel(Workspace ws, SubLayout L, GdgDev P, OsdWork ow, int n, u8 *__restrict__ dec_out,
+                                  u8 *__restrict__ conv_out, long long chunk_base) {
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int count = ws.counters[0];
+    for (int slot = blockIdx.x; slot < count; slot += gridDim.x) {
+        const unsigned char *gblob = ws.blob + (size_t)slot * L.blob_bytes;
+        const BlobHeader gh = *(const BlobHeader *)gblob;
+        const u16 *col = (const u16 *)(gblob + L.off_col);
+        if (gh.status == 0 && !ow.need_osd[slot]) {
+            const u8 *rec = ws.rec + (size_t)slot * P.n_rec * P.rec_stride;
+            const u32 *bits = (const u32 *)(rec + sizeof(RecHeader));
+            for (int j = tid; j < L.nn; j += T) dec_out[(size_t)gh.shot * n + col[j]] = (u8)((bits[j >> 5] >> (j & 31)) & 1u);
+            if (tid == 0) conv_out[gh.shot] = 1;
+        } else if (gh.status != 0) {
+            // decimation / peeling contradiction: bp_decoding is what decode() returned (osd_window.pyx:179-186)
+            for (int v = tid; v < n; v += T) ow.bp_dec[(size_t)(chunk_base + gh.shot) * n + v] = dec_out[(size_t)gh.shot * n + v];
+        }
+    }
+}
+
+// min_pm of BP-converged shots: ordered fp64 sum over ascending column (osd_window.pyx:168-170,190-191);
+// also mirrors bp_decoding for shots that never left the BP stages.  One warp per shot.
+__global__ void osd_pm_kernel(const double *__restrict__ llr, int n, const u8 *__restrict__ dec, const u8 *__restrict__ conv,
+                              long long B, double *__restrict__ pm_out, OsdWork ow, long long chunk_base, const u8 *__restrict__ in_list) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (long long b = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); b < B; b += (long long)gridDim.x * wpb) {
+        const u8 *row = dec + b * n;
+        const bool cv = conv[b] != 0;
+        double pm = 0.0;
+        for (int base = 0; base < n; base += 32) {
+            const int v = base + lane;
+            const u8 bit = (v < n) ? row[v] : 0;
+            if (!in_list[b] && v < n) ow.bp_dec[(size_t)(chunk_base + b) * n + v] = bit;
+            u32 bm = __ballot_sync(FULLMASK, bit != 0);
+            if (cv) while (bm) { const int kk = __ffs(bm) - 1; bm &= bm - 1; pm += llr[base + kk]; }
+        }
+        if (cv && lane == 0 && pm_out) pm_out[b] = pm;
+    }
+}
+
+__global__ void osd_mark_list_kernel(const Workspace ws, u8 *in_list) {
+    const int count = ws.counters[0];
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < count; s += gridDim.x * blockDim.x) in_list[ws.gdg_list[s]] = 1;
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+static inline int osd_r16(int x) { return (x + 15) & ~15; }
+
+static inline int osd_setup(int m, int n, int nn, int rank, int method, int order_w, int num_sm, OsdSmem *S, int *T5, int *grid5) {
+    int np2 = 64; while (np2 < n) np2 <<= 1;
+    S->np2 = np2; S->W64 = (m + 1 + 63) / 64; if (S->W64 < (m + 63) / 64) S->W64 = (m + 63) / 64;
+    S->W64 = (m + 63) / 64;
+    S->k = nn - rank;
+    int o = 0;
+    S->off_key = o; o += 8 * np2;
+    S->off_idx = o; o += 2 * np2; o = osd_r16(o);
+    S->off_tcol = o; o += 8 * (m + 1) * S->W64; o = osd_r16(o);
+    S->off_vt = o; o += 8 * (S->k > 0 ? S->k : 1) * S->W64; o = osd_r16(o);
+    S->off_colinfo = o; o += 2 * n; o = osd_r16(o);
+    S->off_ent = o; o += 4 * (nn + rank + 1); o = osd_r16(o);
+    S->off_vbuf = o; o += 8 * S->W64; o = osd_r16(o);
+    S->off_piv = o; o += 8 * S->W64; o = osd_r16(o);
+    S->off_scan = o; o += 4 * (n + 1); o = osd_r16(o);
+    S->off_wt = o; o += 4 * 64;
+    S->off_red = o; o += 64 * 8 + 64 * 4; o = osd_r16(o);
+    S->off_misc = o; o += 64;
+    S->off_ybest = o; o += 8 * S->W64; o = osd_r16(o);
+    S->total = o;
+    if (S->total > 227 * 1024) return -2;
+    int t = ((m + 1 + 31) / 32) * 32; if (t < 128) t = 128; if (t > 1024) t = 1024;
+    *T5 = t;
+    if (cudaFuncSetAttribute(osd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -3;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, osd_kernel, t, S->total) != cudaSuccess || occ < 1) return -2;
+    *grid5 = num_sm * occ;
+    return 0;
+}
+
+typedef void (*post_fn_t)(Workspace, SubLayout, PathSmem, GdgDev, int, OsdWork, long long);
+static inline post_fn_t pick_post_kernel(int dmax, int T) {
+    if (dmax == 8) {
+        if (T <= 128) return post_bp_kernel<4, 8, 128>;
+        if (T <= 512) return post_bp_kernel<4, 8, 512>;
+        return post_bp_kernel<4, 8, 1024>;
+    }
+    if (T <= 128) return post_bp_kernel<4, 16, 128>;
+    return post_bp_kernel<4, 16, 1024>;
+}
+
+// everything after sort_reset for the osd_window kind
+static inline int osd_launch(const GraphDev &g, const u8 *d_synd, const Workspace &ws, const SubLayout &L, const PathSmem &PS,
+                             const GdgDev &P, const OsdSmem &OS, const OsdWork &ow, int dmax, int T3, int grid3, size_t smem3,
+                             int T5, int grid5, int method, int order_w, int rank, u8 *d_corr, u8 *d_conv, double *d_pm,
+                             long long B, long long chunk_base, cudaStream_t s, uint64_t *launches, u8 *in_list) {
+    post_fn_t post = pick_post_kernel(dmax, T3);
+    if (cudaFuncSetAttribute(post, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -3;
+    post<<<grid3, T3, smem3, s>>>(ws, L, PS, P, g.n, ow, chunk_base);
+    osd_kernel<<<grid5, T5, OS.total, s>>>(g, d_synd, ws, L, P, OS, ow, method, order_w, rank, d_corr, d_pm, chunk_base);
+    osd_finish_kernel<<<grid5, 128, 0, s>>>(ws, L, P, ow, g.n, d_corr, d_conv, chunk_base);
+    cudaMemsetAsync(in_list, 0, (size_t)B, s);
+    osd_mark_list_kernel<<<64, 256, 0, s>>>(ws, in_list);
+    osd_pm_kernel<<<(unsigned)((B + 7) / 8 < 1 ? 1 : ((B + 7) / 8 > 65535 ? 65535 : (B + 7) / 8)), 256, 0, s>>>(g.llr, g.n, d_corr, d_conv, B, d_pm, ow, chunk_base, in_list);
+    *launches += 5;
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}

@@ -128,3 +128,41 @@ def test_sliding_window_driver_matches_reference_loop(oracle_mod):
     assert res["flagged"] == int(ref["flagged"].sum())
     assert res["failed"] == int(ref["failed"].sum())
     assert res["window_unconverged"] == ref["window_unconverged"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_OSD)
+def test_osd_window_bit_exact(name, oracle_mod):
+    """osd_window: BP decisions, OSD-0 / OSD-CS / OSD-E corrections, min_pm, bp_iteration and the posterior
+    history, bit-exact against the reference's recorded outputs."""
+    from slidingwindowdecoder_b200 import osd_window
+    g = load_golden(name)
+    dec = osd_window(g["mat"], channel_probs=g["priors"], **g["kwargs"])
+    corr, conv, pm = dec.decode_batch(g["synd"], return_pm=True)
+    out = dec.last_outputs()
+    assert np.array_equal(conv, g["conv"])
+    bad = np.nonzero((corr != g["dec"]).any(axis=1))[0]
+    assert len(bad) == 0, f"shots {bad[:10]}"
+    assert np.array_equal(out["bp_decoding"], g["bp_decoding"])
+    assert np.array_equal(out["bp_iteration"], g["bp_iteration"])
+    assert np.array_equal(pm, g["min_pm"])
+    nc = g["conv"] == 0
+    assert np.array_equal(out["osd0_decoding"][nc], g["osd0"][nc])
+    for i in range(min(8, len(corr))):
+        if g["bp_iteration"][i] >= 4:
+            assert np.array_equal(out["log_prob_ratios"][i], g["lpr_first8"][i]), i
+
+
+def test_osd_window_single_shot_properties():
+    from slidingwindowdecoder_b200 import osd_window
+    g = load_golden("c2_w1_osdw_cs10")
+    dec = osd_window(g["mat"], channel_probs=g["priors"], **g["kwargs"])
+    i = int(np.nonzero(g["conv"] == 0)[0][0])
+    e = dec.decode(g["synd"][i])
+    assert np.array_equal(e.astype(np.uint8), g["dec"][i])
+    assert dec.converge == 0 and dec.min_pm == g["min_pm"][i] and dec.bp_iteration == g["bp_iteration"][i]
+    assert np.array_equal(dec.osd0_decoding.astype(np.uint8), g["osd0"][i])
+    assert np.array_equal(dec.osdw_decoding.astype(np.uint8), g["dec"][i])
+    H = g["mat"].toarray().astype(np.int64)
+    assert not ((H @ e + g["synd"][i]) % 2).any()          # OSD always reproduces the syndrome
+    with pytest.raises(ValueError):
+        osd_window(g["mat"], channel_probs=g["priors"], osd_method="osd_cs", osd_order=10 ** 6)
