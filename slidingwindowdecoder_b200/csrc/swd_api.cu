@@ -237,6 +237,10 @@ static int setup_kernels(swd_decoder *d) {
     if (c.kind == SWD_KIND_BPGDG && c.multi_thread) {
         if (P.T < 0 || P.T > 10) { set_err("max_tree_depth out of range"); return SWD_ERR_UNSUPPORTED; }
         P.n_tree = (1 << P.T) - 1; P.n_side = std::max(0, P.S - P.T); P.n_rec = 1 + P.n_tree + P.n_side;
+    } else if (c.kind == SWD_KIND_BPGDG) {
+        // single-thread schedule: the side-snapshot area holds the guess stack (max_guess entries, pyx:181)
+        if (P.T < 0 || P.T > 10) { set_err("max_tree_depth out of range"); return SWD_ERR_UNSUPPORTED; }
+        P.n_tree = 0; P.n_side = std::max(0, ((1 << P.T) - 1) * 2 + P.S - P.T); P.n_rec = 1;
     } else { P.n_tree = 0; P.n_side = 0; P.n_rec = 1; }
     if (c.kind == SWD_KIND_OSD_WINDOW) { P.factor = c.ms_scaling_factor; P.low_error = 0; }
     P.rec_stride = r16((int)sizeof(RecHeader) + 4 * ((nn + 31) / 32));

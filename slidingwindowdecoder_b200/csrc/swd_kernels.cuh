@@ -279,11 +279,20 @@ struct RecHeader { double pm; int status; int pad; };          // 16 bytes, foll
 struct SideHeader { int valid, vn, value, depth; };            // 16 bytes, followed by vn_mask, cn_mask, cn_deg
 
 // write (status, pm, error bits) of the current path
-__device__ __forceinline__ void record_result(Ctx &c, u8 *rec, int converged) {
+// path metric of the current `error`, broadcast to the whole CTA (contains barriers)
+__device__ __forceinline__ double block_pm(Ctx &c) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (wid == 0) { const double pm = pm_warp(c, lane); if (lane == 0) c.red_d[62] = pm; }
+    __syncthreads();
+    return c.red_d[62];
+}
+
+__device__ __forceinline__ void record_result(Ctx &c, u8 *rec, int converged, const double *pm_known = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
     __syncthreads();
     if (wid == 0) {
-        double pm = converged ? pm_warp(c, lane) : SWD_MAX_PM;
+        double pm = pm_known ? *pm_known : (converged ? pm_warp(c, lane) : SWD_MAX_PM);
         if (lane == 0) { RecHeader *h = (RecHeader *)rec; h->pm = pm; h->status = converged ? 1 : 2; }
     }
     u32 *bits = (u32 *)(rec + sizeof(RecHeader));
@@ -380,10 +389,13 @@ path_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int phase) {
 
         // ---- one interpreter loop for every kind of branch, so that bp_run / select_vn /
         //      set_and_peel are instantiated once (registers, code size)
-        enum { R_MAIN = 0, R_TREE = 1, R_SIDE = 2, R_GD = 3 };
+        enum { R_MAIN = 0, R_TREE = 1, R_SIDE = 2, R_GD = 3, R_ST = 4 };
         int role, limit, depth = 0, pend_vn = -1, pend_val = 0;
         u8 *rec = recbase;
+        // single-thread schedule (pyx:254-338): guess stack lives in this slot's side-snapshot area
+        int st_used = 0, st_i = 0, st_min_depth = P.max_step, st_conv = 0; double st_min_pm = SWD_MAX_PM;
         if (P.kind == SWD_KIND_BPGD) { role = R_GD; limit = P.max_step; }
+        else if (!P.multi_thread) { role = R_ST; limit = P.max_step; c.A = -3; c.A_sum = -16; }
         else if (phase == 1) {                                  // side branch j (bpgd.cpp:527-570)
             role = R_SIDE; limit = P.side_step; rec = recbase + (size_t)(1 + P.n_tree + path) * P.rec_stride;
             c.A = 0; c.A_sum = -10; depth = sh->depth; pend_vn = sh->vn; pend_val = sh->value;
@@ -403,6 +415,10 @@ path_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int phase) {
             if (!stage_end && steps >= limit) stage_end = true;
             if (!stage_end) {
                 if (role == R_MAIN) c.A_sum = (depth == 0) ? -16 : -12;                          // :631
+                if (role == R_ST) {                                                               // pyx:341-343
+                    c.A = stage ? 0 : -3; c.A_sum = stage ? -10 : -12;
+                    if (depth == 0) c.A_sum = -16;
+                }
                 if (role == R_TREE && stage == 0 && depth > 0 && !on_side) c.A_sum = -12;         // :450
                 conv = bp_run<VPT, DMAX>(c, h, P.num_iter, edge_iters, vn_iters, cn_iters); bp_calls++;
                 steps++;
@@ -423,12 +439,37 @@ path_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int phase) {
                     pend_vn = bi; pend_val = c.misc[3]; depth++;
                     continue;
                 }
-                if (conv && role != R_MAIN) break;                                                // :452-459, :552-559
+                if (role == R_ST && conv) {                                                       // pyx:284-292, :320-330
+                    const double pm = block_pm(c);
+                    st_conv = 1;
+                    if (stage == 0) { st_min_depth = depth; st_min_pm = pm; record_result(c, rec, 1, &pm); }
+                    else if (pm < st_min_pm) {
+                        if (depth < st_min_depth) st_min_depth = depth;
+                        st_min_pm = pm; record_result(c, rec, 1, &pm);
+                    }
+                    stage_end = true;
+                }
+                if (role == R_ST && !stage_end && stage == 1 && depth > st_min_depth + 2) stage_end = true;   // pyx:331
+                if (conv && role != R_MAIN && role != R_ST) break;                                // :452-459, :552-559
+                if (!stage_end) {
                 int guess = -1;
                 int favor = select_vn<VPT>(c, h, depth, guess);
                 if (conv) break;                                                                  // main: :633-649
                 if (favor == -1 || guess == -1) stage_end = true;
                 else {
+                    if (role == R_ST) {                                                           // pyx:416-433
+                        bool do_guess = !(depth > st_min_depth);
+                        if (stage == 0 && depth >= P.S) do_guess = false;
+                        if (stage == 1 && depth > P.T) do_guess = false;
+                        if (do_guess && st_used < P.n_side) {
+                            unsigned char *sp = ws.side + ((size_t)slot * P.n_side + st_used) * P.side_stride;
+                            i8 *svn = (i8 *)(sp + sizeof(SideHeader)); i8 *scn = svn + c.nn; u8 *sdg = (u8 *)(scn + c.m);
+                            for (int j = tid; j < c.nn; j += T) svn[j] = c.vn_mask[j];
+                            for (int r = tid; r < c.m; r += T) { scn[r] = c.cn_mask[r]; sdg[r] = c.cn_deg[r]; }
+                            if (tid == 0) { SideHeader *q = (SideHeader *)sp; q->vn = guess; q->value = 1 - favor; q->depth = depth + 1; q->valid = 1; }
+                            st_used++;
+                        }
+                    }
                     if (role == R_MAIN && depth >= P.T && depth < P.S) {                          // :651-664
                         unsigned char *sp = ws.side + ((size_t)slot * P.n_side + (depth - P.T)) * P.side_stride;
                         i8 *svn = (i8 *)(sp + sizeof(SideHeader)); i8 *scn = svn + c.nn; u8 *sdg = (u8 *)(scn + c.m);
@@ -448,8 +489,31 @@ path_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int phase) {
                     pend_vn = guess; pend_val = favor; depth++;
                     continue;
                 }
+                }
             }
             // ---- the current stage ended without convergence
+            if (role == R_ST) {
+                if (stage == 0 && !st_conv) record_result(c, rec, 0);                             // pyx:295-298
+                bool again = false;
+                while (st_i < st_used) {                                                          // pyx:302-335
+                    const unsigned char *sp = ws.side + ((size_t)slot * P.n_side + st_i) * P.side_stride;
+                    st_i++;
+                    const SideHeader q = *(const SideHeader *)sp;
+                    if (q.depth > st_min_depth) continue;                                         // pyx:304
+                    const i8 *svn = (const i8 *)(sp + sizeof(SideHeader)); const i8 *scn = svn + c.nn; const u8 *sdg = (const u8 *)(scn + c.m);
+                    __syncthreads();
+                    for (int j = tid; j < c.nn; j += T) { const i8 v = svn[j]; c.vn_mask[j] = v; c.error[j] = v; }   // set_masks, bpgd.cpp:241-248
+                    for (int r = tid; r < c.m; r += T) { c.cn_mask[r] = scn[r]; c.cn_deg[r] = sdg[r]; }
+                    __syncthreads();
+                    init_msgs<VPT>(c);
+                    stage = 1; steps = 0; limit = P.side_step; depth = q.depth; pend_vn = q.vn; pend_val = q.value;
+                    again = true;
+                    break;
+                }
+                if (again) continue;
+                conv = 0;
+                break;
+            }
             if (role == R_TREE && stage == 0 && saved) {                                          // :490-503
                 __syncthreads();
                 for (int j = tid; j < c.nn; j += T) { const i8 v = bvn[j]; c.vn_mask[j] = v; c.error[j] = v; }
@@ -461,7 +525,7 @@ path_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int phase) {
             }
             break;
         }
-        if (conv || role == R_MAIN || role == R_GD) record_result(c, rec, conv);
+        if (role != R_ST && (conv || role == R_MAIN || role == R_GD)) record_result(c, rec, conv);
     }
     // ---- work counters
 #pragma unroll

@@ -30,6 +30,17 @@ def test_gdg_multi_thread_matches_oracle_and_golden(name, oracle_mod):
     assert 1.0 - ndiff / len(corr) >= 0.99
 
 
+@pytest.mark.parametrize("name", [g for g in GOLDEN_GDG if g.endswith("mt0")] + ["c1_gdg_sim_uniform_mt0"])
+def test_gdg_single_thread_matches_golden(name, oracle_mod):
+    """multi_thread=False (the constructor default): deterministic schedule, exact vectors vs the reference."""
+    g = load_golden(name)
+    dec = _gdg_cls()(g["mat"], channel_probs=g["priors"], **g["kwargs"])
+    corr, conv = dec.decode_batch(g["synd"])
+    assert np.array_equal(conv, g["conv"])
+    bad = np.nonzero((corr != g["dec"]).any(axis=1))[0]
+    assert len(bad) == 0, f"shots {bad[:10]}"
+
+
 def test_bpgd_matches_oracle_and_golden(oracle_mod):
     from slidingwindowdecoder_b200 import bpgd_decoder
     g = load_golden("c1_bpgd")
