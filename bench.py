@@ -313,6 +313,7 @@ def run_ours(args):
         "window_latency_ms": {"p50_at_batch": round(p50_b, 4), "p99_at_batch": round(p99_b, 4), "p50_batch1": round(p50_1, 4), "p99_batch1": round(p99_1, 4)},
         "results": {"shots": int(total_shots), "flagged": int(counts_res[0]), "failed": int(counts_res[1]),
                     "gdg_fraction": round(ctr["gdg_shots"] / max(1, ctr["shots"]), 4)},
+        "counters": ctr,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -28,15 +28,18 @@ static void set_err(const std::string &s) { g_last_error = s; }
 static inline int r16(int x) { return (x + 15) & ~15; }
 static inline int r32up(int x) { return (x + 31) & ~31; }
 
-typedef void (*path_fn_t)(Workspace, SubLayout, PathSmem, GdgDev, int);
+typedef void (*path_fn_t)(Workspace, SubLayout, SubLayout, PathSmem, GdgDev, int, int, int);
 static path_fn_t pick_path_kernel(int dmax, int T) {
-    if (dmax == 8) {
-        if (T <= 128) return path_kernel<4, 8, 128>;
-        if (T <= 512) return path_kernel<4, 8, 512>;
-        return path_kernel<4, 8, 1024>;
+    if (dmax == 6) {
+#ifndef SWD_MINB
+#define SWD_MINB 4
+#endif
+        if (T <= 128) return path_kernel<4, 6, 128, SWD_MINB>;
+        if (T <= 512) return path_kernel<4, 6, 512, 1>;
+        return path_kernel<4, 6, 1024, 1>;
     }
-    if (T <= 128) return path_kernel<4, 16, 128>;
-    return path_kernel<4, 16, 1024>;
+    if (T <= 128) return path_kernel<4, 16, 128, 3>;
+    return path_kernel<4, 16, 1024, 1>;
 }
 
 struct swd_decoder {
@@ -46,8 +49,9 @@ struct swd_decoder {
     int device = 0, num_sm = 0;
     GraphDev g{};
     void *d_graph[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    SubLayout L{};
-    PathSmem PS{};
+    SubLayout L{}, LsA{}, LsB{};
+    PathSmem PS{}, PSB{};
+    int es_capA = 0, grid3B = 0;
     PreSmem PRE{};
     SortSmem SS{};
     OsdSmem OS{};
@@ -225,6 +229,46 @@ static int occupancy(K kernel, int threads, size_t smem, int *out) {
     return SWD_OK;
 }
 
+static void make_layout(SubLayout &L, int nn, int m, int es, int lcap) {
+    L.nn = nn; L.m = m; L.es_max = es; L.lcap = lcap;
+    int o = 16;
+    L.off_prior = o; o += 8 * nn; o = r16(o);
+    L.off_voff = o; o += 2 * (nn + 1); o = r16(o);
+    L.off_coff = o; o += 2 * (m + 1); o = r16(o);
+    L.off_crank = o; o += 2 * m; o = r16(o);
+    L.off_synd = o; o += m; o = r16(o);
+    L.off_vnmask = o; o += nn; o = r16(o);
+    L.off_cnmask = o; o += m; o = r16(o);
+    L.off_cndeg = o; o += m; o = r16(o);
+    L.off_vperm = o; o += 2 * nn; o = r16(o);
+    L.off_cperm = o; o += 2 * m; o = r16(o);
+    L.off_col = o; o += 2 * nn; o = r16(o);
+    L.fixed_bytes = o;
+    L.off_vrow = o; o += r16(2 * es);
+    L.off_vpos = o; o += r16(2 * es);
+    L.off_cvn = o; o += r16(2 * es);
+    L.blob_bytes = o;
+}
+
+static void make_path_smem(PathSmem &S3, int nn, int m, int es) {
+    int o = 0;
+    S3.off_msg = o; o += 8 * es; o = r16(o);
+    S3.off_vnmask = o; o += nn; o = r16(o);
+    S3.off_error = o; o += nn; o = r16(o);
+    S3.off_dec = o; o += nn; o = r16(o);
+    S3.off_cnmask = o; o += m; o = r16(o);
+    S3.off_cndeg = o; o += m; o = r16(o);
+    S3.off_flip = o; o += m; o = r16(o);
+    S3.off_upar = o; o += 4 * m; o = r16(o);
+    S3.off_bvn = o; o += nn; o = r16(o);
+    S3.off_bcn = o; o += m; o = r16(o);
+    S3.off_bdeg = o; o += m; o = r16(o);
+    S3.off_red = o; o += 64 * 8 + 64 * 4; o = r16(o);
+    S3.off_misc = o; o += 64;
+    S3.off_bar = o; o += 16;
+    S3.total = o;
+}
+
 static int setup_kernels(swd_decoder *d) {
     const int m = d->m, n = d->n, nn = d->nn, es = std::max(d->es_max, 1);
     const swd_config &c = d->cfg;
@@ -245,35 +289,30 @@ static int setup_kernels(swd_decoder *d) {
     if (c.kind == SWD_KIND_OSD_WINDOW) { P.factor = c.ms_scaling_factor; P.low_error = 0; }
     P.rec_stride = r16((int)sizeof(RecHeader) + 4 * ((nn + 31) / 32));
     P.side_stride = r16((int)sizeof(SideHeader) + nn + 2 * m);
-    // ---- blob layout
-    SubLayout &L = d->L;
-    L.nn = nn; L.m = m; L.es_max = es;
-    int o = 16;
-    L.off_prior = o; o += 8 * nn; o = r16(o);
-    L.off_col = o; o += 2 * nn; o = r16(o);
-    L.off_voff = o; o += 2 * (nn + 1); o = r16(o);
-    L.off_coff = o; o += 2 * (m + 1); o = r16(o);
-    L.off_synd = o; o += m; o = r16(o);
-    L.off_vnmask = o; o += nn; o = r16(o);
-    L.off_cnmask = o; o += m; o = r16(o);
-    L.off_cndeg = o; o += m; o = r16(o);
-    L.fixed_bytes = o;
-    L.off_vrow = o; o += r16(2 * es);
-    L.off_vpos = o; o += r16(2 * es);
-    L.off_cvn = o; o += r16(2 * es);
-    L.blob_bytes = o;
+    // ---- blob layouts: global (worst case), shared-memory tier A (typical shots), tier B (worst case)
+    const int lcap = std::min(255, d->max_row_deg);
+    const int es_slots = es + m;      // every row may carry one pad slot
+    make_layout(d->L, nn, m, es_slots, lcap);
+    int capA = (int)((double)nn * d->nnz / n * 1.05) + 16;
+    capA = std::min(es_slots, ((capA + m / 2) + 7) & ~7);
+    if (const char *e = getenv("SWD_ES_TIER_A")) capA = std::min(es_slots, std::max(8, atoi(e)));
+    d->es_capA = capA;
+    make_layout(d->LsA, nn, m, capA, lcap);
+    make_layout(d->LsB, nn, m, es_slots, lcap);
+    make_path_smem(d->PS, nn, m, capA);
+    make_path_smem(d->PSB, nn, m, es_slots);
     // ---- K1
     d->T1 = std::min(256, std::max(64, r32up((n + 3) / 4)));
     if (const char *e = getenv("SWD_T1")) d->T1 = atoi(e);
     PreSmem &S1 = d->PRE;
-    o = 0; S1.off_msg = o; o += 8 * std::max(d->nnz, 1); o = r16(o);
+    int o = 0; S1.off_msg = o; o += 8 * std::max(d->nnz, 1); o = r16(o);
     S1.off_upar = o; o += 4 * m; o = r16(o);
     S1.off_synd = o; o += m; o = r16(o);
     S1.off_dec = o; o += n; o = r16(o);
     S1.off_misc = o; o += 64; S1.total = o;
     if (S1.total > 227 * 1024) { set_err("window graph does not fit in shared memory (nnz too large)"); return SWD_ERR_UNSUPPORTED; }
     int occ = 0, st;
-    if (d->dmax == 8) st = occupancy(pre_bp_kernel<8>, d->T1, S1.total, &occ); else st = occupancy(pre_bp_kernel<16>, d->T1, S1.total, &occ);
+    if (d->max_col_deg <= 8) st = occupancy(pre_bp_kernel<8>, d->T1, S1.total, &occ); else st = occupancy(pre_bp_kernel<16>, d->T1, S1.total, &occ);
     if (st) return st;
     if (occ < 1) { set_err("pre_bp_kernel does not fit"); return SWD_ERR_UNSUPPORTED; }
     d->grid1 = d->num_sm * occ;
@@ -284,12 +323,15 @@ static int setup_kernels(swd_decoder *d) {
     d->T2 = std::min(1024, std::max(128, np2 / 8));
     o = 0; S2.off_key = o; o += 8 * np2; S2.off_idx = o; o += 2 * np2; o = r16(o);
     S2.off_posof = o; o += 2 * n; o = r16(o);
-    S2.off_blob = o; o += L.blob_bytes;
+    S2.off_blob = o; o += d->L.blob_bytes;
     S2.off_u32a = o; o += 4 * (nn + 1); o = r16(o);
     S2.off_u32b = o; o += 4 * (m + 1); o = r16(o);
+    S2.off_u32c = o; o += 4 * (m + 1); o = r16(o);
     S2.off_wt = o; o += 4 * 64;
     S2.off_error = o; o += nn; o = r16(o);
-    S2.off_misc = o; o += 64; S2.total = o;
+    S2.off_misc = o; o += 64;
+    S2.off_bins = o; o += 4 * (17 + 256); o = r16(o);
+    S2.total = o;
     if (S2.total > 227 * 1024) { set_err("sort/reset kernel does not fit in shared memory"); return SWD_ERR_UNSUPPORTED; }
     if ((st = occupancy(sort_reset_kernel, d->T2, S2.total, &occ))) return st;
     if (occ < 1) { set_err("sort_reset_kernel does not fit"); return SWD_ERR_UNSUPPORTED; }
@@ -297,28 +339,16 @@ static int setup_kernels(swd_decoder *d) {
     // ---- K3
     d->T3 = std::max(32, std::max(r32up((nn + 3) / 4), r32up((m + SWD_CPT - 1) / SWD_CPT)));
     if (d->T3 > 1024) { set_err("new_n > 4096 unsupported"); return SWD_ERR_UNSUPPORTED; }
-    PathSmem &S3 = d->PS;
-    o = 0; S3.off_msg = o; o += 8 * es; o = r16(o);
-    S3.off_vnmask = o; o += nn; o = r16(o);
-    S3.off_error = o; o += nn; o = r16(o);
-    S3.off_dec = o; o += nn; o = r16(o);
-    S3.off_cnmask = o; o += m; o = r16(o);
-    S3.off_cndeg = o; o += m; o = r16(o);
-    S3.off_flip = o; o += m; o = r16(o);
-    S3.off_upar = o; o += 4 * m; o = r16(o);
-    S3.off_bvn = o; o += nn; o = r16(o);
-    S3.off_bcn = o; o += m; o = r16(o);
-    S3.off_bdeg = o; o += m; o = r16(o);
-    S3.off_red = o; o += 64 * 8 + 64 * 4; o = r16(o);
-    S3.off_misc = o; o += 64;
-    S3.off_bar = o; o += 16;
-    S3.total = o;
-    const size_t smem3 = (size_t)L.blob_bytes + S3.total;
-    if (smem3 > 227 * 1024) { set_err("shortened graph does not fit in shared memory"); return SWD_ERR_UNSUPPORTED; }
+    const size_t smemB = (size_t)d->LsB.blob_bytes + d->PSB.total;
+    if (smemB > 227 * 1024) { set_err("shortened graph does not fit in shared memory"); return SWD_ERR_UNSUPPORTED; }
+    const size_t smemA = (size_t)d->LsA.blob_bytes + d->PS.total;
+    d->dmax = d->max_col_deg <= 6 ? 6 : (d->max_col_deg <= 8 ? 8 : 16);
     d->path_fn = pick_path_kernel(d->dmax, d->T3);
-    if ((st = occupancy(d->path_fn, d->T3, smem3, &occ))) return st;
+    if ((st = occupancy(d->path_fn, d->T3, smemA, &occ))) return st;
     if (occ < 1) { set_err("path_kernel does not fit"); return SWD_ERR_UNSUPPORTED; }
     d->grid3 = d->num_sm * occ;
+    if ((st = occupancy(d->path_fn, d->T3, smemB, &occ))) return st;
+    d->grid3B = d->num_sm * std::max(1, occ);
     // ---- K5 (OSD)
     if (c.kind == SWD_KIND_OSD_WINDOW) {
         if ((st = osd_setup(d->m, d->n, d->nn, d->rank, d->cfg.osd_method, d->cfg.osd_order, d->num_sm, &d->OS, &d->T5, &d->grid5))) {
@@ -384,7 +414,7 @@ static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_cor
     double *lpr_out = (c.kind == SWD_KIND_OSD_WINDOW) ? d->ow.lpr + (size_t)chunk_base * d->n * 4 : nullptr;
     {
     KTimer kt(d, s, SWD_K_PRE_BP);
-    if (d->dmax == 8)
+    if (d->max_col_deg <= 8)
         pre_bp_kernel<8><<<g1, d->T1, d->PRE.total, s>>>(d->g, d_synd, B, c.max_iter, c.ms_scaling_factor, d_corr, d_conv, d->ws,
                                                         d->hscratch, full_hist, d->PRE, iter_out, lpr_out);
     else
@@ -400,22 +430,28 @@ static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_cor
     if (c.kind == SWD_KIND_BPGD && c.max_iter <= -1) return SWD_OK;   // pyx:506
     const int g2 = (int)std::min<long long>(B, d->grid2);
     { KTimer kt(d, s, SWD_K_SORT_RESET);
-      sort_reset_kernel<<<g2, d->T2, d->SS.total, s>>>(d->g, d_synd, d->ws, d->L, d->P, d->SS, d_corr); }
+      sort_reset_kernel<<<g2, d->T2, d->SS.total, s>>>(d->g, d_synd, d->ws, d->L, d->P, d->SS, d_corr, d->es_capA); }
     d->ctr.kernel_launches++;
-    const size_t smem3 = (size_t)d->L.blob_bytes + d->PS.total;
+    const size_t smem3 = (size_t)d->LsA.blob_bytes + d->PS.total;
+    const size_t smem3B = (size_t)d->LsB.blob_bytes + d->PSB.total;
+    const bool two_tier = d->es_capA < d->L.es_max;
     const int g3 = d->grid3;
     const int phases = (c.kind == SWD_KIND_BPGDG && c.multi_thread && d->P.n_side > 0) ? 2 : 1;
     if (c.kind == SWD_KIND_OSD_WINDOW) {
         KTimer kt(d, s, SWD_K_OSD);
-        int st = osd_launch(d->g, d_synd, d->ws, d->L, d->PS, d->P, d->OS, d->ow, d->dmax, d->T3, g3, smem3, d->T5, d->grid5,
+        int st = osd_launch(d->g, d_synd, d->ws, d->L, d->LsA, d->LsB, d->PS, d->PSB, d->es_capA, d->grid3B, smem3B, d->P, d->OS, d->ow, d->dmax, d->T3, g3, smem3, d->T5, d->grid5,
                             c.osd_method, c.osd_order, d->rank, d_corr, d_conv, d_pm, B, chunk_base, s, &d->ctr.kernel_launches,
                             d->ow.need_osd + d->cap);
         if (st) { set_err("osd launch failed"); return st; }
     } else {
         for (int ph = 0; ph < phases; ph++) {
             KTimer kt(d, s, ph == 0 ? SWD_K_PATH_MAIN : SWD_K_PATH_SIDE);
-            d->path_fn<<<g3, d->T3, smem3, s>>>(d->ws, d->L, d->PS, d->P, ph);
+            d->path_fn<<<g3, d->T3, smem3, s>>>(d->ws, d->L, d->LsA, d->PS, d->P, ph, 0, d->es_capA);
             d->ctr.kernel_launches++;
+            if (two_tier) {      // shots whose shortened graph exceeds tier A (rare): same kernel, worst-case footprint
+                d->path_fn<<<d->grid3B, d->T3, smem3B, s>>>(d->ws, d->L, d->LsB, d->PSB, d->P, ph, 1, d->es_capA);
+                d->ctr.kernel_launches++;
+            }
         }
         { KTimer kt(d, s, SWD_K_SELECT);
           select_kernel<<<std::max(1, std::min<int>((int)B, d->num_sm * 8)), 128, 0, s>>>(d->ws, d->L, d->P, d->n, d_corr, d_conv, d_pm); }

@@ -25,17 +25,21 @@ typedef unsigned long long u64;
 // layouts (byte offsets), computed once on the host
 // ----------------------------------------------------------------------------------------------
 struct SubLayout {              // per-slot "sub-graph blob": shortened graph + reset snapshot
-    int nn, m, es_max;
+    int nn, m, es_max;          // es_max: edge capacity of THIS layout (shared-memory tiers differ)
+    int lcap;                   // max row length of the window graph
     int off_prior;              // double[nn]
     int off_col;                // u16[nn]     original column of sub-VN j (sorted order)
     int off_voff;               // u16[nn+1]
-    int off_coff;               // u16[m+1]
+    int off_coff;               // u16[m+1]    first message slot of the check with rank q (rows padded to odd length)
+    int off_crank;              // u16[m]      rank q of check r (checks ranked by row length, descending)
     int off_synd;               // u8[m]
     int off_vnmask;             // i8[nn]      state after reset (bpgd.cpp:199-239)
     int off_cnmask;             // i8[m]
     int off_cndeg;              // u8[m]
+    int off_vperm;              // u16[nn]     VN ownership order (sorted by degree: uniform work per warp)
+    int off_cperm;              // u16[m]      check ownership order (sorted by row length)
     int fixed_bytes;            // multiple of 16: header + all of the above
-    int off_vrow, off_vpos, off_cvn;   // u16[es_max] each, 16-byte aligned
+    int off_vrow, off_vpos, off_cvn;   // u16[es_max] each, 16-byte aligned; vpos / cvn use jagged-diagonal slots
     int blob_bytes;             // multiple of 16
 };
 struct BlobHeader { int es; int status; int bad_rows; int shot; };   // 16 bytes at offset 0
@@ -190,6 +194,10 @@ __device__ __forceinline__ void block_bitonic_sort(double *key, u16 *idx, int NP
 // ----------------------------------------------------------------------------------------------
 // branch-path context (all pointers into shared memory)
 // ----------------------------------------------------------------------------------------------
+// Message slots: checks are ranked by row length (descending, rank q) and stored row after row in
+// rank order, every row padded to an ODD number of slots (the pad is a permanently dead NaN slot).
+// A warp that owns consecutive ranks runs loops of equal length L, and its 64-bit accesses
+// base + lane*L + k are bank-conflict free because L is odd.
 struct Ctx {
     int m, nn, es;
     int bad_rows;
@@ -198,13 +206,18 @@ struct Ctx {
     int A, A_sum, C, D;                 // bpgd.hpp:15 thresholds (ints)
     double *msg;
     const double *prior;
-    const u16 *voff, *vrow, *vpos, *coff, *cvn;
+    const u16 *voff, *vrow, *vpos, *cvn, *coff, *crank;
+    const u16 *vperm, *cperm;
     const u8 *synd;
     i8 *vn_mask, *error, *cn_mask, *dec;
     u8 *cn_deg, *flip;
     u32 *upar;
     double *red_d; int *red_i; int *misc;
 };
+
+// ownership: slot (tid, i) -> sorted index; odd rounds run backwards so that every warp gets a mix of
+// heavy and light nodes (nodes are sorted by degree)
+__device__ __forceinline__ int own_slot(int i, int tid, int T) { return (i & 1) ? i * T + (T - 1 - tid) : i * T + tid; }
 
 // BPGD::vn_set_value (bpgd.cpp:51-80) executed by ONE warp; lane k handles the k-th check of vn.
 template <bool HASMSG>
@@ -254,12 +267,12 @@ __device__ __forceinline__ int peel_warp(Ctx &c, int lane) {
                 cn = r + 1; continue;
             }
             clean = false;
-            const int p0 = c.coff[r], p1 = c.coff[r + 1];
+            const int q = c.crank[r], p0 = c.coff[q], len = c.coff[q + 1] - p0;
             int vn = -1;
-            for (int pb = p0; pb < p1 && vn < 0; pb += 32) {
-                int p = pb + lane, j = -1;
+            for (int kb = 0; kb < len && vn < 0; kb += 32) {
+                int k = kb + lane, j = -1;
                 bool und = false;
-                if (p < p1) { j = c.cvn[p]; und = c.vn_mask[j] < 0; }
+                if (k < len) { j = c.cvn[p0 + k]; und = (j != 0xffff) && (c.vn_mask[j] < 0); }
                 u32 ub = __ballot_sync(FULLMASK, und);
                 if (ub) vn = __shfl_sync(FULLMASK, j, __ffs(ub) - 1);
             }
@@ -290,58 +303,110 @@ __device__ __forceinline__ void init_msgs(Ctx &c) {
     const int T = blockDim.x, tid = threadIdx.x;
 #pragma unroll
     for (int i = 0; i < VPT; i++) {
-        const int j = tid + i * T;
-        if (j < c.nn) {
+        const int sl = own_slot(i, tid, T);
+        if (sl < c.nn) {
+            const int j = c.vperm[sl];
             const int e0 = c.voff[j], e1 = c.voff[j + 1];
             const double v = (c.vn_mask[j] < 0) ? c.prior[j] : dnan();
             for (int e = e0; e < e1; e++) c.msg[c.vpos[e]] = v;
         }
     }
+#pragma unroll
+    for (int i = 0; i < SWD_CPT; i++) {
+        const int q = own_slot(i, tid, T);
+        if (q < c.m) { const int p1 = c.coff[q + 1]; if (p1 > c.coff[q] && c.cvn[p1 - 1] == 0xffff) c.msg[p1 - 1] = dnan(); }
+    }
+}
+
+// one check update in min1/min2/argmin/parity form (== bpgd.cpp:103-148) on message slots p0 .. p0+len
+__device__ __forceinline__ void check_update(Ctx &c, int p0, int len, int cm, double fpos, double fneg) {
+    double m1 = SWD_BIG, m2 = SWD_BIG; int arg = -1, par = cm;
+    double *row = c.msg + p0;
+    if (len <= 32) {
+        u32 neg = 0, dead = 0;
+        for (int k = 0; k < len; k++) {
+            const double b = row[k];
+            const bool isdead = (b != b);                        // decided VN or pad slot
+            const bool isneg = (b <= 0.0);                       // false for NaN
+            const double a = isdead ? SWD_BIG : fmin(fabs(b), SWD_CLIP);
+            if (a < m1) arg = k;
+            m2 = fmin(m2, fmax(m1, a));
+            m1 = fmin(m1, a);
+            neg |= (u32)isneg << k; dead |= (u32)isdead << k;
+        }
+        par ^= __popc(neg) & 1;
+        u32 live = ~dead & (len == 32 ? 0xffffffffu : ((1u << len) - 1u));
+        while (live) {
+            const int k = __ffs(live) - 1; live &= live - 1;
+            const double mag = (k == arg) ? m2 : m1;
+            row[k] = mag * ((par ^ (int)((neg >> k) & 1u)) ? fneg : fpos);
+        }
+    } else {
+        for (int k = 0; k < len; k++) {
+            const double b = row[k];
+            if (b != b) continue;
+            const double a = fmin(fabs(b), SWD_CLIP);
+            if (a < m1) { m2 = m1; m1 = a; arg = k; } else if (a < m2) m2 = a;
+            par ^= (b <= 0.0);
+        }
+        for (int k = 0; k < len; k++) {
+            const double b = row[k];
+            if (b != b) continue;
+            const double mag = (k == arg) ? m2 : m1;
+            row[k] = mag * ((par ^ (int)(b <= 0.0)) ? fneg : fpos);
+        }
+    }
 }
 
 // BPGD::min_sum_log (bpgd.cpp:97-197) on the shortened graph, whole CTA.
-// h[i][s]: posterior history of VN (tid + i*T), slot s = iteration % 4.  Returns 1 on convergence.
+// h[i][s]: posterior history of the VN owned as slot i, ring slot s = iteration % 4.
+// Two barriers per iteration: the H*error == syndrome test of iteration `it` (bpgd.cpp:185-194;
+// decided VNs are folded into cn_mask) is evaluated by the check threads at the start of the next
+// check pass and reduced by the barrier that separates the check pass from the variable pass.
+// On a converged return the messages may already hold the next check pass; they are never used then.
 template <int VPT, int DMAX>
 __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter, u64 &edge_iters, u32 &vn_iters, u32 &cn_iters,
                                       int *iters_done = nullptr) {
     const int T = blockDim.x, tid = threadIdx.x;
     const double fpos = c.factor, fneg = -c.factor;
-    for (int it = 0; it < num_iter; it++) {
-        // ---- check pass: min1/min2/argmin/parity, then overwrite b2c by c2b in place
-        for (int r = tid; r < c.m; r += T) {
-            c.upar[r] = 0;
+    for (int it = 0; it <= num_iter; it++) {
+        // ---- check pass (+ convergence test of the previous iteration)
+        int mism = (it > 0) ? c.bad_rows : 0;
+        const bool last = (it == num_iter);
+#pragma unroll
+        for (int i = 0; i < SWD_CPT; i++) {
+            const int q = own_slot(i, tid, T);
+            if (q >= c.m) continue;
+            const int r = c.cperm[q];
             const int cm = c.cn_mask[r];
-            if (cm < 0) continue;
+            if (it > 0) {
+                const int f = (cm < 0) ? 0 : (c.upar[r] != (u32)cm);
+                c.flip[r] = (u8)f;
+                mism |= f;
+            }
+            c.upar[r] = 0;
+            if (cm < 0 || last) continue;
             cn_iters++;
-            const int p0 = c.coff[r], p1 = c.coff[r + 1];
-            double m1 = SWD_BIG, m2 = SWD_BIG; int arg = -1, par = cm;
-            for (int p = p0; p < p1; p++) {
-                const double b = c.msg[p];
-                if (b != b) continue;                       // decided VN
-                const double a = fmin(fabs(b), SWD_CLIP);
-                if (a < m1) { m2 = m1; m1 = a; arg = p; } else if (a < m2) m2 = a;
-                par ^= (b <= 0.0);
-            }
-            for (int p = p0; p < p1; p++) {
-                const double b = c.msg[p];
-                if (b != b) continue;
-                const double mag = (p == arg) ? m2 : m1;
-                c.msg[p] = mag * ((par ^ (int)(b <= 0.0)) ? fneg : fpos);
-            }
+            { const int p0 = c.coff[q]; check_update(c, p0, c.coff[q + 1] - p0, cm, fpos, fneg); }
         }
-        __syncthreads();
+        if (it > 0) {
+            if (!__syncthreads_or(mism)) { if (iters_done) *iters_done = it; return 1; }
+        } else __syncthreads();
+        if (last) break;
         // ---- variable pass: ordered prefix / suffix sums (bpgd.cpp:151-182)
 #pragma unroll
         for (int i = 0; i < VPT; i++) {
-            const int j = tid + i * T;
-            if (j < c.nn && c.vn_mask[j] < 0) {
-                const int e0 = c.voff[j], d = c.voff[j + 1] - e0;
+            const int sl = own_slot(i, tid, T);
+            int j = -1, e0 = 0, d = 0;
+            if (sl < c.nn) { j = c.vperm[sl]; if (c.vn_mask[j] < 0) { e0 = c.voff[j]; d = c.voff[j + 1] - e0; } else j = -1; }
+            const int dw = __reduce_max_sync(FULLMASK, d);     // VNs are owned in degree order: ~uniform per warp
+            if (j >= 0) {
                 double cc[DMAX], pre[DMAX]; int pp[DMAX];
                 double t = c.prior[j];
 #pragma unroll
-                for (int k = 0; k < DMAX; k++) if (k < d) { pp[k] = c.vpos[e0 + k]; cc[k] = c.msg[pp[k]]; }
+                for (int k = 0; k < DMAX; k++) { if (k >= dw) break; if (k < d) { pp[k] = c.vpos[e0 + k]; cc[k] = c.msg[pp[k]]; } }
 #pragma unroll
-                for (int k = 0; k < DMAX; k++) if (k < d) { pre[k] = t; t += cc[k]; }
+                for (int k = 0; k < DMAX; k++) { if (k >= dw) break; if (k < d) { pre[k] = t; t += cc[k]; } }
                 switch (it & 3) { case 0: h[i][0] = t; break; case 1: h[i][1] = t; break; case 2: h[i][2] = t; break; default: h[i][3] = t; }
                 const int hard = (t <= 0.0);
                 c.error[j] = (i8)hard;
@@ -353,15 +418,6 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
             }
         }
         __syncthreads();
-        // ---- H*error == syndrome (bpgd.cpp:185-194): decided VNs are folded into cn_mask
-        int mism = c.bad_rows;
-        for (int r = tid; r < c.m; r += T) {
-            const int cm = c.cn_mask[r];
-            const int f = (cm < 0) ? 0 : (c.upar[r] != (u32)cm);
-            c.flip[r] = (u8)f;
-            mism |= f;
-        }
-        if (!__syncthreads_or(mism)) { if (iters_done) *iters_done = it + 1; return 1; }
     }
     if (iters_done) *iters_done = num_iter > 0 ? num_iter : 0;
     return 0;
@@ -379,8 +435,9 @@ __device__ __forceinline__ int select_vn(Ctx &c, const double (&h)[VPT][4], int 
     if (tid == 0) c.misc[0] = 0x7fffffff;                    // failpos
 #pragma unroll
     for (int i = 0; i < VPT; i++) {
-        const int j = tid + i * T;
-        if (j < c.nn) {
+        const int sl = own_slot(i, tid, T);
+        if (sl < c.nn) {
+            const int j = c.vperm[sl];
             int action = -1;
             if (c.vn_mask[j] < 0) {
                 const int e0 = c.voff[j], d = c.voff[j + 1] - e0;
@@ -400,8 +457,8 @@ __device__ __forceinline__ int select_vn(Ctx &c, const double (&h)[VPT][4], int 
                     else if (!c.low_error && nf >= 3 && geD) action = 0;
                     else if (!c.low_error && leA && sum < (double)c.A_sum) action = 1;
                     else {
-                        if (sum < best) { best = sum; bi = j; }
-                        if (neg && sum < bestn) { bestn = sum; bni = j; }
+                        if (sum < best || (sum == best && j < bi)) { best = sum; bi = j; }      // sum < MAX_PM is implied
+                        if (neg && (sum < bestn || (sum == bestn && j < bni))) { bestn = sum; bni = j; }
                     }
                 }
             }
@@ -414,22 +471,25 @@ __device__ __forceinline__ int select_vn(Ctx &c, const double (&h)[VPT][4], int 
         // per check: how many of its undecided VNs were decimated, with which parity, last scan index
         int ndg[SWD_CPT], nmk[SWD_CPT];                      // SWD_CPT checks per thread (m <= SWD_CPT*T)
 #pragma unroll
-        for (int q = 0; q < SWD_CPT; q++) {
-            const int r = tid + q * T;
-            ndg[q] = -1; nmk[q] = 0;
-            if (r >= c.m) continue;
+        for (int i = 0; i < SWD_CPT; i++) {
+            const int q = own_slot(i, tid, T);
+            ndg[i] = -1; nmk[i] = 0;
+            if (q >= c.m) continue;
+            const int r = c.cperm[q];
             const int cm = c.cn_mask[r];
             if (cm < 0) continue;
             int cnt = 0, par = 0, last = -1;
-            for (int p = c.coff[r]; p < c.coff[r + 1]; p++) {
+            const int p0 = c.coff[q], p1 = c.coff[q + 1];
+            for (int p = p0; p < p1; p++) {
                 const int j = c.cvn[p];
+                if (j == 0xffff) continue;
                 const int a = c.dec[j];
                 if (a >= 0) { cnt++; par ^= a; last = max(last, j); }
             }
             if (cnt) {
                 const int nd = (int)c.cn_deg[r] - cnt, nm = cm ^ par;
                 if (nd == 0 && nm != 0) atomicMin(&c.misc[0], last);
-                ndg[q] = nd; nmk[q] = (nd == 0) ? -1 : nm;
+                ndg[i] = nd; nmk[i] = (nd == 0) ? -1 : nm;
             }
         }
         __syncthreads();
@@ -437,24 +497,30 @@ __device__ __forceinline__ int select_vn(Ctx &c, const double (&h)[VPT][4], int 
         if (failpos != 0x7fffffff) {                         // contradiction: branch is dead
 #pragma unroll
             for (int i = 0; i < VPT; i++) {
-                const int j = tid + i * T;
-                if (j < c.nn && c.dec[j] >= 0 && j <= failpos) { c.vn_mask[j] = c.dec[j]; c.error[j] = c.dec[j]; }
+                const int sl = own_slot(i, tid, T);
+                if (sl < c.nn) {
+                    const int j = c.vperm[sl];
+                    if (c.dec[j] >= 0 && j <= failpos) { c.vn_mask[j] = c.dec[j]; c.error[j] = c.dec[j]; }
+                }
             }
             __syncthreads();
             guess = -1;
             return -1;
         }
 #pragma unroll
-        for (int q = 0; q < SWD_CPT; q++) {
-            const int r = tid + q * T;
-            if (r < c.m && ndg[q] >= 0) { c.cn_deg[r] = (u8)ndg[q]; c.cn_mask[r] = (i8)nmk[q]; }
+        for (int i = 0; i < SWD_CPT; i++) {
+            const int q = own_slot(i, tid, T);
+            if (q < c.m && ndg[i] >= 0) { const int r = c.cperm[q]; c.cn_deg[r] = (u8)ndg[i]; c.cn_mask[r] = (i8)nmk[i]; }
         }
 #pragma unroll
         for (int i = 0; i < VPT; i++) {
-            const int j = tid + i * T;
-            if (j < c.nn && c.dec[j] >= 0) {
-                c.vn_mask[j] = c.dec[j]; c.error[j] = c.dec[j];
-                for (int e = c.voff[j]; e < c.voff[j + 1]; e++) c.msg[c.vpos[e]] = dnan();
+            const int sl = own_slot(i, tid, T);
+            if (sl < c.nn) {
+                const int j = c.vperm[sl];
+                if (c.dec[j] >= 0) {
+                    c.vn_mask[j] = c.dec[j]; c.error[j] = c.dec[j];
+                    for (int e = c.voff[j]; e < c.voff[j + 1]; e++) c.msg[c.vpos[e]] = dnan();
+                }
             }
         }
     }

@@ -127,11 +127,11 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
 // ----------------------------------------------------------------------------------------------
 // K2: sort + reset
 // ----------------------------------------------------------------------------------------------
-struct SortSmem { int off_key, off_idx, off_posof, off_blob, off_u32a, off_u32b, off_wt, off_error, off_misc, total; int np2; };
+struct SortSmem { int off_key, off_idx, off_posof, off_blob, off_u32a, off_u32b, off_u32c, off_wt, off_error, off_misc, off_bins, total; int np2; };
 
 __global__ void __launch_bounds__(1024)
 sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayout L, GdgDev P, SortSmem S,
-                  u8 *__restrict__ dec_out) {
+                  u8 *__restrict__ dec_out, int capA) {
     extern __shared__ __align__(16) unsigned char smem[];
     double *key = (double *)(smem + S.off_key);
     u16 *idx = (u16 *)(smem + S.off_idx);
@@ -139,6 +139,7 @@ sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayo
     unsigned char *blob = smem + S.off_blob;
     u32 *ua = (u32 *)(smem + S.off_u32a);         // [nn+1]
     u32 *ub = (u32 *)(smem + S.off_u32b);         // [m+1]
+    u32 *uc = (u32 *)(smem + S.off_u32c);         // [m+1]
     u32 *wt = (u32 *)(smem + S.off_wt);
     i8 *s_error = (i8 *)(smem + S.off_error);
     int *misc = (int *)(smem + S.off_misc);
@@ -150,6 +151,7 @@ sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayo
     u16 *col = (u16 *)(blob + L.off_col);
     u16 *voff = (u16 *)(blob + L.off_voff);
     u16 *coff = (u16 *)(blob + L.off_coff);
+    u16 *crank = (u16 *)(blob + L.off_crank);
     u8 *s_synd = blob + L.off_synd;
     i8 *vn_mask = (i8 *)(blob + L.off_vnmask);
     i8 *cn_mask = (i8 *)(blob + L.off_cnmask);
@@ -157,6 +159,9 @@ sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayo
     u16 *vrow = (u16 *)(blob + L.off_vrow);
     u16 *vpos = (u16 *)(blob + L.off_vpos);
     u16 *cvn = (u16 *)(blob + L.off_cvn);
+    u16 *vperm = (u16 *)(blob + L.off_vperm);
+    u16 *cperm = (u16 *)(blob + L.off_cperm);
+    u32 *bins = (u32 *)(smem + S.off_bins);       // [17 + 256]
 
     const int count = ws.counters[0];
     for (int slot = blockIdx.x; slot < count; slot += gridDim.x) {
@@ -191,37 +196,58 @@ sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayo
             for (int q = g.rp[r]; q < g.rp[r + 1]; q++) cnt += (posof[g.rc[q]] < nn);
             ub[r] = (u32)cnt;
         }
-        if (tid == 0) ub[m] = 0;
         __syncthreads();
-        block_excl_scan(ub, m + 1, wt);
+        // kept-row lengths are in ub[0..m): rank the checks by length (descending); message slots are laid out
+        // row after row in rank order, each row padded to an odd number of slots (bank-conflict-free warps)
+        for (int i = tid; i < 17 + 256; i += T) bins[i] = 0;
+        __syncthreads();
+        for (int j = tid; j < nn; j += T) atomicAdd(&bins[16 - (int)(ua[j + 1] - ua[j])], 1u);
+        for (int r = tid; r < m; r += T) atomicAdd(&bins[17 + 255 - (int)ub[r]], 1u);
+        __syncthreads();
+        if (tid == 0) { u32 a = 0; for (int i = 0; i < 17; i++) { u32 t = bins[i]; bins[i] = a; a += t; } }
+        if (tid == 32) { u32 a = 0; for (int i = 17; i < 17 + 256; i++) { u32 t = bins[i]; bins[i] = a; a += t; } }
+        __syncthreads();
+        for (int j = tid; j < nn; j += T) vperm[atomicAdd(&bins[16 - (int)(ua[j + 1] - ua[j])], 1u)] = (u16)j;
         int bad = 0;
         for (int r = tid; r < m; r += T) {
-            int p = (int)ub[r];
-            const int d = (int)ub[r + 1] - p;
-            coff[r] = (u16)p;
-            for (int q = g.rp[r]; q < g.rp[r + 1]; q++) {
-                const int j = posof[g.rc[q]];
-                if (j < nn) {
-                    cvn[p] = (u16)j;
-                    for (int e = voff[j]; e < voff[j + 1]; e++) if (vrow[e] == r) vpos[e] = (u16)p;
-                    p++;
-                }
-            }
+            const int d = (int)ub[r];
+            const int q = (int)atomicAdd(&bins[17 + 255 - d], 1u);
+            cperm[q] = (u16)r; crank[r] = (u16)q;
             const int s = synd[(size_t)shot * m + r];
             s_synd[r] = (u8)s;
             cn_deg[r] = (u8)d;
             cn_mask[r] = (d == 0) ? (i8)-1 : (i8)s;          // bpgd.cpp:210-217
             bad |= (d == 0 && s);
         }
-        if (tid == 0) { coff[m] = (u16)ub[m]; misc[0] = 0x7fffffff; }
+        if (tid == 0) misc[0] = 0x7fffffff;
         bad = __syncthreads_or(bad);
+        for (int q = tid; q < m; q += T) { const u32 d = ub[cperm[q]]; uc[q] = (d > 0 && !(d & 1u)) ? d + 1 : d; }
+        if (tid == 0) uc[m] = 0;
+        __syncthreads();
+        block_excl_scan(uc, m + 1, wt);
+        const int nslots = (int)uc[m];
+        for (int q = tid; q <= m; q += T) coff[q] = (u16)uc[q];
+        for (int r = tid; r < m; r += T) {
+            const int q = crank[r];
+            int p = (int)uc[q];
+            for (int qq = g.rp[r]; qq < g.rp[r + 1]; qq++) {
+                const int j = posof[g.rc[qq]];
+                if (j < nn) {
+                    cvn[p] = (u16)j;
+                    for (int e = voff[j]; e < voff[j + 1]; e++) if (vrow[e] == r) vpos[e] = (u16)p;
+                    p++;
+                }
+            }
+            if (p < (int)uc[q + 1]) cvn[p] = (u16)0xffff;      // pad slot
+        }
+        __syncthreads();
 
         int status = 0;
         if (P.kind == SWD_KIND_OSD_WINDOW && bad) {
             // osd_window.pyx:178-181: decimating the dropped columns in sorted order hits a check whose
             // every VN is dropped while its syndrome bit is 1; failure at the last of them in scan order.
             for (int r = tid; r < m; r += T) {
-                if (ub[r + 1] == ub[r] && s_synd[r]) {
+                if (ub[r] == 0 && s_synd[r]) {
                     int last = -1;
                     for (int q = g.rp[r]; q < g.rp[r + 1]; q++) last = max(last, (int)posof[g.rc[q]]);
                     atomicMin(&misc[0], last);
@@ -235,7 +261,7 @@ sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayo
             for (int j = nn + tid; j < n; j += T) dec_out[(size_t)shot * n + idx[j]] = 0;   // pyx:250-251 / :270-271
             Ctx c;
             c.m = m; c.nn = nn; c.es = es; c.msg = nullptr; c.prior = prior; c.voff = voff; c.vrow = vrow; c.vpos = vpos;
-            c.coff = coff; c.cvn = cvn; c.synd = s_synd; c.vn_mask = vn_mask; c.error = s_error; c.cn_mask = cn_mask;
+            c.coff = coff; c.crank = crank; c.cvn = cvn; c.vperm = vperm; c.cperm = cperm; c.synd = s_synd; c.vn_mask = vn_mask; c.error = s_error; c.cn_mask = cn_mask;
             c.cn_deg = cn_deg;
             if (wid == 0) {
                 int st = peel_warp<false>(c, lane);                                          // bpgd.cpp:236
@@ -248,13 +274,13 @@ sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayo
                 for (int j = tid; j < nn; j += T) if (vn_mask[j] >= 0) dec_out[(size_t)shot * n + col[j]] = (u8)vn_mask[j];
             }
         }
-        if (tid == 0) { hdr->es = es; hdr->status = status; hdr->bad_rows = bad; hdr->shot = shot; }
+        if (tid == 0) { hdr->es = nslots; hdr->status = status; hdr->bad_rows = bad; hdr->shot = shot; if (nslots > capA) atomicAdd(&ws.counters[8], 1); }
         __syncthreads();
         // publish the blob (16-byte vectors): fixed part + the three es-sized arrays
         {
             uint4 *dst = (uint4 *)(ws.blob + (size_t)slot * L.blob_bytes);
             const uint4 *src = (const uint4 *)blob;
-            const int nfix = L.fixed_bytes >> 4, nvar = (es * 2 + 15) >> 4;
+            const int nfix = L.fixed_bytes >> 4, nvar = (nslots * 2 + 15) >> 4;
             for (int i = tid; i < nfix; i += T) dst[i] = src[i];
             for (int i = tid; i < nvar; i += T) {
                 dst[(L.off_vrow >> 4) + i] = src[(L.off_vrow >> 4) + i];
@@ -304,9 +330,9 @@ __device__ __forceinline__ void record_result(Ctx &c, u8 *rec, int converged, co
     }
 }
 
-template <int VPT, int DMAX, int MAXT>
-__global__ void __launch_bounds__(MAXT)
-path_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int phase) {
+template <int VPT, int DMAX, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int phase, int tier, int capA) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
     unsigned char *blob = smem;
@@ -315,7 +341,9 @@ path_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int phase) {
     c.m = L.m; c.nn = L.nn; c.factor = P.factor; c.low_error = P.low_error;
     c.prior = (const double *)(blob + L.off_prior);
     c.voff = (const u16 *)(blob + L.off_voff); c.coff = (const u16 *)(blob + L.off_coff);
+    c.crank = (const u16 *)(blob + L.off_crank);
     c.vrow = (const u16 *)(blob + L.off_vrow); c.vpos = (const u16 *)(blob + L.off_vpos); c.cvn = (const u16 *)(blob + L.off_cvn);
+    c.vperm = (const u16 *)(blob + L.off_vperm); c.cperm = (const u16 *)(blob + L.off_cperm);
     c.synd = blob + L.off_synd;
     c.msg = (double *)(st + S.off_msg);
     c.vn_mask = (i8 *)(st + S.off_vnmask); c.error = (i8 *)(st + S.off_error); c.dec = (i8 *)(st + S.off_dec);
@@ -330,7 +358,7 @@ path_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int phase) {
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     u32 mphase = 0;
-    const int count = ws.counters[0];
+    const int count = (tier == 1 && ws.counters[8] == 0) ? 0 : ws.counters[0];
     const int npaths = (phase == 0) ? ((P.kind == SWD_KIND_BPGDG && P.multi_thread) ? 1 + P.n_tree : 1) : P.n_side;
     const long long total = (long long)npaths * count;
     u64 edge_iters = 0, bp_calls = 0, paths_run = 0;
@@ -338,14 +366,15 @@ path_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int phase) {
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) c.misc[2] = atomicAdd(&ws.counters[1 + phase], 1);
+        if (tid == 0) c.misc[2] = atomicAdd(&ws.counters[1 + phase + 3 * tier], 1);
         __syncthreads();
         const long long item = c.misc[2];
         if (item >= total) break;
         const int path = (int)(item / count), slot = (int)(item % count);
-        const unsigned char *gblob = ws.blob + (size_t)slot * L.blob_bytes;
+        const unsigned char *gblob = ws.blob + (size_t)slot * LG.blob_bytes;
         const BlobHeader gh = *(const BlobHeader *)gblob;
         if (gh.status != 0) continue;
+        if ((gh.es > capA) != (tier == 1)) continue;          // tier A: typical shots; tier B: oversized shortened graphs
         const SideHeader *sh = nullptr;
         if (phase == 1) {
             sh = (const SideHeader *)(ws.side + ((size_t)slot * P.n_side + path) * P.side_stride);
@@ -358,9 +387,9 @@ path_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int phase) {
             mbar_expect_tx(bar, (u32)L.fixed_bytes + 3 * vb);
             bulk_g2s(blob, gblob, (u32)L.fixed_bytes, bar);
             if (vb) {
-                bulk_g2s(blob + L.off_vrow, gblob + L.off_vrow, vb, bar);
-                bulk_g2s(blob + L.off_vpos, gblob + L.off_vpos, vb, bar);
-                bulk_g2s(blob + L.off_cvn, gblob + L.off_cvn, vb, bar);
+                bulk_g2s(blob + L.off_vrow, gblob + LG.off_vrow, vb, bar);
+                bulk_g2s(blob + L.off_vpos, gblob + LG.off_vpos, vb, bar);
+                bulk_g2s(blob + L.off_cvn, gblob + LG.off_cvn, vb, bar);
             }
         }
         mbar_wait(bar, mphase);
@@ -428,13 +457,16 @@ path_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int phase) {
                     double best = 0.0; int bi = 0x7fffffff;   // argmax |h[3]|, first wins
 #pragma unroll
                     for (int i = 0; i < VPT; i++) {
-                        const int j = tid + i * T;
-                        if (j < c.nn && c.vn_mask[j] < 0) { const double a = -fabs(h[i][3]); if (a < best) { best = a; bi = j; } }
+                        const int sl = own_slot(i, tid, T);
+                        if (sl < c.nn) {
+                            const int j = c.vperm[sl];
+                            if (c.vn_mask[j] < 0) { const double a = -fabs(h[i][3]); if (a < best || (a == best && a < 0.0 && j < bi)) { best = a; bi = j; } }
+                        }
                     }
                     block_argmin(best, bi, c.red_d, c.red_i);
                     if (bi == 0x7fffffff) break;
 #pragma unroll
-                    for (int i = 0; i < VPT; i++) if (tid + i * T == bi) c.misc[3] = (h[i][3] > 0.0) ? 0 : 1;
+                    for (int i = 0; i < VPT; i++) { const int sl = own_slot(i, tid, T); if (sl < c.nn && c.vperm[sl] == bi) c.misc[3] = (h[i][3] > 0.0) ? 0 : 1; }
                     __syncthreads();
                     pend_vn = bi; pend_val = c.misc[3]; depth++;
                     continue;

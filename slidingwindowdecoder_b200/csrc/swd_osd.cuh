@@ -52,9 +52,9 @@ static inline void osd_free_outputs(OsdWork *ow) {
 // ----------------------------------------------------------------------------------------------
 // post-BP on the shortened graph (osd_window.pyx:187-192): one CTA per non-converged shot
 // ----------------------------------------------------------------------------------------------
-template <int VPT, int DMAX, int MAXT>
-__global__ void __launch_bounds__(MAXT)
-post_bp_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int n, OsdWork ow, long long chunk_base) {
+template <int VPT, int DMAX, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+post_bp_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int n, OsdWork ow, long long chunk_base, int tier, int capA) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
     unsigned char *blob = smem;
@@ -63,7 +63,9 @@ post_bp_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int n, OsdWork o
     c.m = L.m; c.nn = L.nn; c.factor = P.factor; c.low_error = 0;
     c.prior = (const double *)(blob + L.off_prior);
     c.voff = (const u16 *)(blob + L.off_voff); c.coff = (const u16 *)(blob + L.off_coff);
+    c.crank = (const u16 *)(blob + L.off_crank);
     c.vrow = (const u16 *)(blob + L.off_vrow); c.vpos = (const u16 *)(blob + L.off_vpos); c.cvn = (const u16 *)(blob + L.off_cvn);
+    c.vperm = (const u16 *)(blob + L.off_vperm); c.cperm = (const u16 *)(blob + L.off_cperm);
     c.synd = blob + L.off_synd;
     c.msg = (double *)(st + S.off_msg);
     c.vn_mask = (i8 *)(st + S.off_vnmask); c.error = (i8 *)(st + S.off_error); c.dec = (i8 *)(st + S.off_dec);
@@ -78,16 +80,17 @@ post_bp_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int n, OsdWork o
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     u32 mphase = 0;
-    const int count = ws.counters[0];
+    const int count = (tier == 1 && ws.counters[8] == 0) ? 0 : ws.counters[0];
     u64 edge_iters = 0, bp_calls = 0, paths_run = 0; u32 vn_iters = 0, cn_iters = 0;
     for (;;) {
         __syncthreads();
-        if (tid == 0) c.misc[2] = atomicAdd(&ws.counters[1], 1);
+        if (tid == 0) c.misc[2] = atomicAdd(&ws.counters[1 + 3 * tier], 1);
         __syncthreads();
         const int slot = c.misc[2];
         if (slot >= count) break;
-        const unsigned char *gblob = ws.blob + (size_t)slot * L.blob_bytes;
+        const unsigned char *gblob = ws.blob + (size_t)slot * LG.blob_bytes;
         const BlobHeader gh = *(const BlobHeader *)gblob;
+        if ((gh.es > capA) != (tier == 1)) continue;
         if (tid == 0) ow.need_osd[slot] = 0;
         if (gh.status != 0) continue;
         if (tid == 0) {
@@ -96,9 +99,9 @@ post_bp_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int n, OsdWork o
             mbar_expect_tx(bar, (u32)L.fixed_bytes + 3 * vb);
             bulk_g2s(blob, gblob, (u32)L.fixed_bytes, bar);
             if (vb) {
-                bulk_g2s(blob + L.off_vrow, gblob + L.off_vrow, vb, bar);
-                bulk_g2s(blob + L.off_vpos, gblob + L.off_vpos, vb, bar);
-                bulk_g2s(blob + L.off_cvn, gblob + L.off_cvn, vb, bar);
+                bulk_g2s(blob + L.off_vrow, gblob + LG.off_vrow, vb, bar);
+                bulk_g2s(blob + L.off_vpos, gblob + LG.off_vpos, vb, bar);
+                bulk_g2s(blob + L.off_cvn, gblob + LG.off_cvn, vb, bar);
             }
         }
         mbar_wait(bar, mphase);
@@ -113,9 +116,10 @@ post_bp_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int n, OsdWork o
         const double *hg = ws.hist + (size_t)slot * n * 4;
 #pragma unroll
         for (int i = 0; i < VPT; i++) {
-            const int j = tid + i * T;
+            const int sl = own_slot(i, tid, T);
+            const int j = (sl < c.nn) ? (int)c.vperm[sl] : -1;
 #pragma unroll
-            for (int s = 0; s < 4; s++) h[i][s] = (j < c.nn) ? hg[(size_t)col[j] * 4 + s] : 0.0;
+            for (int s = 0; s < 4; s++) h[i][s] = (j >= 0) ? hg[(size_t)col[j] * 4 + s] : 0.0;
         }
         __syncthreads();
         paths_run++;
@@ -130,8 +134,9 @@ post_bp_kernel(Workspace ws, SubLayout L, PathSmem S, GdgDev P, int n, OsdWork o
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < VPT; i++) {
-            const int j = tid + i * T;
-            if (j < c.nn) {
+            const int sl = own_slot(i, tid, T);
+            if (sl < c.nn) {
+                const int j = c.vperm[sl];
                 const int cj = col[j];
                 const int vm = c.vn_mask[j];
                 double k;
@@ -451,25 +456,27 @@ static inline int osd_setup(int m, int n, int nn, int rank, int method, int orde
     return 0;
 }
 
-typedef void (*post_fn_t)(Workspace, SubLayout, PathSmem, GdgDev, int, OsdWork, long long);
+typedef void (*post_fn_t)(Workspace, SubLayout, SubLayout, PathSmem, GdgDev, int, OsdWork, long long, int, int);
 static inline post_fn_t pick_post_kernel(int dmax, int T) {
-    if (dmax == 8) {
-        if (T <= 128) return post_bp_kernel<4, 8, 128>;
-        if (T <= 512) return post_bp_kernel<4, 8, 512>;
-        return post_bp_kernel<4, 8, 1024>;
+    if (dmax == 6) {
+        if (T <= 128) return post_bp_kernel<4, 6, 128, 5>;
+        if (T <= 512) return post_bp_kernel<4, 6, 512, 1>;
+        return post_bp_kernel<4, 6, 1024, 1>;
     }
-    if (T <= 128) return post_bp_kernel<4, 16, 128>;
-    return post_bp_kernel<4, 16, 1024>;
+    if (T <= 128) return post_bp_kernel<4, 16, 128, 3>;
+    return post_bp_kernel<4, 16, 1024, 1>;
 }
 
 // everything after sort_reset for the osd_window kind
-static inline int osd_launch(const GraphDev &g, const u8 *d_synd, const Workspace &ws, const SubLayout &L, const PathSmem &PS,
+static inline int osd_launch(const GraphDev &g, const u8 *d_synd, const Workspace &ws, const SubLayout &L, const SubLayout &LsA,
+                             const SubLayout &LsB, const PathSmem &PS, const PathSmem &PSB, int capA, int grid3B, size_t smem3B,
                              const GdgDev &P, const OsdSmem &OS, const OsdWork &ow, int dmax, int T3, int grid3, size_t smem3,
                              int T5, int grid5, int method, int order_w, int rank, u8 *d_corr, u8 *d_conv, double *d_pm,
                              long long B, long long chunk_base, cudaStream_t s, uint64_t *launches, u8 *in_list) {
     post_fn_t post = pick_post_kernel(dmax, T3);
     if (cudaFuncSetAttribute(post, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -3;
-    post<<<grid3, T3, smem3, s>>>(ws, L, PS, P, g.n, ow, chunk_base);
+    post<<<grid3, T3, smem3, s>>>(ws, L, LsA, PS, P, g.n, ow, chunk_base, 0, capA);
+    if (capA < L.es_max) { post<<<grid3B, T3, smem3B, s>>>(ws, L, LsB, PSB, P, g.n, ow, chunk_base, 1, capA); *launches += 1; }
     osd_kernel<<<grid5, T5, OS.total, s>>>(g, d_synd, ws, L, P, OS, ow, method, order_w, rank, d_corr, d_pm, chunk_base);
     osd_finish_kernel<<<grid5, 128, 0, s>>>(ws, L, P, ow, g.n, d_corr, d_conv, chunk_base);
     cudaMemsetAsync(in_list, 0, (size_t)B, s);
