@@ -43,12 +43,41 @@ def build_plan():
 _CPU = {}
 
 
-def _cpu_init(plan_blob):
-    from oracle.oracle import Oracle
+def _cpu_init(plan_blob, use_ref=False):
+    """use_ref: decode with oracle/_ref (the reference's own bpgd.cpp, 15 std::threads per shot) instead of the C port."""
+    import ctypes as C
+    from oracle.oracle import Oracle, ref_lib, _p
     _CPU["plan"] = plan_blob
     _CPU["orc"] = [Oracle(w.mat, w.prior) for w in plan_blob.windows]
     _CPU["chkT"] = plan_blob.chk.T.tocsr()
     _CPU["obsT"] = plan_blob.obs.T.tocsr()
+    _CPU["ref"] = None
+    if use_ref:
+        lib = ref_lib()
+        lib.ref_gdg_create.restype = C.c_void_p
+        hs = []
+        for o in _CPU["orc"]:
+            h = lib.ref_gdg_create(o.m, o.n, _p(o.cp, C.c_int), _p(o.cr, C.c_int), _p(o.llr, C.c_double), GDG_KW["max_iter"],
+                                   C.c_double(1.0), GDG_KW["max_iter_per_step"], GDG_KW["max_step"], GDG_KW["max_tree_depth"],
+                                   GDG_KW["max_side_depth"], GDG_KW["max_tree_branch_step"], GDG_KW["max_side_branch_step"],
+                                   C.c_double(1.0), 0, 0)
+            hs.append(C.c_void_p(h))
+        _CPU["ref"] = (lib, hs)
+
+
+def _decode_window(i, synd):
+    import ctypes as C
+    from oracle.oracle import _p
+    if _CPU["ref"] is None:
+        dec, conv, _, _ = _CPU["orc"][i].bpgdg_batch(synd, **GDG_KW)
+        return dec
+    lib, hs = _CPU["ref"]
+    o = _CPU["orc"][i]
+    s = np.ascontiguousarray(synd.astype(np.int8))
+    dec = np.zeros((s.shape[0], o.n), dtype=np.int8)
+    conv = np.zeros(s.shape[0], dtype=np.int8)
+    lib.ref_gdg_decode_batch(hs[i], _p(s, C.c_int8), C.c_longlong(s.shape[0]), _p(dec, C.c_int8), _p(conv, C.c_int8))
+    return dec
 
 
 def _cpu_decode_shard(args):
@@ -58,8 +87,8 @@ def _cpu_decode_shard(args):
     B = det.shape[0]
     new_det = det.copy()
     total = np.zeros((B, plan.chk.shape[1]), dtype=np.uint8)
-    for w, orc in zip(plan.windows, _CPU["orc"]):
-        dec, conv, _, _ = orc.bpgdg_batch(new_det[:, w.row0:w.row1], **GDG_KW)
+    for w in plan.windows:
+        dec = _decode_window(w.index, new_det[:, w.row0:w.row1])
         total[:, w.col0:w.col0 + w.ncommit] = dec[:, :w.ncommit]
         upd = np.asarray(total[:, w.col0:w.col0 + w.ncommit].astype(np.float32) @ _CPU["chkT"][w.col0:w.col0 + w.ncommit].astype(np.float32)) % 2
         new_det = (new_det + upd.astype(np.uint8)) % 2
@@ -77,15 +106,16 @@ def sample_host(plan, shots, seed):
 class CpuArm:
     """Oracle port on all host cores (process-level sharding over shots: the 'all-core' CPU figure of BASELINE.md §3)."""
 
-    def __init__(self, plan):
+    def __init__(self, plan, use_ref=False, procs=None):
         import multiprocessing as mp
         self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.procs = procs or self.cores
         self.plan = plan
-        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init, initargs=(plan,))
+        self.pool = mp.get_context("fork").Pool(self.procs, initializer=_cpu_init, initargs=(plan, use_ref))
 
     def run(self, det, obs):
         B = det.shape[0]
-        nshard = min(B, self.cores * 4)
+        nshard = min(B, self.procs * 4)
         idx = np.array_split(np.arange(B), nshard)
         t0 = time.perf_counter()
         res = self.pool.map(_cpu_decode_shard, [(det[i], obs[i]) for i in idx if len(i)])
@@ -178,6 +208,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from slidingwindowdecoder_b200.sliding_window import SlidingWindowDecoder
+    from slidingwindowdecoder_b200.distributed import reduce_counters, max_over_ranks
     plan = build_plan()
     swd = SlidingWindowDecoder(plan, decoder="gdg", device=local, **GDG_KW)
     B, K, W = args.batch, args.steps, args.warmup
@@ -221,13 +252,9 @@ def run_ours(args):
             counts += fn(i)
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-            dist.all_reduce(counts, op=dist.ReduceOp.SUM)      # the path's only collective: failure counters
-        return ms, counts.cpu().numpy()
+        ms = max_over_ranks(e0.elapsed_time(e1), dev)                # device time, max over ranks
+        counts = reduce_counters(counts, dev)                        # the path's only collective: failure counters
+        return ms, np.array(counts)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -285,6 +312,9 @@ def run_ours(args):
                 "share_of_kernel_time": round(path_ms / tot_k, 4),
                 "note": "messages are held in shared memory, so algorithmic message bytes/s is compared with the HBM "
                         "roof only to show on-chip residency; see smem_achieved_gbs for the binding on-chip roof",
+                "smem": {"achieved": round(achieved, 1), "peak": round(148 * 128 * 1.965, 1), "unit": "GB/s",
+                         "frac": round(achieved / (148 * 128 * 1.965), 4),
+                         "note": "same algorithmic bytes against the shared-memory roof (148 SMs x 128 B/clk x 1.965 GHz)"},
                 "pre_bp_achieved_gbs": round(pre_bytes / (ktimes.get("pre_bp", [1e-9, 0])[0] / 1e3) / 1e9, 1) if ktimes.get("pre_bp", [0, 0])[0] else None,
                 "kernel_ms": kernel_ms}
     # ---- CPU baseline on a bounded sample
@@ -325,6 +355,21 @@ def run_reference(args):
     if rank != 0:
         return
     plan = build_plan()
+    # (i) the reference as shipped: ONE process, bpgd.cpp's own 15 std::threads per decode (oracle/_ref), if it was built
+    as_shipped = None
+    from oracle.oracle import ref_lib
+    if ref_lib() is not None:
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(2); os.dup2(devnull, 2)          # "Error setting thread affinity" spam on hosts with < 15 cores
+        try:
+            a1 = CpuArm(plan, use_ref=True, procs=1)
+            det, obs = sample_host(plan, 48, 7)
+            dt, _, _ = a1.run(det, obs)
+            a1.close()
+            as_shipped = round(48 / dt, 2)
+        finally:
+            os.dup2(saved, 2)
+    # (ii) all-core: one process per core, each running the C port on a shard of the shots
     arm = CpuArm(plan)
     nsample = calibrate_cpu_sample(arm, plan, 8.0)
     K, W = args.steps, args.warmup
@@ -342,7 +387,10 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "shots_per_step": nsample},
             "cpu_baseline": {"value": round(v, 2), "unit": "shots/s", "cores": arm.cores, "kind": "port",
-                             "sample": f"{nsample} shots x 11 windows per step, oracle port (C restatement), one process per core"},
+                             "sample": f"{nsample} shots x 11 windows per step, oracle port (C restatement), one process per core",
+                             "reference_as_shipped_shots_per_s": as_shipped,
+                             "reference_as_shipped_note": "oracle/_ref = the reference's own bpgd.cpp/mod2sparse.c, one process, "
+                                                          "15 std::threads per decode, 48 shots" if as_shipped else "oracle/_ref not built"},
             "e2e": {"value": round(v, 2), "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "results": {"shots": n, "failed": fails}}
     print(json.dumps(line), flush=True)

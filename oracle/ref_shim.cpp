@@ -7,6 +7,7 @@
 // what lives in the reference's Cython layer and therefore cannot be compiled without Cython:
 // the unmasked pre-BP loop (bp_guessing_decoder.pyx:48-139) and the decode() glue (pyx:221-251),
 // both written against the reference's mod2sparse container.
+#include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>

@@ -627,10 +627,9 @@ static int eff_new_n(int m, int n, int new_n) {
     return new_n < n ? new_n : n;
 }
 
-/* bpgdg_decoder.decode, pyx:221-236 */
-int orc_bpgdg_decode(int m, int n, const int *cp, const int *cr, const double *llr, const int8_t *synd,
-                     const orc_gdg_params *P, int8_t *dec, double *min_pm_out, orc_stats *st) {
-    graph *g = graph_build(m, n, cp, cr, NULL);
+/* bpgdg_decoder.decode, pyx:221-236 (g: the window graph, built once per decoder / batch) */
+static int bpgdg_decode_g(graph *g, int m, int n, const int *cp, const int *cr, const double *llr, const int8_t *synd,
+                          const orc_gdg_params *P, int8_t *dec, double *min_pm_out, orc_stats *st) {
     double *hist = (double *)calloc(4 * n + 4, sizeof(double));
     int iters = 0, conv;
     int64_t ei = 0;
@@ -660,8 +659,16 @@ int orc_bpgdg_decode(int m, int n, const int *cp, const int *cr, const double *l
         if (min_pm_out) *min_pm_out = pm;
         free(err); graph_free(sub); free(sum); free(cols);
     }
-    free(hist); graph_free(g);
+    free(hist);
     return conv;
+}
+
+int orc_bpgdg_decode(int m, int n, const int *cp, const int *cr, const double *llr, const int8_t *synd,
+                     const orc_gdg_params *P, int8_t *dec, double *min_pm_out, orc_stats *st) {
+    graph *g = graph_build(m, n, cp, cr, NULL);
+    int r = bpgdg_decode_g(g, m, n, cp, cr, llr, synd, P, dec, min_pm_out, st);
+    graph_free(g);
+    return r;
 }
 
 /* bpgd_decoder.decode / gd, pyx:501-560 */
@@ -942,14 +949,16 @@ static void stats_add(orc_stats *sum, const orc_stats *s) {
 }
 void orc_bpgdg_decode_batch(int m, int n, const int *cp, const int *cr, const double *llr, const int8_t *synd,
                             int64_t B, const orc_gdg_params *P, int8_t *dec, int8_t *conv, double *pm, orc_stats *sum) {
+    graph *g = graph_build(m, n, cp, cr, NULL);
     for (int64_t b = 0; b < B; b++) {
         orc_stats s; memset(&s, 0, sizeof s);
         double p = 0;
-        int c = orc_bpgdg_decode(m, n, cp, cr, llr, synd + b * m, P, dec + b * n, &p, &s);
+        int c = bpgdg_decode_g(g, m, n, cp, cr, llr, synd + b * m, P, dec + b * n, &p, &s);
         if (conv) conv[b] = (int8_t)c;
         if (pm) pm[b] = p;
         if (sum) stats_add(sum, &s);
     }
+    graph_free(g);
 }
 void orc_osd_window_decode_batch(int m, int n, const int *cp, const int *cr, const double *llr, const int8_t *synd,
                                  int64_t B, const orc_osd_params *P, int rank, int8_t *dec, int8_t *conv, double *pm,

@@ -318,7 +318,13 @@ __device__ __forceinline__ void init_msgs(Ctx &c) {
     }
 }
 
-// one check update in min1/min2/argmin/parity form (== bpgd.cpp:103-148) on message slots p0 .. p0+len
+// sign-flip of a double by xor on the sign bit (mag * -f == -(mag * f) exactly in IEEE arithmetic)
+__device__ __forceinline__ double flip_sign(double x, u32 flip) {
+    return __hiloint2double(__double2hiint(x) ^ (int)(flip << 31), __double2loint(x));
+}
+
+// one check update in min1/min2/argmin/parity form (== bpgd.cpp:103-148) on message slots p0 .. p0+len.
+// Plain compares instead of fmin/fmax: no operand can be NaN once dead slots are mapped to 1e308.
 __device__ __forceinline__ void check_update(Ctx &c, int p0, int len, int cm, double fpos, double fneg) {
     double m1 = SWD_BIG, m2 = SWD_BIG; int arg = -1, par = cm;
     double *row = c.msg + p0;
@@ -328,24 +334,28 @@ __device__ __forceinline__ void check_update(Ctx &c, int p0, int len, int cm, do
             const double b = row[k];
             const bool isdead = (b != b);                        // decided VN or pad slot
             const bool isneg = (b <= 0.0);                       // false for NaN
-            const double a = isdead ? SWD_BIG : fmin(fabs(b), SWD_CLIP);
-            if (a < m1) arg = k;
-            m2 = fmin(m2, fmax(m1, a));
-            m1 = fmin(m1, a);
+            double a = fabs(b);
+            a = (a > SWD_CLIP) ? SWD_CLIP : a;
+            a = isdead ? SWD_BIG : a;
+            const bool lt = a < m1;
+            const double hi = lt ? m1 : a;                       // max(m1, a)
+            m2 = (hi < m2) ? hi : m2;
+            m1 = lt ? a : m1;
+            arg = lt ? k : arg;
             neg |= (u32)isneg << k; dead |= (u32)isdead << k;
         }
         par ^= __popc(neg) & 1;
+        const double q1 = m1 * fpos, q2 = m2 * fpos;             // c2b magnitude * alpha (sign applied below)
         u32 live = ~dead & (len == 32 ? 0xffffffffu : ((1u << len) - 1u));
         while (live) {
             const int k = __ffs(live) - 1; live &= live - 1;
-            const double mag = (k == arg) ? m2 : m1;
-            row[k] = mag * ((par ^ (int)((neg >> k) & 1u)) ? fneg : fpos);
+            row[k] = flip_sign((k == arg) ? q2 : q1, (u32)par ^ ((neg >> k) & 1u));
         }
     } else {
         for (int k = 0; k < len; k++) {
             const double b = row[k];
             if (b != b) continue;
-            const double a = fmin(fabs(b), SWD_CLIP);
+            double a = fabs(b); a = (a > SWD_CLIP) ? SWD_CLIP : a;
             if (a < m1) { m2 = m1; m1 = a; arg = k; } else if (a < m2) m2 = a;
             par ^= (b <= 0.0);
         }
