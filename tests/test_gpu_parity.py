@@ -177,3 +177,94 @@ def test_osd_window_single_shot_properties():
     assert not ((H @ e + g["synd"][i]) % 2).any()          # OSD always reproduces the syndrome
     with pytest.raises(ValueError):
         osd_window(g["mat"], channel_probs=g["priors"], osd_method="osd_cs", osd_order=10 ** 6)
+
+
+@pytest.fixture(scope="module")
+def c4_window():
+    """[[288,12,18]] p=0.003, 6 rounds (same window shapes as 18 rounds), (W,F)=(4,1): middle window 576 x 4896."""
+    from slidingwindowdecoder_b200.codes import bb_code
+    from slidingwindowdecoder_b200.dem import bb_memory_circuit, detector_error_model, dem_to_check_matrices
+    from slidingwindowdecoder_b200.windows import build_windows
+    from slidingwindowdecoder_b200.sliding_window import sample_dem
+    code, A, B = bb_code(288)
+    chk, obs, pri = dem_to_check_matrices(detector_error_model(bb_memory_circuit(code, A, B, 0.003, 6)))
+    plan = build_windows(chk, obs, pri, code.N, W=4, F=1, method=1)
+    w = plan.windows[1]
+    assert w.mat.shape == (576, 4896) and w.mat.nnz == 16992
+    det, _, _ = sample_dem(plan.chk, plan.obs, plan.priors, 400, np.random.default_rng(288))
+    s = det[:, w.row0:w.row1]
+    return w, s[s.any(axis=1)][:160]
+
+
+def test_c4_large_window_osd(c4_window, oracle_mod):
+    """Config 4: BP + OSD-CS10 on the large [[288,12,18]] window, bit-exact vs the oracle."""
+    from slidingwindowdecoder_b200 import osd_window
+    w, synd = c4_window
+    kw = dict(pre_max_iter=8, post_max_iter=200, ms_scaling_factor=1.0, osd_method="osd_cs", osd_order=10)
+    dec = osd_window(w.mat, channel_probs=w.prior, **kw)
+    corr, conv, pm = dec.decode_batch(synd, return_pm=True)
+    orc = oracle_mod.Oracle(w.mat, w.prior)
+    n_osd = 0
+    for i in range(len(synd)):
+        r = orc.osd_window(synd[i], **kw)
+        assert conv[i] == r["converge"], i
+        assert np.array_equal(corr[i], r["dec"].astype(np.uint8)), i
+        assert pm[i] == r["min_pm"], i
+        n_osd += int(r["stats"].stage == 2)
+    assert n_osd > 0
+    H = w.mat.toarray().astype(np.int64)
+    assert not ((corr.astype(np.int64) @ H.T + synd) % 2).any()        # OSD: every output reproduces its syndrome
+
+
+def test_c4_large_window_gdg(c4_window, oracle_mod):
+    from slidingwindowdecoder_b200 import bpgdg_decoder
+    w, synd = c4_window
+    kw = dict(max_iter=8, max_tree_depth=4, max_side_depth=20, max_step=40, max_tree_branch_step=30, max_side_branch_step=20,
+              multi_thread=True, low_error_mode=True)
+    dec = bpgdg_decoder(w.mat, channel_probs=w.prior, **kw)
+    corr, conv = dec.decode_batch(synd[:64])
+    orc = oracle_mod.Oracle(w.mat, w.prior)
+    o_dec, o_conv, _, _ = orc.bpgdg_batch(synd[:64], **kw)
+    assert np.array_equal(conv, o_conv.astype(np.uint8))
+    assert np.array_equal(corr, o_dec.astype(np.uint8))
+
+
+def _random_pcm(m, n, rng, wmin, wmax):
+    """Random sparse PCM with column weights in [wmin, wmax] (SHYPS-like: heavy columns, long rows)."""
+    H = np.zeros((m, n), dtype=np.uint8)
+    for c in range(n):
+        H[rng.choice(m, size=int(rng.integers(wmin, wmax + 1)), replace=False), c] = 1
+    return H
+
+
+@pytest.mark.parametrize("kind", ["gdg_mt", "gdg_st", "bpgd", "osd_cs", "osd_e"])
+def test_heavy_columns_long_rows(kind, oracle_mod):
+    """Column weight up to 12 (DMAX=16 kernels) and rows longer than 64 (generic check update), as in the SHYPS DEMs
+    (r=4: row weight <= 88, column weight <= 12; SHYPS.ipynb:212)."""
+    from slidingwindowdecoder_b200 import bpgdg_decoder, bpgd_decoder, osd_window
+    rng = np.random.default_rng(99)
+    m, n = 63, 588
+    H = _random_pcm(m, n, rng, 2, 12)
+    assert H.sum(axis=1).max() > 64
+    pri = 0.004 * (1 + rng.random(n))
+    err = (rng.random((300, n)) < pri * 1.5).astype(np.int64)
+    synd = (err @ H.T % 2).astype(np.uint8)
+    orc = oracle_mod.Oracle(H, pri)
+    if kind.startswith("gdg"):
+        kw = dict(max_iter=8, multi_thread=(kind == "gdg_mt"))
+        corr, conv = bpgdg_decoder(H, channel_probs=pri, **kw).decode_batch(synd)
+        o_dec, o_conv, _, _ = orc.bpgdg_batch(synd, **kw)
+    elif kind == "bpgd":
+        kw = dict(max_iter=8, ms_scaling_factor=0.9, max_iter_per_step=6, max_step=25, gd_factor=0.9)
+        corr, conv = bpgd_decoder(H, channel_probs=pri, **kw).decode_batch(synd)
+        o = [orc.bpgd(s, **kw) for s in synd]
+        o_dec = np.array([x[0] for x in o]); o_conv = np.array([x[1] for x in o])
+    else:
+        kw = dict(pre_max_iter=8, post_max_iter=40, ms_scaling_factor=0.9,
+                  osd_method="osd_cs" if kind == "osd_cs" else "osd_e", osd_order=10 if kind == "osd_cs" else 5)
+        corr, conv = osd_window(H, channel_probs=pri, **kw).decode_batch(synd)
+        o = [orc.osd_window(s, **kw) for s in synd]
+        o_dec = np.array([x["dec"] for x in o]); o_conv = np.array([x["converge"] for x in o])
+    assert np.array_equal(conv, o_conv.astype(np.uint8))
+    bad = np.nonzero((corr != o_dec.astype(np.uint8)).any(axis=1))[0]
+    assert len(bad) == 0, f"shots {bad[:10]}"
