@@ -297,15 +297,15 @@ def run_ours(args):
         peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
-    path_ms = ktimes.get("path_main", [0, 0])[0] + ktimes.get("path_side", [0, 0])[0]
-    path_launches = ktimes.get("path_main", [0, 0])[1] + ktimes.get("path_side", [0, 0])[1]
+    path_ms = sum(ktimes.get(k, [0, 0])[0] for k in ("path_main", "path_side", "path_trunk"))
+    path_launches = sum(ktimes.get(k, [0, 0])[1] for k in ("path_main", "path_side", "path_trunk"))
     # B_iter = 4 E w + 2 n_a w + (n_a + m_a)/8 with w = 8, summed over executed iterations
     path_bytes = 32.0 * ctr["path_edge_iters"] + 16.0 * ctr["path_vn_iters"] + (ctr["path_vn_iters"] + ctr["path_cn_iters"]) / 8.0
     pre_bytes = 32.0 * ctr["pre_bp_edge_iters"]
     achieved = path_bytes / (path_ms / 1e3) / 1e9 if path_ms > 0 else 0.0
     kernel_ms = {k: round(v[0], 3) for k, v in ktimes.items() if v[1]}
     tot_k = sum(kernel_ms.values()) or 1.0
-    roofline = {"kernel": "path_kernel (GDG branch paths, phases main+side)", "bound": "hbm", "achieved": round(achieved, 1),
+    roofline = {"kernel": "path_kernel (GDG branch paths: shared-prefix nodes + main/tree + side launches)", "bound": "hbm", "achieved": round(achieved, 1),
                 "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": round(path_bytes / max(1, path_launches)),
                 "avg_launch_ms": round(path_ms / max(1, path_launches), 4), "launches": path_launches,

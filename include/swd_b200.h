@@ -97,6 +97,7 @@ typedef struct swd_counters {
 #define SWD_K_PATH_SIDE  3   /* path_kernel phase 1: side branches                                         */
 #define SWD_K_SELECT     4
 #define SWD_K_OSD        5
+#define SWD_K_PATH_TRUNK 6   /* path_kernel on shared-prefix nodes (decimation depths < max_tree_depth)                 */
 #define SWD_K_COUNT      8
 
 /* pcm as CSC: colptr[n+1], rowidx[nnz] (any order inside a column; sorted internally, as

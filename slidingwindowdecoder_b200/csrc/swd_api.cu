@@ -289,6 +289,7 @@ static int setup_kernels(swd_decoder *d) {
     if (c.kind == SWD_KIND_OSD_WINDOW) { P.factor = c.ms_scaling_factor; P.low_error = 0; }
     P.rec_stride = r16((int)sizeof(RecHeader) + 4 * ((nn + 31) / 32));
     P.side_stride = r16((int)sizeof(SideHeader) + nn + 2 * m);
+    P.shared_T = 0; P.n_nodes = 0; P.node_stride = 16;
     // ---- blob layouts: global (worst case), shared-memory tier A (typical shots), tier B (worst case)
     const int lcap = std::min(255, d->max_row_deg);
     const int es_slots = es + m;      // every row may carry one pad slot
@@ -349,6 +350,19 @@ static int setup_kernels(swd_decoder *d) {
     d->grid3 = d->num_sm * occ;
     if ((st = occupancy(d->path_fn, d->T3, smemB, &occ))) return st;
     d->grid3B = d->num_sm * std::max(1, occ);
+    // shared-prefix tree (multi-thread GDG): depths 0..T-1 are computed once per decision prefix
+    if (c.kind == SWD_KIND_BPGDG && c.multi_thread && P.T >= 1 && P.T <= 6 && P.max_step >= P.T && !getenv("SWD_NO_SHARED_PREFIX")) {
+        P.shared_T = P.T; P.n_nodes = (1 << P.T) - 1;
+        int q = (int)sizeof(NodeHeader);
+        q += nn; q = r16(q); P.node_off_err = q;
+        q += nn; q = r16(q); P.node_off_cn = q;
+        q += m; q = r16(q); P.node_off_deg = q;
+        q += m; q = r16(q); P.node_off_flip = q;
+        q += m; q = r16(q); P.node_off_msg = q;
+        q += 8 * es_slots; q = r16(q); P.node_off_hist = q;
+        q += 8 * 16 * d->T3; q = r16(q);
+        P.node_stride = q;
+    }
     // ---- K5 (OSD)
     if (c.kind == SWD_KIND_OSD_WINDOW) {
         if ((st = osd_setup(d->m, d->n, d->nn, d->rank, d->cfg.osd_method, d->cfg.osd_order, d->num_sm, &d->OS, &d->T5, &d->grid5))) {
@@ -365,7 +379,8 @@ static int alloc_workspace(swd_decoder *d, long long want) {
     if (const char *e = getenv("SWD_WS_BYTES")) budget = (size_t)atoll(e);
     const int n = d->n;
     const bool osd = d->cfg.kind == SWD_KIND_OSD_WINDOW;
-    size_t per = (size_t)n * 8 + d->L.blob_bytes + (size_t)d->P.n_rec * d->P.rec_stride + (size_t)d->P.n_side * d->P.side_stride + 4 + 64;
+    size_t per = (size_t)n * 8 + d->L.blob_bytes + (size_t)d->P.n_rec * d->P.rec_stride + (size_t)d->P.n_side * d->P.side_stride + 4 + 64 +
+                 (size_t)d->P.n_nodes * d->P.node_stride;
     if (osd) per += (size_t)n * 32 + osd_bytes_per_shot(d->m, n);
     long long cap = std::max<long long>(1, std::min<long long>(want, (long long)(budget / per)));
     if (cap <= d->cap) return SWD_OK;
@@ -380,6 +395,7 @@ static int alloc_workspace(swd_decoder *d, long long want) {
     size_t o_blob = o; o += a256((size_t)cap * d->L.blob_bytes);
     size_t o_rec = o; o += a256((size_t)cap * d->P.n_rec * d->P.rec_stride);
     size_t o_side = o; o += a256((size_t)cap * std::max(1, d->P.n_side) * d->P.side_stride);
+    size_t o_node = o; o += a256((size_t)cap * std::max(1, d->P.n_nodes) * d->P.node_stride);
     size_t o_osd = o; if (osd) o += a256((size_t)cap * osd_bytes_per_shot(d->m, n));
     cudaError_t e = cudaMalloc(&d->ws_block, o);
     if (e != cudaSuccess) { set_err("workspace cudaMalloc failed"); return SWD_ERR_NOMEM; }
@@ -387,7 +403,7 @@ static int alloc_workspace(swd_decoder *d, long long want) {
     unsigned char *b = (unsigned char *)d->ws_block;
     d->ws.counters = (int *)(b + o_cnt); d->ws.stats = (u64 *)(b + o_stats); d->ws.gdg_list = (int *)(b + o_list);
     d->ws.sum = (double *)(b + o_sum); d->ws.hist = osd ? (double *)(b + o_hist) : nullptr;
-    d->ws.blob = b + o_blob; d->ws.rec = b + o_rec; d->ws.side = b + o_side;
+    d->ws.blob = b + o_blob; d->ws.rec = b + o_rec; d->ws.side = b + o_side; d->ws.node = b + o_node;
     if (osd) osd_bind(&d->ow, b + o_osd, cap, d->m, n);
     if (!d->hscratch) CK(cudaMalloc(&d->hscratch, (size_t)d->grid1 * 4 * n * sizeof(double)));
     d->cap = cap;
@@ -444,6 +460,15 @@ static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_cor
                             d->ow.need_osd + d->cap);
         if (st) { set_err("osd launch failed"); return st; }
     } else {
+        for (int lv = 0; lv < d->P.shared_T; lv++) {       // shared-prefix nodes, level by level
+            KTimer kt(d, s, SWD_K_PATH_TRUNK);
+            d->path_fn<<<g3, d->T3, smem3, s>>>(d->ws, d->L, d->LsA, d->PS, d->P, 2 + lv, 0, d->es_capA);
+            d->ctr.kernel_launches++;
+            if (two_tier) {
+                d->path_fn<<<d->grid3B, d->T3, smem3B, s>>>(d->ws, d->L, d->LsB, d->PSB, d->P, 2 + lv, 1, d->es_capA);
+                d->ctr.kernel_launches++;
+            }
+        }
         for (int ph = 0; ph < phases; ph++) {
             KTimer kt(d, s, ph == 0 ? SWD_K_PATH_MAIN : SWD_K_PATH_SIDE);
             d->path_fn<<<g3, d->T3, smem3, s>>>(d->ws, d->L, d->LsA, d->PS, d->P, ph, 0, d->es_capA);

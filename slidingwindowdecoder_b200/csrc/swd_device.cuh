@@ -75,6 +75,10 @@ struct GdgDev {                 // parameters of the decimation tree
     int kind;                   // SWD_KIND_*
     int multi_thread;
     int post_max_iter;
+    // shared-prefix tree: the first shared_T decimation steps are identical for all branch paths with the same
+    // prefix of favour/flip decisions, so they are computed once per prefix ("nodes") instead of once per path
+    int shared_T, n_nodes, node_stride;
+    int node_off_err, node_off_cn, node_off_deg, node_off_flip, node_off_msg, node_off_hist;
 };
 
 struct Workspace {              // per-batch device buffers
@@ -85,6 +89,7 @@ struct Workspace {              // per-batch device buffers
     u8 *blob;                   // [cap][blob_bytes]
     u8 *rec;                    // [cap][n_rec][rec_stride]
     u8 *side;                   // [cap][n_side][side_stride]
+    u8 *node;                   // [cap][n_nodes][node_stride] shared-prefix snapshots (masks, messages, history)
     u64 *stats;                 // device counters: [0] pre edge-iters [1] path edge-iters [2] paths [3] bp calls [4] osd shots
 };
 

@@ -293,6 +293,7 @@ sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayo
             u32 *rec = (u32 *)(ws.rec + (size_t)slot * P.n_rec * P.rec_stride);
             for (int i = tid; i < (P.n_rec * P.rec_stride) >> 2; i += T) rec[i] = 0;
             for (int j = tid; j < P.n_side; j += T) *(int *)(ws.side + ((size_t)slot * P.n_side + j) * P.side_stride) = 0;
+            for (int j = tid; j < P.n_nodes; j += T) *(int *)(ws.node + ((size_t)slot * P.n_nodes + j) * P.node_stride) = 0;
         }
         __syncthreads();
     }
@@ -303,6 +304,7 @@ sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayo
 // ----------------------------------------------------------------------------------------------
 struct RecHeader { double pm; int status; int pad; };          // 16 bytes, followed by error bit words
 struct SideHeader { int valid, vn, value, depth; };            // 16 bytes, followed by vn_mask, cn_mask, cn_deg
+struct NodeHeader { int alive, guess, favor, pad; };           // 16 bytes, followed by masks, messages, history
 
 // write (status, pm, error bits) of the current path
 // path metric of the current `error`, broadcast to the whole CTA (contains barriers)
@@ -359,14 +361,17 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
     __syncthreads();
     u32 mphase = 0;
     const int count = (tier == 1 && ws.counters[8] == 0) ? 0 : ws.counters[0];
-    const int npaths = (phase == 0) ? ((P.kind == SWD_KIND_BPGDG && P.multi_thread) ? 1 + P.n_tree : 1) : P.n_side;
+    const int node_level = (phase >= 2) ? phase - 2 : -1;          // >= 0: shared-prefix node of that depth
+    const int npaths = (node_level >= 0) ? (1 << node_level)
+                     : (phase == 0) ? ((P.kind == SWD_KIND_BPGDG && P.multi_thread) ? 1 + P.n_tree : 1) : P.n_side;
+    const int ticket = (node_level >= 0) ? 16 + 2 * node_level + tier : 1 + phase + 3 * tier;
     const long long total = (long long)npaths * count;
     u64 edge_iters = 0, bp_calls = 0, paths_run = 0;
     u32 vn_iters = 0, cn_iters = 0;
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) c.misc[2] = atomicAdd(&ws.counters[1 + phase + 3 * tier], 1);
+        if (tid == 0) c.misc[2] = atomicAdd(&ws.counters[ticket], 1);
         __syncthreads();
         const long long item = c.misc[2];
         if (item >= total) break;
@@ -380,17 +385,28 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
             sh = (const SideHeader *)(ws.side + ((size_t)slot * P.n_side + path) * P.side_stride);
             if (!sh->valid) continue;
         }
+        // parent node of the shared-prefix tree (if this item continues from one)
+        const unsigned char *pnode = nullptr;
+        NodeHeader ph = {0, -1, 0, 0};
+        if (P.shared_T > 0 && (node_level > 0 || phase == 0)) {
+            const int plevel = (node_level > 0) ? node_level - 1 : P.shared_T - 1;
+            pnode = ws.node + ((size_t)slot * P.n_nodes + ((1 << plevel) - 1) + (path >> 1)) * P.node_stride;
+            ph = *(const NodeHeader *)pnode;
+            if (!ph.alive) continue;                              // that prefix already converged or died
+        }
         // ---- stage the shot's shortened graph into shared memory with TMA bulk copies
         if (tid == 0) {
             fence_proxy_async();
             const u32 vb = (u32)((gh.es * 2 + 15) & ~15);
-            mbar_expect_tx(bar, (u32)L.fixed_bytes + 3 * vb);
+            const u32 mb = pnode ? (u32)((gh.es * 8 + 15) & ~15) : 0u;
+            mbar_expect_tx(bar, (u32)L.fixed_bytes + 3 * vb + mb);
             bulk_g2s(blob, gblob, (u32)L.fixed_bytes, bar);
             if (vb) {
                 bulk_g2s(blob + L.off_vrow, gblob + LG.off_vrow, vb, bar);
                 bulk_g2s(blob + L.off_vpos, gblob + LG.off_vpos, vb, bar);
                 bulk_g2s(blob + L.off_cvn, gblob + LG.off_cvn, vb, bar);
             }
+            if (mb) bulk_g2s(c.msg, pnode + P.node_off_msg, mb, bar);       // messages of the parent node
         }
         mbar_wait(bar, mphase);
         mphase ^= 1;
@@ -398,7 +414,21 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
         c.C = 30; c.D = 3;
 
         // ---- load the start state
-        if (phase == 0) {
+        double h[VPT][4];
+        if (pnode) {
+            const i8 *nvn = (const i8 *)(pnode + sizeof(NodeHeader)), *ner = (const i8 *)(pnode + P.node_off_err);
+            const i8 *ncn = (const i8 *)(pnode + P.node_off_cn);
+            const u8 *ndg = pnode + P.node_off_deg, *nfl = pnode + P.node_off_flip;
+            const double *nh = (const double *)(pnode + P.node_off_hist);
+            for (int j = tid; j < c.nn; j += T) { c.vn_mask[j] = nvn[j]; c.error[j] = ner[j]; }
+            for (int r = tid; r < c.m; r += T) { c.cn_mask[r] = ncn[r]; c.cn_deg[r] = ndg[r]; c.flip[r] = nfl[r]; }
+#pragma unroll
+            for (int i = 0; i < VPT; i++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) h[i][q] = nh[(size_t)(i * 4 + q) * T + tid];
+            __syncthreads();
+        } else {
+        if (phase != 1) {
             for (int j = tid; j < c.nn; j += T) { const i8 v = snap_vn[j]; c.vn_mask[j] = v; c.error[j] = v < 0 ? 0 : v; }
             for (int r = tid; r < c.m; r += T) { c.cn_mask[r] = snap_cn[r]; c.cn_deg[r] = snap_deg[r]; c.flip[r] = 0; }
         } else {
@@ -408,32 +438,47 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
         }
         __syncthreads();
         init_msgs<VPT>(c);
-        double h[VPT][4];
 #pragma unroll
         for (int i = 0; i < VPT; i++) { h[i][0] = 0.0; h[i][1] = 0.0; h[i][2] = 0.0; h[i][3] = 0.0; }
         __syncthreads();
+        }
         paths_run++;
 
         u8 *recbase = ws.rec + (size_t)slot * P.n_rec * P.rec_stride;
 
         // ---- one interpreter loop for every kind of branch, so that bp_run / select_vn /
         //      set_and_peel are instantiated once (registers, code size)
-        enum { R_MAIN = 0, R_TREE = 1, R_SIDE = 2, R_GD = 3, R_ST = 4 };
+        enum { R_MAIN = 0, R_TREE = 1, R_SIDE = 2, R_GD = 3, R_ST = 4, R_NODE = 5 };
         int role, limit, depth = 0, pend_vn = -1, pend_val = 0;
         u8 *rec = recbase;
+        bool mainlike = false, node_alive = false; int node_guess = -1, node_favor = 0;
         // single-thread schedule (pyx:254-338): guess stack lives in this slot's side-snapshot area
         int st_used = 0, st_i = 0, st_min_depth = P.max_step, st_conv = 0; double st_min_pm = SWD_MAX_PM;
         if (P.kind == SWD_KIND_BPGD) { role = R_GD; limit = P.max_step; }
         else if (!P.multi_thread) { role = R_ST; limit = P.max_step; c.A = -3; c.A_sum = -16; }
+        else if (node_level >= 0) {
+            // shared-prefix node: ONE decimation step for every branch path whose first node_level decisions equal
+            // `path` (bit k of the prefix = decision at depth k flipped, bpgd.cpp:464-470)
+            role = R_NODE; limit = 1; depth = node_level; mainlike = (path == 0);
+            rec = recbase + (size_t)(path << (P.shared_T - node_level)) * P.rec_stride;     // lowest branch id with this prefix
+            if (path == 0) { c.A = -3; c.A_sum = (depth == 0) ? -16 : -12; } else { c.A = 0; c.A_sum = -10; }
+            if (pnode) { pend_vn = ph.guess; pend_val = ph.favor ^ (path & 1); }
+        }
         else if (phase == 1) {                                  // side branch j (bpgd.cpp:527-570)
             role = R_SIDE; limit = P.side_step; rec = recbase + (size_t)(1 + P.n_tree + path) * P.rec_stride;
             c.A = 0; c.A_sum = -10; depth = sh->depth; pend_vn = sh->vn; pend_val = sh->value;
-        } else if (path == 0) { role = R_MAIN; limit = P.max_step; c.A = -3; c.A_sum = -16; }   // bpgd.cpp:623-683
+        } else if (path == 0) { role = R_MAIN; mainlike = true; limit = P.max_step; c.A = -3; c.A_sum = -16; }   // bpgd.cpp:623-683
         else {                                                  // tree branch id (bpgd.cpp:435-525)
             role = R_TREE; limit = P.tree_step + P.T + 1; rec = recbase + (size_t)path * P.rec_stride;
             c.A = -3; c.A_sum = -16;
         }
         int stage = 0, steps = 0, on_side = 0, saved = 0, bvar = -1, bval = 0, conv = 0;
+        if (pnode && node_level < 0) {
+            // continue from the last shared node: decision of depth shared_T-1 with this path's own bit, then depth shared_T
+            depth = P.shared_T; steps = P.shared_T;
+            pend_vn = ph.guess; pend_val = ph.favor ^ (path & 1);
+            if (role == R_TREE) { on_side = 1; c.A = 0; c.A_sum = -10; }      // every tree id has taken a flip by now
+        }
         for (;;) {
             bool stage_end = false;
             if (pend_vn >= 0) {
@@ -482,13 +527,14 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
                     stage_end = true;
                 }
                 if (role == R_ST && !stage_end && stage == 1 && depth > st_min_depth + 2) stage_end = true;   // pyx:331
-                if (conv && role != R_MAIN && role != R_ST) break;                                // :452-459, :552-559
+                if (conv && !mainlike && role != R_ST) break;                                     // :452-459, :552-559
                 if (!stage_end) {
                 int guess = -1;
                 int favor = select_vn<VPT>(c, h, depth, guess);
                 if (conv) break;                                                                  // main: :633-649
                 if (favor == -1 || guess == -1) stage_end = true;
                 else {
+                    if (role == R_NODE) { node_alive = true; node_guess = guess; node_favor = favor; break; }
                     if (role == R_ST) {                                                           // pyx:416-433
                         bool do_guess = !(depth > st_min_depth);
                         if (stage == 0 && depth >= P.S) do_guess = false;
@@ -557,7 +603,22 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
             }
             break;
         }
-        if (role != R_ST && (conv || role == R_MAIN || role == R_GD)) record_result(c, rec, conv);
+        if (node_alive) {
+            // publish the node: state after select_vn of this depth, before the decision is applied
+            unsigned char *nd = ws.node + ((size_t)slot * P.n_nodes + ((1 << node_level) - 1) + path) * P.node_stride;
+            i8 *nvn = (i8 *)(nd + sizeof(NodeHeader)), *ner = (i8 *)(nd + P.node_off_err), *ncn = (i8 *)(nd + P.node_off_cn);
+            u8 *ndg = nd + P.node_off_deg, *nfl = nd + P.node_off_flip;
+            double *nm = (double *)(nd + P.node_off_msg), *nh = (double *)(nd + P.node_off_hist);
+            __syncthreads();
+            for (int j = tid; j < c.nn; j += T) { nvn[j] = c.vn_mask[j]; ner[j] = c.error[j]; }
+            for (int r = tid; r < c.m; r += T) { ncn[r] = c.cn_mask[r]; ndg[r] = c.cn_deg[r]; nfl[r] = c.flip[r]; }
+            for (int p = tid; p < c.es; p += T) nm[p] = c.msg[p];
+#pragma unroll
+            for (int i = 0; i < VPT; i++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) nh[(size_t)(i * 4 + q) * T + tid] = h[i][q];
+            if (tid == 0) { NodeHeader *hd = (NodeHeader *)nd; hd->guess = node_guess; hd->favor = node_favor; hd->alive = 1; }
+        } else if (role != R_ST && (conv || mainlike || role == R_GD)) record_result(c, rec, conv);
     }
     // ---- work counters
 #pragma unroll
