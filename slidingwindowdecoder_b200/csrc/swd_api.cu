@@ -32,7 +32,7 @@ typedef void (*path_fn_t)(Workspace, SubLayout, SubLayout, PathSmem, GdgDev, int
 static path_fn_t pick_path_kernel(int dmax, int T) {
     if (dmax == 6) {
 #ifndef SWD_MINB
-#define SWD_MINB 4
+#define SWD_MINB 6
 #endif
         if (T <= 128) return path_kernel<4, 6, 128, SWD_MINB>;
         if (T <= 512) return path_kernel<4, 6, 512, 1>;
