@@ -303,10 +303,16 @@ def run_ours(args):
     path_bytes = 32.0 * ctr["path_edge_iters"] + 16.0 * ctr["path_vn_iters"] + (ctr["path_vn_iters"] + ctr["path_cn_iters"]) / 8.0
     pre_bytes = 32.0 * ctr["pre_bp_edge_iters"]
     achieved = path_bytes / (path_ms / 1e3) / 1e9 if path_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath)).get("path_kernel", {})
+        if tj.get("batch") == B:                 # the capture was taken at this batch size
+            traffic = int(tj["dram_bytes_per_launch_avg"]); traffic_src = tj.get("source")
     kernel_ms = {k: round(v[0], 3) for k, v in ktimes.items() if v[1]}
     tot_k = sum(kernel_ms.values()) or 1.0
     roofline = {"kernel": "path_kernel (GDG branch paths: shared-prefix nodes + main/tree + side launches)", "bound": "hbm", "achieved": round(achieved, 1),
-                "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": round(path_bytes / max(1, path_launches)),
                 "avg_launch_ms": round(path_ms / max(1, path_launches), 4), "launches": path_launches,
                 "share_of_kernel_time": round(path_ms / tot_k, 4),

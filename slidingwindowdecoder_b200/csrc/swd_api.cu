@@ -42,13 +42,15 @@ static path_fn_t pick_path_kernel(int dmax, int T) {
     return path_kernel<4, 16, 1024, 1>;
 }
 
+typedef void (*pre_fn_t)(GraphDev, const u8 *, long long, int, double, u8 *, u8 *, Workspace, double *, int, PreSmem, int *, double *);
 struct swd_decoder {
     swd_config cfg;
     path_fn_t path_fn = nullptr;
+    pre_fn_t pre_fn = nullptr;
     int m = 0, n = 0, nnz = 0, nn = 0, max_col_deg = 0, max_row_deg = 0, es_max = 0, rank = -1;
     int device = 0, num_sm = 0;
     GraphDev g{};
-    void *d_graph[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *d_graph[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     SubLayout L{}, LsA{}, LsB{};
     PathSmem PS{}, PSB{};
     int es_capA = 0, grid3B = 0;
@@ -187,14 +189,23 @@ extern "C" int swd_create(const swd_config *cfg, int m, int n, const int32_t *co
     d->num_sm = prop.multiProcessorCount;
     std::vector<u16> cr16(cr.begin(), cr.end()), rc16(rc.begin(), rc.end()), cpos16(cpos.begin(), cpos.end());
     std::vector<double> llr(channel_llr, channel_llr + n);
+    std::vector<u16> vord(n);
+    {
+        std::vector<int> idx(n);
+        for (int c = 0; c < n; c++) idx[c] = c;
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return cp[a + 1] - cp[a] > cp[b + 1] - cp[b]; });
+        for (int c = 0; c < n; c++) vord[c] = (u16)idx[c];
+    }
     int st;
     if ((st = upload(rp, &d->d_graph[0])) || (st = upload(rc16, &d->d_graph[1])) || (st = upload(cp, &d->d_graph[2])) ||
-        (st = upload(cr16, &d->d_graph[3])) || (st = upload(cpos16, &d->d_graph[4])) || (st = upload(llr, &d->d_graph[5]))) {
+        (st = upload(cr16, &d->d_graph[3])) || (st = upload(cpos16, &d->d_graph[4])) || (st = upload(llr, &d->d_graph[5])) ||
+        (st = upload(vord, &d->d_graph[6]))) {
         swd_destroy(d); return st;
     }
     d->g.m = m; d->g.n = n; d->g.nnz = nnz;
     d->g.rp = (const int *)d->d_graph[0]; d->g.rc = (const u16 *)d->d_graph[1]; d->g.cp = (const int *)d->d_graph[2];
     d->g.cr = (const u16 *)d->d_graph[3]; d->g.cpos = (const u16 *)d->d_graph[4]; d->g.llr = (const double *)d->d_graph[5];
+    d->g.vord = (const u16 *)d->d_graph[6];
     if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) { swd_destroy(d); set_err("stream create failed"); return SWD_ERR_CUDA; }
     if ((st = setup_kernels(d)) != SWD_OK) { swd_destroy(d); return st; }
     *out = d;
@@ -313,7 +324,8 @@ static int setup_kernels(swd_decoder *d) {
     S1.off_misc = o; o += 64; S1.total = o;
     if (S1.total > 227 * 1024) { set_err("window graph does not fit in shared memory (nnz too large)"); return SWD_ERR_UNSUPPORTED; }
     int occ = 0, st;
-    if (d->max_col_deg <= 8) st = occupancy(pre_bp_kernel<8>, d->T1, S1.total, &occ); else st = occupancy(pre_bp_kernel<16>, d->T1, S1.total, &occ);
+    d->pre_fn = d->max_col_deg <= 6 ? pre_bp_kernel<6> : (d->max_col_deg <= 8 ? pre_bp_kernel<8> : pre_bp_kernel<16>);
+    st = occupancy(d->pre_fn, d->T1, S1.total, &occ);
     if (st) return st;
     if (occ < 1) { set_err("pre_bp_kernel does not fit"); return SWD_ERR_UNSUPPORTED; }
     d->grid1 = d->num_sm * occ;
@@ -430,12 +442,8 @@ static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_cor
     double *lpr_out = (c.kind == SWD_KIND_OSD_WINDOW) ? d->ow.lpr + (size_t)chunk_base * d->n * 4 : nullptr;
     {
     KTimer kt(d, s, SWD_K_PRE_BP);
-    if (d->max_col_deg <= 8)
-        pre_bp_kernel<8><<<g1, d->T1, d->PRE.total, s>>>(d->g, d_synd, B, c.max_iter, c.ms_scaling_factor, d_corr, d_conv, d->ws,
-                                                        d->hscratch, full_hist, d->PRE, iter_out, lpr_out);
-    else
-        pre_bp_kernel<16><<<g1, d->T1, d->PRE.total, s>>>(d->g, d_synd, B, c.max_iter, c.ms_scaling_factor, d_corr, d_conv, d->ws,
-                                                         d->hscratch, full_hist, d->PRE, iter_out, lpr_out);
+    d->pre_fn<<<g1, d->T1, d->PRE.total, s>>>(d->g, d_synd, B, c.max_iter, c.ms_scaling_factor, d_corr, d_conv, d->ws,
+                                              d->hscratch, full_hist, d->PRE, iter_out, lpr_out);
     }
     d->ctr.kernel_launches++;
     if (d_pm) {

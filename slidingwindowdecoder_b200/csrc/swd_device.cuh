@@ -64,6 +64,7 @@ struct GraphDev {               // static window graph (device pointers)
     const int *cp;              // [n+1]  CSC column pointer
     const u16 *cr;              // [nnz]  CSC row index (ascending)
     const u16 *cpos;            // [nnz]  CSC entry -> CSR position
+    const u16 *vord;            // [n]    columns in descending degree order (ownership order of the pre-BP kernel)
     const double *llr;          // [n]
 };
 

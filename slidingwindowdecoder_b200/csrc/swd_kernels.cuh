@@ -34,7 +34,7 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
     const int T = blockDim.x, tid = threadIdx.x;
     const int m = g.m, n = g.n;
     double *hs = hscratch + (size_t)blockIdx.x * 4 * n;
-    const double fpos = alpha, fneg = -alpha;
+    const double fpos = alpha;
     u64 edge_iters = 0;
 
     for (long long shot = blockIdx.x; shot < B; shot += gridDim.x) {
@@ -48,39 +48,51 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
         __syncthreads();
         int conv = 0, it = 0;
         for (; it < max_iter; it++) {
+            // ---- check pass: min1/min2/argmin/parity with plain compares, sign applied by xor (all edges live)
             for (int r = tid; r < m; r += T) {
                 upar[r] = 0;
                 const int p0 = g.rp[r], p1 = g.rp[r + 1];
-                double m1 = SWD_BIG, m2 = SWD_BIG; int arg = -1, par = s_synd[r];
+                double m1 = SWD_BIG, m2 = SWD_BIG; int arg = -1; u32 par = s_synd[r];
                 for (int p = p0; p < p1; p++) {
                     const double b = msg[p];
-                    const double a = fmin(fabs(b), SWD_CLIP);
-                    if (a < m1) { m2 = m1; m1 = a; arg = p; } else if (a < m2) m2 = a;
-                    par ^= (b <= 0.0);
+                    double a = fabs(b);
+                    a = (a > SWD_CLIP) ? SWD_CLIP : a;
+                    const bool lt = a < m1;
+                    const double hi = lt ? m1 : a;
+                    m2 = (hi < m2) ? hi : m2;
+                    m1 = lt ? a : m1;
+                    arg = lt ? p : arg;
+                    par ^= (u32)(b <= 0.0);
                 }
+                const double q1 = m1 * fpos, q2 = m2 * fpos;
                 for (int p = p0; p < p1; p++) {
                     const double b = msg[p];
-                    const double mag = (p == arg) ? m2 : m1;
-                    msg[p] = mag * ((par ^ (int)(b <= 0.0)) ? fneg : fpos);
+                    msg[p] = flip_sign((p == arg) ? q2 : q1, par ^ (u32)(b <= 0.0));
                 }
             }
             __syncthreads();
             const bool keep = full_hist || (it >= max_iter - 4);
-            for (int v = tid; v < n; v += T) {
-                const int e0 = g.cp[v], d = g.cp[v + 1] - e0;
-                double cc[DMAX], pre[DMAX]; int pp[DMAX];
-                double t = g.llr[v];
+            // ---- variable pass: columns are owned in degree order (g.vord), so a warp's loop bound is uniform
+            for (int base = 0; base < n; base += T) {
+                const int sl = base + tid;
+                int v = -1, e0 = 0, d = 0;
+                if (sl < n) { v = g.vord[sl]; e0 = g.cp[v]; d = g.cp[v + 1] - e0; }
+                const int dw = __reduce_max_sync(FULLMASK, d);
+                if (v >= 0) {
+                    double cc[DMAX], pre[DMAX]; int pp[DMAX];
+                    double t = g.llr[v];
 #pragma unroll
-                for (int k = 0; k < DMAX; k++) if (k < d) { pp[k] = g.cpos[e0 + k]; cc[k] = msg[pp[k]]; }
+                    for (int k = 0; k < DMAX; k++) { if (k >= dw) break; if (k < d) { pp[k] = g.cpos[e0 + k]; cc[k] = msg[pp[k]]; } }
 #pragma unroll
-                for (int k = 0; k < DMAX; k++) if (k < d) { pre[k] = t; t += cc[k]; }
-                if (keep) hs[(size_t)(it & 3) * n + v] = t;
-                const int hard = (t <= 0.0);
-                s_dec[v] = (u8)hard;
-                if (hard) for (int k = 0; k < d; k++) atomicXor(&upar[g.cr[e0 + k]], 1u);
-                double s = 0.0;
+                    for (int k = 0; k < DMAX; k++) { if (k >= dw) break; if (k < d) { pre[k] = t; t += cc[k]; } }
+                    if (keep) hs[(size_t)(it & 3) * n + v] = t;
+                    const int hard = (t <= 0.0);
+                    s_dec[v] = (u8)hard;
+                    if (hard) for (int k = 0; k < d; k++) atomicXor(&upar[g.cr[e0 + k]], 1u);
+                    double s = 0.0;
 #pragma unroll
-                for (int k = DMAX - 1; k >= 0; k--) if (k < d) { msg[pp[k]] = pre[k] + s; s += cc[k]; }
+                    for (int k = DMAX - 1; k >= 0; k--) if (k < d) { msg[pp[k]] = pre[k] + s; s += cc[k]; }
+                }
             }
             edge_iters += 1;
             __syncthreads();

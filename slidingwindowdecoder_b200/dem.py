@@ -146,6 +146,139 @@ def bb_memory_circuit(code, A_list, B_list, p, num_repeat, z_basis=True):
     return c
 
 
+def _gf2_polydiv(num, den):
+    """Quotient and remainder of GF(2) polynomials given as coefficient lists (increasing degree)."""
+    num = list(num); den = list(den)
+    dn = max(i for i, c in enumerate(den) if c)
+    quo = [0] * max(1, len(num) - dn)
+    for i in range(len(num) - 1, dn - 1, -1):
+        if num[i]:
+            quo[i - dn] = 1
+            for k in range(dn + 1):
+                num[i - dn + k] ^= den[k]
+    return quo, num[:dn]
+
+
+def shyps_code(r):
+    """Subsystem hypergraph-product simplex code (build_SHYPS_circuit.py:9-57): gauge / stabiliser / logical matrices."""
+    n_r = 2 ** r - 1
+    taps = {3: [0, 2, 3], 4: [0, 3, 4], 5: [0, 2, 5]}[r]          # primitive h(x)
+    hpoly = [0] * (max(taps) + 1)
+    for t in taps:
+        hpoly[t] = 1
+    first = np.zeros(n_r, dtype=np.int64); first[:len(hpoly)] = hpoly
+    H = np.array([np.roll(first, i) for i in range(n_r)])
+    xn = [1] + [0] * (n_r - 1) + [1]                                # x^n - 1
+    gpoly, rem = _gf2_polydiv(xn, hpoly)
+    assert not any(rem)
+    gfirst = np.zeros(n_r, dtype=np.int64); gfirst[:len(gpoly)] = gpoly
+    G = np.array([np.roll(gfirst, i) for i in range(r)])
+    assert not (G @ H % 2).any()
+    I = np.identity(n_r, dtype=np.int64)
+    from .codes import gf2_row_reduce
+    # P with P G^T = I_r: row-reduce G^T (n_r x r); the transform's first r rows invert the pivot block
+    R, piv, rk, Tm = gf2_row_reduce(G.T)
+    assert rk == r
+    P = Tm[:r].astype(np.int64)
+    assert np.array_equal(P @ G.T % 2, np.identity(r, dtype=np.int64))
+    return dict(r=r, n_r=n_r, N=n_r * n_r, H=H, G=G,
+                S_X=np.kron(H.T, G), gauge_X=np.kron(H.T, I), aggregate_X=np.kron(I, G),
+                S_Z=np.kron(G, H.T), gauge_Z=np.kron(I, H.T), aggregate_Z=np.kron(G, I),
+                L_X=np.kron(P, G), L_Z=np.kron(G, P))
+
+
+def _edge_colouring_circulant(M):
+    """Proper edge colouring of a bipartite graph whose every row and column has the same degree D, by repeated
+    perfect matchings (Hall); returns D lists of (row, col).  (The reference uses Hopcroft-Karp matchings,
+    utils.py:577-623; any proper colouring is a valid CNOT schedule.)"""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import maximum_bipartite_matching
+    M = np.array(M, dtype=np.int64).copy()
+    colours = []
+    while M.any():
+        match = maximum_bipartite_matching(csr_matrix(M), perm_type="column")
+        layer = [(u, int(v)) for u, v in enumerate(match) if v >= 0]
+        for u, v in layer:
+            M[u, v] = 0
+        colours.append(layer)
+    return colours
+
+
+def shyps_memory_circuit(r, p, num_repeat, z_basis=True):
+    """Memory experiment of the SHYPS code with the gate order and noise placement of build_SHYPS_circuit.py:59-191
+    (gauge measurements in 3 + 3 CNOT layers per round, detectors on aggregated gauge outcomes)."""
+    cd = shyps_code(r)
+    N = cd["N"]
+    XG, DQ, ZG = 0, N, 2 * N
+    col_Z = _edge_colouring_circulant(cd["gauge_Z"])
+    col_X = _edge_colouring_circulant(cd["gauge_X"])
+    assert len(col_Z) == 3 and len(col_X) == 3
+    agg = cd["aggregate_Z"] if z_basis else cd["aggregate_X"]
+    c = Ops()
+
+    def detectors(repeat):
+        for row in agg:
+            rec = []
+            for i in np.nonzero(row)[0]:
+                rec.append(-N + int(i))
+                if repeat:
+                    rec.append(-3 * N + int(i))
+            c.detector(rec)
+
+    def block(repeat):
+        if repeat:
+            for i in range(N):
+                c.noise("X_ERROR", p, ZG + i)
+                c.noise("Z_ERROR", p, XG + i)
+                c.noise("DEPOLARIZE1", p, DQ + i)
+        for layer in col_Z:
+            for g, dq in layer:
+                c.gate("CNOT", DQ + dq, ZG + g)
+                c.noise("DEPOLARIZE2", p, DQ + dq, ZG + g)
+        for i in range(N):
+            c.noise("X_ERROR", p, ZG + i)
+            c.gate("M", ZG + i)
+        if z_basis:
+            detectors(repeat)
+        for i in range(N):
+            c.gate("RX", XG + i)
+            c.noise("Z_ERROR", p, XG + i)
+        for layer in col_X:
+            for g, dq in layer:
+                c.gate("CNOT", XG + g, DQ + dq)
+                c.noise("DEPOLARIZE2", p, XG + g, DQ + dq)
+        for i in range(N):
+            c.noise("Z_ERROR", p, XG + i)
+            c.gate("MX", XG + i)
+        if not z_basis:
+            detectors(repeat)
+        for i in range(N):
+            c.gate("R", ZG + i)
+            c.noise("X_ERROR", p, ZG + i)
+
+    for i in range(N):
+        c.gate("RX", XG + i); c.noise("Z_ERROR", p, XG + i)
+        c.gate("R", ZG + i); c.noise("X_ERROR", p, ZG + i)
+    for i in range(N):
+        c.gate("R" if z_basis else "RX", DQ + i)
+        c.noise("X_ERROR" if z_basis else "Z_ERROR", p, DQ + i)
+    block(False)
+    for _ in range(num_repeat - 1):
+        block(True)
+    for i in range(N):
+        c.noise("X_ERROR" if z_basis else "Z_ERROR", p, DQ + i)
+        c.gate("M" if z_basis else "MX", DQ + i)
+    pcm = cd["S_Z"] if z_basis else cd["S_X"]
+    logical = cd["L_Z"] if z_basis else cd["L_X"]
+    for ri, row in enumerate(pcm):
+        rec = [-N + int(j) for j in np.nonzero(row)[0]]
+        rec += [-(3 if z_basis else 2) * N + int(j) for j in np.nonzero(agg[ri])[0]]
+        c.detector(rec)
+    for i, row in enumerate(logical):
+        c.observable(i, [-N + int(j) for j in np.nonzero(row)[0]])
+    return c
+
+
 def detector_error_model(circ):
     """-> (symptoms list[int], probs list[float], num_detectors, num_observables).
 

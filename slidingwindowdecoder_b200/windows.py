@@ -40,19 +40,21 @@ class WindowPlan:
     noisy_prior: np.ndarray = None
 
 
-def reshuffle_by_round(chk, obs, priors, n):
-    """guessing.py:49-84: regroup the columns by (first, last) detector round; compute anchors."""
+def reshuffle_by_round(chk, obs, priors, n=None, h=None):
+    """guessing.py:49-84 (h = n/2 detectors per round) / SHYPS.ipynb cell 1 (h = r(2^r-1)): regroup the columns by
+    (first, last) detector round; compute anchors."""
     chk = csc_matrix(chk)
     obs = csc_matrix(obs)
     num_row, num_col = chk.shape
-    h = n // 2
+    if h is None:
+        h = n // 2
     regions = []
     i = 0
     while i < num_row:
         regions.append((i, i + h))
-        if i + n > num_row:
+        if i + 2 * h > num_row:
             break
-        regions.append((i, i + n))
+        regions.append((i, i + 2 * h))
         i += h
     region_id = {r: k for k, r in enumerate(regions)}
     buckets = [[] for _ in regions]
@@ -78,10 +80,12 @@ def reshuffle_by_round(chk, obs, priors, n):
     return chk, obs, priors, anchors
 
 
-def build_windows(chk, obs, priors, n, W=3, F=1, method=1, noisy_prior=None):
-    """-> WindowPlan.  chk/obs/priors as returned by dem_to_check_matrices (any column order)."""
-    chk, obs, priors, anchors = reshuffle_by_round(chk, obs, priors, n)
-    h = n // 2
+def build_windows(chk, obs, priors, n=None, W=3, F=1, method=1, noisy_prior=None, h=None):
+    """-> WindowPlan.  chk/obs/priors as returned by dem_to_check_matrices (any column order).
+    n: number of data qubits of a BB code (h = n/2 detectors per round); or pass h directly (SHYPS: method=0)."""
+    if h is None:
+        h = n // 2
+    chk, obs, priors, anchors = reshuffle_by_round(chk, obs, priors, h=h)
     if noisy_prior is None and method != 0:
         b = anchors[W]
         c = anchors[W - 1]

@@ -72,8 +72,37 @@ def run_osd(cls, mat, priors, synd, kwargs):
                 osd0=np.packbits(o0, axis=1), lpr_first8=lpr[:8])
 
 
+def shyps_section(bpgdg_decoder, osd_window):
+    """C5: SHYPS r=3 memory experiment, 6 rounds, (3,1) windows of 63 x 588 (SHYPS.ipynb cell 1), p = 3e-3."""
+    from slidingwindowdecoder_b200.dem import shyps_memory_circuit, detector_error_model, dem_to_check_matrices
+    from slidingwindowdecoder_b200.windows import build_windows
+    from slidingwindowdecoder_b200.sliding_window import sample_dem
+    chk, obs, pri = dem_to_check_matrices(detector_error_model(shyps_memory_circuit(3, 0.003, 6)))
+    plan = build_windows(chk, obs, pri, h=21, W=3, F=1, method=0)
+    det, ob, _ = sample_dem(plan.chk, plan.obs, plan.priors, 2500, np.random.default_rng(5))
+    for wi in (0, len(plan.windows) - 1):
+        w = plan.windows[wi]
+        s = det[:, w.row0:w.row1]
+        s = s[np.nonzero(s.any(axis=1))[0][:500]]
+        kw = dict(pre_max_iter=8, post_max_iter=100, ms_scaling_factor=1.0, osd_method="osd_cs", osd_order=10)
+        save(f"c5_w{wi}_osdw_cs10", w.mat, w.prior, s, kw, **run_osd(osd_window, w.mat, w.prior, s, kw))
+        kw = dict(max_iter=8, multi_thread=False)
+        d, c = run_gdg(bpgdg_decoder, w.mat, w.prior, s, kw)
+        save(f"c5_w{wi}_gdg_mt0", w.mat, w.prior, s, kw, dec=d, conv=c)
+        kw = dict(max_iter=8, multi_thread=True)
+        d, c = run_gdg(bpgdg_decoder, w.mat, w.prior, s, kw)
+        save(f"c5_w{wi}_gdg_mt1", w.mat, w.prior, s, kw, dec=d, conv=c)
+
+
 def main():
     build_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "shyps":
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 2)
+        from src.bp_guessing_decoder import bpgdg_decoder
+        from src.osd_window import osd_window
+        shyps_section(bpgdg_decoder, osd_window)
+        return
     devnull = os.open(os.devnull, os.O_WRONLY)
     os.dup2(devnull, 2)      # the reference prints "Error setting thread affinity" per thread on small hosts
     from src.bp_guessing_decoder import bpgdg_decoder, bpgd_decoder
@@ -149,6 +178,7 @@ def main():
     s = det[:, w.row0:w.row1]; s = s[np.nonzero(s.any(axis=1))[0][:200]]
     kw = dict(pre_max_iter=8, post_max_iter=100, ms_scaling_factor=1.0, osd_method="osd_cs", osd_order=10)
     save("c3_w5_osdw_cs10", w.mat, w.prior, s, kw, **run_osd(osd_window, w.mat, w.prior, s, kw))
+    shyps_section(bpgdg_decoder, osd_window)
 
 
 if __name__ == "__main__":

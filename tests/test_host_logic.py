@@ -34,6 +34,21 @@ def test_dem_known_answers(dem144):
     assert [w.ncommit for w in plan.windows] == [648, 720, 1656]
 
 
+def test_shyps_dem_known_answers():
+    """SHYPS.ipynb:212 (output of real stim): r=3, 4 rounds -> 105 x 833, max (row, col) weight (44, 9), min (28, 2)."""
+    from slidingwindowdecoder_b200.dem import shyps_memory_circuit, detector_error_model, dem_to_check_matrices, shyps_code
+    from slidingwindowdecoder_b200.windows import build_windows
+    cd = shyps_code(3)
+    assert not (cd["S_X"] @ cd["S_Z"].T % 2).any() and not (cd["gauge_X"] @ cd["L_Z"].T % 2).any()
+    chk, obs, pri = dem_to_check_matrices(detector_error_model(shyps_memory_circuit(3, 0.001, 4)))
+    assert chk.shape == (105, 833) and obs.shape[0] == 9
+    rw = np.asarray(chk.sum(axis=1)).ravel()
+    cw = np.asarray(chk.sum(axis=0)).ravel()
+    assert (rw.max(), cw.max(), rw.min(), cw.min()) == (44, 9, 28, 2)
+    plan = build_windows(chk, obs, pri, h=21, W=3, F=1, method=0)
+    assert [w.mat.shape for w in plan.windows] == [(63, 588), (63, 588), (63, 441)]
+
+
 def test_dem_sampling_consistency(dem144):
     from slidingwindowdecoder_b200.sliding_window import sample_dem
     code, chk, obs, pri = dem144
