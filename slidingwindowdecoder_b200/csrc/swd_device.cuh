@@ -352,9 +352,8 @@ __device__ __forceinline__ void check_update(Ctx &c, int p0, int len, int cm, do
         }
         par ^= __popc(neg) & 1;
         const double q1 = m1 * fpos, q2 = m2 * fpos;             // c2b magnitude * alpha (sign applied below)
-        u32 live = ~dead & (len == 32 ? 0xffffffffu : ((1u << len) - 1u));
-        while (live) {
-            const int k = __ffs(live) - 1; live &= live - 1;
+        for (int k = 0; k < len; k++) {                          // uniform trip count across the warp (rows are ranked)
+            if ((dead >> k) & 1u) continue;
             row[k] = flip_sign((k == arg) ? q2 : q1, (u32)par ^ ((neg >> k) & 1u));
         }
     } else {

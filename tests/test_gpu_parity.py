@@ -271,3 +271,23 @@ def test_heavy_columns_long_rows(kind, oracle_mod):
     assert np.array_equal(conv, o_conv.astype(np.uint8))
     bad = np.nonzero((corr != o_dec.astype(np.uint8)).any(axis=1))[0]
     assert len(bad) == 0, f"shots {bad[:10]}"
+
+
+def test_chunked_workspace_gives_identical_results(monkeypatch):
+    """Batches larger than the workspace capacity are decoded in chunks (SWD_WS_BYTES caps the workspace)."""
+    from slidingwindowdecoder_b200 import bpgdg_decoder, osd_window
+    g = load_golden("c2_w1_gdg_mt1")
+    synd = np.concatenate([g["synd"]] * 3)
+    ref, refc = bpgdg_decoder(g["mat"], channel_probs=g["priors"], **g["kwargs"]).decode_batch(synd)
+    monkeypatch.setenv("SWD_WS_BYTES", str(40 << 20))
+    small = bpgdg_decoder(g["mat"], channel_probs=g["priors"], **g["kwargs"])
+    corr, conv = small.decode_batch(synd)
+    assert np.array_equal(corr, ref) and np.array_equal(conv, refc)
+    go = load_golden("c2_w1_osdw_cs10")
+    so = np.concatenate([go["synd"]] * 3)
+    d = osd_window(go["mat"], channel_probs=go["priors"], **go["kwargs"])
+    corr, conv, pm = d.decode_batch(so, return_pm=True)
+    out = d.last_outputs()
+    assert np.array_equal(corr, np.concatenate([go["dec"]] * 3))
+    assert np.array_equal(pm, np.concatenate([go["min_pm"]] * 3))
+    assert np.array_equal(out["bp_iteration"], np.concatenate([go["bp_iteration"]] * 3))
