@@ -263,3 +263,23 @@ class osd_window(_window_decoder_base):
     @property
     def log_prob_ratios(self):
         return self.last_outputs(1)["log_prob_ratios"][0].copy()
+
+
+class BpOsdDecoder(osd_window):
+    """Facade with the constructor kwargs the reference's drivers pass to `ldpc.BpOsdDecoder`
+    (osd.py:142-150, guessing.py:150-158, simulation.py:39-47): min-sum BP for `max_iter` iterations on the whole
+    matrix (no shortening: new_n = n, no second BP stage), then OSD.  It runs this repository's `osd_window`
+    kernels; `ldpc` itself is a third-party dependency that is not vendored by the reference, so its exact
+    tie-breaking (it ranks by the last posterior, this ranks by the 4-iteration history sum) is NOT reproduced:
+    parity with `ldpc` is unpinned.  `osd0_decoding` / `converge` follow osd_window."""
+
+    def __init__(self, parity_check_matrix, **kwargs):
+        method = str(kwargs.get("bp_method", "minimum_sum")).lower()
+        if method not in ("minimum_sum", "ms", "min_sum", "msl"):
+            raise ValueError("only bp_method='minimum_sum' is implemented (product-sum is not part of the reference's own code)")
+        n = parity_check_matrix.shape[1]
+        super().__init__(parity_check_matrix, channel_probs=kwargs.get("channel_probs"),
+                         pre_max_iter=int(kwargs.get("max_iter", 0)) or n, post_max_iter=0,
+                         ms_scaling_factor=float(kwargs.get("ms_scaling_factor", 1.0)), new_n=n,
+                         osd_method=kwargs.get("osd_method", "osd_0"), osd_order=kwargs.get("osd_order", 0),
+                         device=kwargs.get("device", 0))

@@ -291,3 +291,20 @@ def test_chunked_workspace_gives_identical_results(monkeypatch):
     assert np.array_equal(corr, np.concatenate([go["dec"]] * 3))
     assert np.array_equal(pm, np.concatenate([go["min_pm"]] * 3))
     assert np.array_equal(out["bp_iteration"], np.concatenate([go["bp_iteration"]] * 3))
+
+
+def test_bposd_facade_matches_osd_window_semantics(oracle_mod):
+    """`BpOsdDecoder(max_iter, osd_method, osd_order)` == osd_window(pre_max_iter=max_iter, post_max_iter=0, new_n=n)."""
+    from slidingwindowdecoder_b200 import BpOsdDecoder
+    g = load_golden("c2_w1_osdw_cs10")          # middle window: full row rank, every syndrome has a solution
+    dec = BpOsdDecoder(g["mat"], channel_probs=list(g["priors"]), max_iter=30, bp_method="minimum_sum", ms_scaling_factor=1.0,
+                       osd_method="OSD_CS", osd_order=10)
+    synd = g["synd"][:200]
+    corr, conv = dec.decode_batch(synd)
+    orc = oracle_mod.Oracle(g["mat"], g["priors"])
+    kw = dict(pre_max_iter=30, post_max_iter=0, ms_scaling_factor=1.0, new_n=g["mat"].shape[1], osd_method="osd_cs", osd_order=10)
+    for i, s in enumerate(synd):
+        r = orc.osd_window(s, **kw)
+        assert conv[i] == r["converge"] and np.array_equal(corr[i], r["dec"].astype(np.uint8)), i
+    H = g["mat"].toarray().astype(np.int64)
+    assert not ((corr.astype(np.int64) @ H.T + synd) % 2).any()
