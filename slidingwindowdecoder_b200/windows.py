@@ -80,17 +80,21 @@ def reshuffle_by_round(chk, obs, priors, n=None, h=None):
     return chk, obs, priors, anchors
 
 
-def build_windows(chk, obs, priors, n=None, W=3, F=1, method=1, noisy_prior=None, h=None):
+def build_windows(chk, obs, priors, n=None, W=3, F=1, method=1, noisy_prior=None, h=None, keep_cols=None):
     """-> WindowPlan.  chk/obs/priors as returned by dem_to_check_matrices (any column order).
-    n: number of data qubits of a BB code (h = n/2 detectors per round); or pass h directly (SHYPS: method=0)."""
+    n: number of data qubits of a BB code (h = n/2 detectors per round); or pass h directly (SHYPS: method=0).
+    keep_cols: un-merged columns of the round after the window for method=1 (default 3h as guessing.py:90,112;
+    osd.py:83,106 uses n for the x basis)."""
     if h is None:
         h = n // 2
+    if keep_cols is None:
+        keep_cols = 3 * h
     chk, obs, priors, anchors = reshuffle_by_round(chk, obs, priors, h=h)
     if noisy_prior is None and method != 0:
         b = anchors[W]
         c = anchors[W - 1]
         if method == 1:
-            c = (c[0], c[1] + 3 * h)
+            c = (c[0], c[1] + keep_cols)
         sub = chk[c[0]:b[0], c[1]:b[1]]
         noisy_prior = np.asarray(sub.multiply(priors[c[1]:b[1]][None, :]).sum(axis=1)).ravel()
     noisy = None if method == 0 else np.ones(h) * noisy_prior
@@ -104,7 +108,7 @@ def build_windows(chk, obs, priors, n=None, W=3, F=1, method=1, noisy_prior=None
         if not last and method != 0:
             c = anchors[top_left + W - 1]
             if method == 1:
-                c = (c[0], c[1] + 3 * h)
+                c = (c[0], c[1] + keep_cols)
             body = chk[a[0]:b[0], a[1]:c[1]]
             ident = sp_vstack([csc_matrix((h * (W - 1), h), dtype=np.uint8), sp_identity(h, dtype=np.uint8, format="csc")])
             mat = sp_hstack([body, ident]).tocsc()

@@ -49,6 +49,26 @@ def test_shyps_dem_known_answers():
     assert [w.mat.shape for w in plan.windows] == [(63, 588), (63, 588), (63, 441)]
 
 
+@pytest.mark.parametrize("W,F,method", [(3, 1, 1), (5, 2, 1), (4, 1, 2), (3, 1, 0), (2, 2, 1)])
+def test_window_commits_partition_the_columns(dem144, W, F, method):
+    """Whatever (W, F, method): the committed column ranges tile the DEM columns exactly once and in order, every window
+    has W rounds of detectors (the last one reaches the end), identity columns carry the summed prior of what they merge."""
+    from slidingwindowdecoder_b200.windows import build_windows
+    code, chk, obs, pri = dem144
+    plan = build_windows(chk, obs, pri, code.N, W=W, F=F, method=method)
+    h = code.N // 2
+    pos = 0
+    for w in plan.windows:
+        assert w.col0 == pos
+        pos += w.ncommit
+        assert w.row1 - w.row0 == (W * h if not w.last else w.row1 - w.row0)
+        if method != 0 and not w.last:
+            ident = w.mat[:, w.ncols_dem:].toarray()
+            assert np.array_equal(ident[-h:], np.eye(h, dtype=ident.dtype)) and not ident[:-h].any()
+            assert np.allclose(w.prior[w.ncols_dem:], plan.noisy_prior)
+    assert pos == plan.chk.shape[1] and plan.windows[-1].last and plan.windows[-1].row1 == plan.chk.shape[0]
+
+
 def test_dem_sampling_consistency(dem144):
     from slidingwindowdecoder_b200.sliding_window import sample_dem
     code, chk, obs, pri = dem144
