@@ -324,7 +324,7 @@ def run_ours(args):
                 "pre_bp_achieved_gbs": round(pre_bytes / (ktimes.get("pre_bp", [1e-9, 0])[0] / 1e3) / 1e9, 1) if ktimes.get("pre_bp", [0, 0])[0] else None,
                 "kernel_ms": kernel_ms}
     # ---- CPU baseline on a bounded sample
-    if args.skip_cpu:
+    if args.skip_cpu or world > 1:        # the CPU baseline is timed on rank 0 of the 1-GPU run only
         cpu_baseline = None
     else:
         arm = CpuArm(plan)
