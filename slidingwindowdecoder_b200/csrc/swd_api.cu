@@ -315,7 +315,7 @@ static int setup_kernels(swd_decoder *d) {
     make_path_smem(d->PSB, nn, m, es_slots);
     // ---- K1
     d->T1 = std::min(256, std::max(64, r32up((n + 3) / 4)));
-    if (const char *e = getenv("SWD_T1")) d->T1 = atoi(e);
+    if (const char *e = getenv("SWD_T1")) d->T1 = std::min(256, std::max(32, r32up(atoi(e))));
     PreSmem &S1 = d->PRE;
     int o = 0; S1.off_msg = o; o += 8 * std::max(d->nnz, 1); o = r16(o);
     S1.off_upar = o; o += 4 * m; o = r16(o);

@@ -329,47 +329,64 @@ __device__ __forceinline__ double flip_sign(double x, u32 flip) {
     return __hiloint2double(__double2hiint(x) ^ (int)(flip << 31), __double2loint(x));
 }
 
-// one check update in min1/min2/argmin/parity form (== bpgd.cpp:103-148) on message slots p0 .. p0+len.
+// one message slot of the first check-update loop: running (min1, min2, argmin), sign and dead masks.
 // Plain compares instead of fmin/fmax: no operand can be NaN once dead slots are mapped to 1e308.
-__device__ __forceinline__ void check_update(Ctx &c, int p0, int len, int cm, double fpos, double fneg) {
+__device__ __forceinline__ void check_slot(const double b, const int k, double &m1, double &m2, int &arg, u32 &neg, u32 &dead) {
+    const bool isdead = (b != b);                                // decided VN or pad slot
+    const bool isneg = (b <= 0.0);                               // false for NaN
+    double a = fabs(b);
+    a = (a > SWD_CLIP) ? SWD_CLIP : a;
+    a = isdead ? SWD_BIG : a;
+    const bool lt = a < m1;
+    const double hi = lt ? m1 : a;                               // max(m1, a)
+    m2 = (hi < m2) ? hi : m2;
+    m1 = lt ? a : m1;
+    arg = lt ? k : arg;
+    neg |= (u32)isneg << k; dead |= (u32)isdead << k;
+}
+
+// rows longer than 32 slots (heavy checks of non-BB codes): out of line, so that the hot loop stays small
+__device__ __noinline__ void check_update_long(double *row, int len, int cm, double fpos, double fneg) {
     double m1 = SWD_BIG, m2 = SWD_BIG; int arg = -1, par = cm;
+#pragma unroll 1
+    for (int k = 0; k < len; k++) {
+        const double b = row[k];
+        if (b != b) continue;
+        double a = fabs(b); a = (a > SWD_CLIP) ? SWD_CLIP : a;
+        if (a < m1) { m2 = m1; m1 = a; arg = k; } else if (a < m2) m2 = a;
+        par ^= (b <= 0.0);
+    }
+#pragma unroll 1
+    for (int k = 0; k < len; k++) {
+        const double b = row[k];
+        if (b != b) continue;
+        const double mag = (k == arg) ? m2 : m1;
+        row[k] = mag * ((par ^ (int)(b <= 0.0)) ? fneg : fpos);
+    }
+}
+
+// one check update in min1/min2/argmin/parity form (== bpgd.cpp:103-148) on message slots p0 .. p0+len.
+// Deliberately compact code (two slots per trip, no further unrolling): the min-sum iteration has to stay
+// resident in the instruction caches (L0 ~6 KB, L1.5 32 KB) while 6 CTAs per SM run different phases.
+__device__ __forceinline__ void check_update(Ctx &c, int p0, int len, int cm, double fpos, double fneg) {
     double *row = c.msg + p0;
-    if (len <= 32) {
-        u32 neg = 0, dead = 0;
-        for (int k = 0; k < len; k++) {
-            const double b = row[k];
-            const bool isdead = (b != b);                        // decided VN or pad slot
-            const bool isneg = (b <= 0.0);                       // false for NaN
-            double a = fabs(b);
-            a = (a > SWD_CLIP) ? SWD_CLIP : a;
-            a = isdead ? SWD_BIG : a;
-            const bool lt = a < m1;
-            const double hi = lt ? m1 : a;                       // max(m1, a)
-            m2 = (hi < m2) ? hi : m2;
-            m1 = lt ? a : m1;
-            arg = lt ? k : arg;
-            neg |= (u32)isneg << k; dead |= (u32)isdead << k;
-        }
-        par ^= __popc(neg) & 1;
-        const double q1 = m1 * fpos, q2 = m2 * fpos;             // c2b magnitude * alpha (sign applied below)
-        for (int k = 0; k < len; k++) {                          // uniform trip count across the warp (rows are ranked)
-            if ((dead >> k) & 1u) continue;
-            row[k] = flip_sign((k == arg) ? q2 : q1, (u32)par ^ ((neg >> k) & 1u));
-        }
-    } else {
-        for (int k = 0; k < len; k++) {
-            const double b = row[k];
-            if (b != b) continue;
-            double a = fabs(b); a = (a > SWD_CLIP) ? SWD_CLIP : a;
-            if (a < m1) { m2 = m1; m1 = a; arg = k; } else if (a < m2) m2 = a;
-            par ^= (b <= 0.0);
-        }
-        for (int k = 0; k < len; k++) {
-            const double b = row[k];
-            if (b != b) continue;
-            const double mag = (k == arg) ? m2 : m1;
-            row[k] = mag * ((par ^ (int)(b <= 0.0)) ? fneg : fpos);
-        }
+    if (len > 32) { check_update_long(row, len, cm, fpos, fneg); return; }
+    double m1 = SWD_BIG, m2 = SWD_BIG; int arg = -1;
+    u32 neg = 0, dead = 0;
+#pragma unroll 1
+    for (int k = 0; k < len; k += 2) {
+        const double b0 = row[k];
+        const double b1 = (k + 1 < len) ? row[k + 1] : dnan();
+        check_slot(b0, k, m1, m2, arg, neg, dead);
+        check_slot(b1, k + 1, m1, m2, arg, neg, dead);
+    }
+    const u32 par = (u32)cm ^ (__popc(neg) & 1u);
+    const double q1 = m1 * fpos, q2 = m2 * fpos;                 // c2b magnitude * alpha (sign applied below)
+    u32 live = ~dead & ((len >= 32) ? 0xffffffffu : ((1u << len) - 1u));
+#pragma unroll 1
+    while (live) {                                               // live slots only
+        const int k = __ffs(live) - 1; live &= live - 1;
+        row[k] = flip_sign((k == arg) ? q2 : q1, par ^ ((neg >> k) & 1u));
     }
 }
 
@@ -388,7 +405,7 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
         // ---- check pass (+ convergence test of the previous iteration)
         int mism = (it > 0) ? c.bad_rows : 0;
         const bool last = (it == num_iter);
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < SWD_CPT; i++) {
             const int q = own_slot(i, tid, T);
             if (q >= c.m) continue;
@@ -408,24 +425,28 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
             if (!__syncthreads_or(mism)) { if (iters_done) *iters_done = it; return 1; }
         } else __syncthreads();
         if (last) break;
-        // ---- variable pass: ordered prefix / suffix sums (bpgd.cpp:151-182)
+        // ---- variable pass: ordered prefix / suffix sums (bpgd.cpp:151-182); predicated straight-line code per slot
+        const int ring = it & 3;
 #pragma unroll
         for (int i = 0; i < VPT; i++) {
             const int sl = own_slot(i, tid, T);
             int j = -1, e0 = 0, d = 0;
             if (sl < c.nn) { j = c.vperm[sl]; if (c.vn_mask[j] < 0) { e0 = c.voff[j]; d = c.voff[j + 1] - e0; } else j = -1; }
-            const int dw = __reduce_max_sync(FULLMASK, d);     // VNs are owned in degree order: ~uniform per warp
             if (j >= 0) {
                 double cc[DMAX], pre[DMAX]; int pp[DMAX];
                 double t = c.prior[j];
 #pragma unroll
-                for (int k = 0; k < DMAX; k++) { if (k >= dw) break; if (k < d) { pp[k] = c.vpos[e0 + k]; cc[k] = c.msg[pp[k]]; } }
+                for (int k = 0; k < DMAX; k++) if (k < d) { pp[k] = c.vpos[e0 + k]; cc[k] = c.msg[pp[k]]; }
 #pragma unroll
-                for (int k = 0; k < DMAX; k++) { if (k >= dw) break; if (k < d) { pre[k] = t; t += cc[k]; } }
-                switch (it & 3) { case 0: h[i][0] = t; break; case 1: h[i][1] = t; break; case 2: h[i][2] = t; break; default: h[i][3] = t; }
+                for (int k = 0; k < DMAX; k++) if (k < d) { pre[k] = t; t += cc[k]; }
+                h[i][0] = (ring == 0) ? t : h[i][0]; h[i][1] = (ring == 1) ? t : h[i][1];
+                h[i][2] = (ring == 2) ? t : h[i][2]; h[i][3] = (ring == 3) ? t : h[i][3];
                 const int hard = (t <= 0.0);
                 c.error[j] = (i8)hard;
-                if (hard) for (int k = 0; k < d; k++) atomicXor(&c.upar[c.vrow[e0 + k]], 1u);
+                if (hard) {
+#pragma unroll 1
+                    for (int k = 0; k < d; k++) atomicXor(&c.upar[c.vrow[e0 + k]], 1u);
+                }
                 double s = 0.0;
 #pragma unroll
                 for (int k = DMAX - 1; k >= 0; k--) if (k < d) { c.msg[pp[k]] = pre[k] + s; s += cc[k]; }

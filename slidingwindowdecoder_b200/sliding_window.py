@@ -29,7 +29,10 @@ class SlidingWindowDecoder:
     """Holds one decoder per distinct window matrix (the reference rebuilds one per window,
     guessing.py:160-174) and the device-side window bookkeeping."""
 
-    def __init__(self, plan: WindowPlan, decoder="gdg", device=0, last_window_kwargs=None, **decoder_kwargs):
+    def __init__(self, plan: WindowPlan, decoder="gdg", device=0, last_window_kwargs=None, streams=1, **decoder_kwargs):
+        """streams > 1: every batch is split into that many sub-batches which run the window loop on their own CUDA
+        streams with their own decoder workspaces, so that one sub-batch's kernel tails (a few long branch paths
+        finishing) are filled by the next sub-batch's work.  Results do not depend on `streams`."""
         import torch
         self.torch = torch
         self.plan = plan
@@ -50,22 +53,26 @@ class SlidingWindowDecoder:
                                         self._obs_ri.ctypes.data_as(i32p), C.byref(self._win))
         _lib.check(st, "swd_window_create")
         cls = {"gdg": bpgdg_decoder, "osd": osd_window}.get(decoder, decoder)
-        self.decoders = []
-        cache = []
-        for w in plan.windows:
-            kw = dict(decoder_kwargs)
-            if w.last and last_window_kwargs:
-                kw.update(last_window_kwargs)
-            found = None
-            for (m0, p0, kw0, d0) in cache:
-                if kw0 == kw and m0.shape == w.mat.shape and m0.nnz == w.mat.nnz and (m0 != w.mat).nnz == 0 and np.array_equal(p0, w.prior):
-                    found = d0
-                    break
-            if found is None:
-                found = cls(w.mat, channel_probs=w.prior, device=self.device, **kw)
-                cache.append((w.mat, w.prior, kw, found))
-            self.decoders.append(found)
-        self._counts = None
+        self.nstreams = max(1, int(streams))
+        self.decoder_sets = []                 # [stream][window] -> decoder (windows with equal matrices share one)
+        for _ in range(self.nstreams):
+            decs, cache = [], []
+            for w in plan.windows:
+                kw = dict(decoder_kwargs)
+                if w.last and last_window_kwargs:
+                    kw.update(last_window_kwargs)
+                found = None
+                for (m0, p0, kw0, d0) in cache:
+                    if kw0 == kw and m0.shape == w.mat.shape and m0.nnz == w.mat.nnz and (m0 != w.mat).nnz == 0 and np.array_equal(p0, w.prior):
+                        found = d0
+                        break
+                if found is None:
+                    found = cls(w.mat, channel_probs=w.prior, device=self.device, **kw)
+                    cache.append((w.mat, w.prior, kw, found))
+                decs.append(found)
+            self.decoder_sets.append(decs)
+        self.decoders = self.decoder_sets[0]
+        self._side_streams = None
 
     def __del__(self):
         w = getattr(self, "_win", None)
@@ -75,21 +82,19 @@ class SlidingWindowDecoder:
 
     def unique_decoders(self):
         seen, out = set(), []
-        for d in self.decoders:
-            if id(d) not in seen:
-                seen.add(id(d)); out.append(d)
+        for decs in self.decoder_sets:
+            for d in decs:
+                if id(d) not in seen:
+                    seen.add(id(d)); out.append(d)
         return out
 
-    def decode_device(self, det, obs, return_corrections=False, window_events=None):
-        """det [B, num_det], obs [B, num_obs]: torch CUDA uint8 tensors, MODIFIED IN PLACE into the residual
-        syndrome / residual observables.  Returns dict with device tensors:
-          counts uint64[2] = (flagged shots, failed shots), window_unconverged int64[num_win]."""
+    def _run_windows(self, det, obs, decs, total, window_events):
+        """The window loop for one (sub-)batch on the current stream; det / obs are updated in place."""
         torch = self.torch
         B = det.shape[0]
         stream = C.c_void_p(torch.cuda.current_stream(det.device).cuda_stream)
         unconv = []
-        total = torch.zeros((B, self.num_col), dtype=torch.uint8, device=det.device) if return_corrections else None
-        for w, dec in zip(self.plan.windows, self.decoders):
+        for w, dec in zip(self.plan.windows, decs):
             m = w.row1 - w.row0
             synd = torch.empty((B, m), dtype=torch.uint8, device=det.device)
             _lib.check(self.lib.swd_window_extract(self._win, det.data_ptr(), B, w.row0, m, synd.data_ptr(), stream), "extract")
@@ -102,12 +107,44 @@ class SlidingWindowDecoder:
             _lib.check(self.lib.swd_window_commit(self._win, corr.data_ptr(), B, n_win, w.col0, w.ncommit, det.data_ptr(),
                                                   obs.data_ptr() if self.num_obs else None, stream), "commit")
             unconv.append((B - conv.sum(dtype=torch.int64)))
-            if return_corrections:
+            if total is not None:
                 total[:, w.col0:w.col0 + w.ncommit] = corr[:, :w.ncommit]
         counts = torch.zeros(2, dtype=torch.int64, device=det.device)
         _lib.check(self.lib.swd_window_count_failures(self._win, det.data_ptr(), obs.data_ptr() if self.num_obs else None, B,
                                                       counts.data_ptr(), stream), "count")
-        out = dict(counts=counts, window_unconverged=torch.stack(unconv))
+        return counts, torch.stack(unconv)
+
+    def decode_device(self, det, obs, return_corrections=False, window_events=None):
+        """det [B, num_det], obs [B, num_obs]: torch CUDA uint8 tensors, MODIFIED IN PLACE into the residual
+        syndrome / residual observables.  Returns dict with device tensors:
+          counts uint64[2] = (flagged shots, failed shots), window_unconverged int64[num_win]."""
+        torch = self.torch
+        B = det.shape[0]
+        total = torch.zeros((B, self.num_col), dtype=torch.uint8, device=det.device) if return_corrections else None
+        ns = self.nstreams if (window_events is None and B >= 2 * self.nstreams) else 1
+        if ns == 1:
+            counts, unconv = self._run_windows(det, obs, self.decoders, total, window_events)
+        else:
+            if self._side_streams is None:
+                self._side_streams = [torch.cuda.Stream(device=det.device) for _ in range(self.nstreams)]
+            cur = torch.cuda.current_stream(det.device)
+            bounds = [(B * i) // ns for i in range(ns + 1)]
+            parts = []
+            for i in range(ns):
+                st = self._side_streams[i]
+                st.wait_stream(cur)
+                lo, hi = bounds[i], bounds[i + 1]
+                with torch.cuda.stream(st):
+                    parts.append(self._run_windows(det[lo:hi], obs[lo:hi], self.decoder_sets[i],
+                                                   None if total is None else total[lo:hi], None))
+                for t in (det, obs, total):
+                    if t is not None:
+                        t.record_stream(st)
+            for st in self._side_streams[:ns]:
+                cur.wait_stream(st)
+            counts = sum(p[0] for p in parts)
+            unconv = sum(p[1] for p in parts)
+        out = dict(counts=counts, window_unconverged=unconv)
         if return_corrections:
             out["total_e_hat"] = total
         return out
