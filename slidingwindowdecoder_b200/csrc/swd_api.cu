@@ -32,7 +32,7 @@ typedef void (*path_fn_t)(Workspace, SubLayout, SubLayout, PathSmem, GdgDev, int
 static path_fn_t pick_path_kernel(int dmax, int T) {
     if (dmax == 6) {
 #ifndef SWD_MINB
-#define SWD_MINB 6
+#define SWD_MINB 7
 #endif
         if (T <= 128) return path_kernel<4, 6, 128, SWD_MINB>;
         if (T <= 512) return path_kernel<4, 6, 512, 1>;
@@ -240,7 +240,8 @@ static int occupancy(K kernel, int threads, size_t smem, int *out) {
     return SWD_OK;
 }
 
-static void make_layout(SubLayout &L, int nn, int m, int es, int lcap) {
+// with_col = false: shared-memory image of the blob; `col` (needed only for the final scatter) stays in HBM
+static void make_layout(SubLayout &L, int nn, int m, int es, int lcap, bool with_col = true) {
     L.nn = nn; L.m = m; L.es_max = es; L.lcap = lcap;
     int o = 16;
     L.off_prior = o; o += 8 * nn; o = r16(o);
@@ -253,7 +254,7 @@ static void make_layout(SubLayout &L, int nn, int m, int es, int lcap) {
     L.off_cndeg = o; o += m; o = r16(o);
     L.off_vperm = o; o += 2 * nn; o = r16(o);
     L.off_cperm = o; o += 2 * m; o = r16(o);
-    L.off_col = o; o += 2 * nn; o = r16(o);
+    L.off_col = o; if (with_col) { o += 2 * nn; o = r16(o); }
     L.fixed_bytes = o;
     L.off_vrow = o; o += r16(2 * es);
     L.off_vpos = o; o += r16(2 * es);
@@ -266,7 +267,7 @@ static void make_path_smem(PathSmem &S3, int nn, int m, int es) {
     S3.off_msg = o; o += 8 * es; o = r16(o);
     S3.off_vnmask = o; o += nn; o = r16(o);
     S3.off_error = o; o += nn; o = r16(o);
-    S3.off_dec = o; o += nn; o = r16(o);
+    S3.off_dec = o; o += std::max(nn, 2 * m); o = r16(o);      // select_vn actions (i8[nn]) / active-check list of bp_run (u16[m])
     S3.off_cnmask = o; o += m; o = r16(o);
     S3.off_cndeg = o; o += m; o = r16(o);
     S3.off_flip = o; o += m; o = r16(o);
@@ -305,14 +306,6 @@ static int setup_kernels(swd_decoder *d) {
     const int lcap = std::min(255, d->max_row_deg);
     const int es_slots = es + m;      // every row may carry one pad slot
     make_layout(d->L, nn, m, es_slots, lcap);
-    int capA = (int)((double)nn * d->nnz / n * 1.05) + 16;
-    capA = std::min(es_slots, ((capA + m / 2) + 7) & ~7);
-    if (const char *e = getenv("SWD_ES_TIER_A")) capA = std::min(es_slots, std::max(8, atoi(e)));
-    d->es_capA = capA;
-    make_layout(d->LsA, nn, m, capA, lcap);
-    make_layout(d->LsB, nn, m, es_slots, lcap);
-    make_path_smem(d->PS, nn, m, capA);
-    make_path_smem(d->PSB, nn, m, es_slots);
     // ---- K1
     d->T1 = std::min(256, std::max(64, r32up((n + 3) / 4)));
     if (const char *e = getenv("SWD_T1")) d->T1 = std::min(256, std::max(32, r32up(atoi(e))));
@@ -352,11 +345,40 @@ static int setup_kernels(swd_decoder *d) {
     // ---- K3
     d->T3 = std::max(32, std::max(r32up((nn + 3) / 4), r32up((m + SWD_CPT - 1) / SWD_CPT)));
     if (d->T3 > 1024) { set_err("new_n > 4096 unsupported"); return SWD_ERR_UNSUPPORTED; }
+    d->dmax = d->max_col_deg <= 6 ? 6 : (d->max_col_deg <= 8 ? 8 : 16);
+    d->path_fn = pick_path_kernel(d->dmax, d->T3);
+    // Tier A capacity: the largest that still allows the best occupancy, provided it covers the typical shortened
+    // graph (the nn most error-prone columns are lighter than average: ~0.8 x mean degree measured on BB windows;
+    // oversized shots fall to tier B, same kernel with the worst-case footprint, so this only affects speed).
+    auto path_smem = [&](int cap) {
+        SubLayout a; PathSmem b;
+        make_layout(a, nn, m, cap, lcap, false); make_path_smem(b, nn, m, cap);
+        return (size_t)a.blob_bytes + b.total;
+    };
+    const int typ = std::min(es_slots, (int)((double)nn * d->nnz / n * 0.85) + m / 2 + 16);
+    int max_occ_threads = 1;                                   // limit set by registers / threads alone
+    if ((st = occupancy(d->path_fn, d->T3, path_smem(8), &max_occ_threads))) return st;
+    max_occ_threads = std::max(1, max_occ_threads);
+    int capA = es_slots;
+    for (int occ = max_occ_threads; occ >= 1; occ--) {
+        const size_t budget = (size_t)233472 / occ - 1024;
+        if (path_smem(8) > budget) continue;
+        int lo = 8, hi = es_slots;
+        while (lo < hi) { const int mid = (lo + hi + 1) / 2; if (path_smem(mid) <= budget) lo = mid; else hi = mid - 1; }
+        const int cap = (lo == es_slots) ? lo : (lo & ~7);
+        if (cap >= typ) { capA = std::min(es_slots, cap); break; }
+    }
+    if (const char *e = getenv("SWD_ES_TIER_A")) capA = std::min(es_slots, std::max(8, atoi(e)));
+    d->es_capA = capA;
+    make_layout(d->LsA, nn, m, capA, lcap, false);
+    make_layout(d->LsB, nn, m, es_slots, lcap, false);
+    make_path_smem(d->PS, nn, m, capA);
+    make_path_smem(d->PSB, nn, m, es_slots);
+    if (getenv("SWD_DEBUG")) fprintf(stderr, "[swd] m=%d n=%d nn=%d es_slots=%d typ=%d capA=%d smemA=%zu smemB=%zu\n", m, n, nn, es_slots, typ, capA,
+                                     (size_t)d->LsA.blob_bytes + d->PS.total, (size_t)d->LsB.blob_bytes + d->PSB.total);
     const size_t smemB = (size_t)d->LsB.blob_bytes + d->PSB.total;
     if (smemB > 227 * 1024) { set_err("shortened graph does not fit in shared memory"); return SWD_ERR_UNSUPPORTED; }
     const size_t smemA = (size_t)d->LsA.blob_bytes + d->PS.total;
-    d->dmax = d->max_col_deg <= 6 ? 6 : (d->max_col_deg <= 8 ? 8 : 16);
-    d->path_fn = pick_path_kernel(d->dmax, d->T3);
     if ((st = occupancy(d->path_fn, d->T3, smemA, &occ))) return st;
     if (occ < 1) { set_err("path_kernel does not fit"); return SWD_ERR_UNSUPPORTED; }
     d->grid3 = d->num_sm * occ;

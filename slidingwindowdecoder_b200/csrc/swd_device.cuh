@@ -144,6 +144,7 @@ __device__ __forceinline__ void block_argmin(double &v, int &idx, double *red_d,
     if (lane == 0) { red_d[wid] = v; red_i[wid] = idx; }
     __syncthreads();
     double bv = red_d[0]; int bi = red_i[0];
+#pragma unroll 1
     for (int w = 1; w < nw; w++) {
         double ov = red_d[w]; int oi = red_i[w];
         if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
@@ -295,6 +296,7 @@ __device__ __forceinline__ int peel_warp(Ctx &c, int lane) {
 // warp computes the same value.
 __device__ __forceinline__ double pm_warp(const Ctx &c, int lane) {
     double pm = 0.0;
+#pragma unroll 1
     for (int base = 0; base < c.nn; base += 32) {
         int j = base + lane;
         u32 b = __ballot_sync(FULLMASK, j < c.nn && c.error[j] != 0);
@@ -307,17 +309,18 @@ __device__ __forceinline__ double pm_warp(const Ctx &c, int lane) {
 template <int VPT>
 __device__ __forceinline__ void init_msgs(Ctx &c) {
     const int T = blockDim.x, tid = threadIdx.x;
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < VPT; i++) {
         const int sl = own_slot(i, tid, T);
         if (sl < c.nn) {
             const int j = c.vperm[sl];
             const int e0 = c.voff[j], e1 = c.voff[j + 1];
             const double v = (c.vn_mask[j] < 0) ? c.prior[j] : dnan();
+#pragma unroll 1
             for (int e = e0; e < e1; e++) c.msg[c.vpos[e]] = v;
         }
     }
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < SWD_CPT; i++) {
         const int q = own_slot(i, tid, T);
         if (q < c.m) { const int p1 = c.coff[q + 1]; if (p1 > c.coff[q] && c.cvn[p1 - 1] == 0xffff) c.msg[p1 - 1] = dnan(); }
@@ -401,23 +404,52 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
                                       int *iters_done = nullptr) {
     const int T = blockDim.x, tid = threadIdx.x;
     const double fpos = c.factor, fneg = -c.factor;
+    // ---- active checks of this call, compacted in rank order (cn_mask does not change inside a call; an
+    //      inactive check has no undecided neighbour, so its parity / flip flags are never read).  The list
+    //      aliases `dec`, which is only live inside select_vn.
+    u16 *alist = (u16 *)c.dec;
+    int na = 0;
+    {
+        const int lane = tid & 31, wid = tid >> 5, nw = (T + 31) >> 5;
+        int *wcnt = (int *)c.red_d;                           // [SWD_CPT * nw] <= 128 ints = the 512 bytes of red_d
+        u32 bal[SWD_CPT];
+#pragma unroll
+        for (int i = 0; i < SWD_CPT; i++) {
+            const int q = i * T + tid;
+            const bool act = (q < c.m) && (c.cn_mask[c.cperm[q]] >= 0);
+            bal[i] = __ballot_sync(FULLMASK, act);
+            if (lane == 0) wcnt[i * nw + wid] = __popc(bal[i]);
+        }
+        __syncthreads();
+        int run = 0;
+#pragma unroll
+        for (int i = 0; i < SWD_CPT; i++) {
+            int off = run;
+#pragma unroll 1
+            for (int w = 0; w < nw; w++) { const int cw = wcnt[i * nw + w]; if (w < wid) off += cw; run += cw; }
+            if ((bal[i] >> lane) & 1u) alist[off + __popc(bal[i] & ((1u << lane) - 1u))] = (u16)(i * T + tid);
+        }
+        na = run;
+        __syncthreads();
+    }
     for (int it = 0; it <= num_iter; it++) {
         // ---- check pass (+ convergence test of the previous iteration)
         int mism = (it > 0) ? c.bad_rows : 0;
         const bool last = (it == num_iter);
 #pragma unroll 1
-        for (int i = 0; i < SWD_CPT; i++) {
-            const int q = own_slot(i, tid, T);
-            if (q >= c.m) continue;
+        for (int i = 0; i * T < na; i++) {
+            const int k = own_slot(i, tid, T);
+            if (k >= na) continue;
+            const int q = alist[k];
             const int r = c.cperm[q];
             const int cm = c.cn_mask[r];
             if (it > 0) {
-                const int f = (cm < 0) ? 0 : (c.upar[r] != (u32)cm);
+                const int f = (c.upar[r] != (u32)cm);
                 c.flip[r] = (u8)f;
                 mism |= f;
             }
             c.upar[r] = 0;
-            if (cm < 0 || last) continue;
+            if (last) continue;
             cn_iters++;
             { const int p0 = c.coff[q]; check_update(c, p0, c.coff[q + 1] - p0, cm, fpos, fneg); }
         }
@@ -439,8 +471,8 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
                 for (int k = 0; k < DMAX; k++) if (k < d) { pp[k] = c.vpos[e0 + k]; cc[k] = c.msg[pp[k]]; }
 #pragma unroll
                 for (int k = 0; k < DMAX; k++) if (k < d) { pre[k] = t; t += cc[k]; }
-                h[i][0] = (ring == 0) ? t : h[i][0]; h[i][1] = (ring == 1) ? t : h[i][1];
-                h[i][2] = (ring == 2) ? t : h[i][2]; h[i][3] = (ring == 3) ? t : h[i][3];
+                h[i][ring] = t;      // dynamic ring index: the history lives in (L1/L2-backed) local memory, written once per
+                                     // iteration and read once per call by select_vn - it does not occupy 32 registers
                 const int hard = (t <= 0.0);
                 c.error[j] = (i8)hard;
                 if (hard) {
@@ -479,6 +511,7 @@ __device__ __forceinline__ int select_vn(Ctx &c, const double (&h)[VPT][4], int 
                 const int e0 = c.voff[j], d = c.voff[j + 1] - e0;
                 if (d > 2) {
                     int nf = 0;
+#pragma unroll 1
                     for (int k = 0; k < d; k++) nf += c.flip[c.vrow[e0 + k]];
                     bool geC = true, geD = true, leA = true, neg = true; double sum = 0.0;
 #pragma unroll
@@ -516,6 +549,7 @@ __device__ __forceinline__ int select_vn(Ctx &c, const double (&h)[VPT][4], int 
             if (cm < 0) continue;
             int cnt = 0, par = 0, last = -1;
             const int p0 = c.coff[q], p1 = c.coff[q + 1];
+#pragma unroll 1
             for (int p = p0; p < p1; p++) {
                 const int j = c.cvn[p];
                 if (j == 0xffff) continue;
@@ -555,6 +589,7 @@ __device__ __forceinline__ int select_vn(Ctx &c, const double (&h)[VPT][4], int 
                 const int j = c.vperm[sl];
                 if (c.dec[j] >= 0) {
                     c.vn_mask[j] = c.dec[j]; c.error[j] = c.dec[j];
+#pragma unroll 1
                     for (int e = c.voff[j]; e < c.voff[j + 1]; e++) c.msg[c.vpos[e]] = dnan();
                 }
             }

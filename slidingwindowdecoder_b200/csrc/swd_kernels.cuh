@@ -340,6 +340,7 @@ __device__ __forceinline__ void record_result(Ctx &c, u8 *rec, int converged, co
     }
     u32 *bits = (u32 *)(rec + sizeof(RecHeader));
     const int nwords = (c.nn + 31) >> 5;
+#pragma unroll 1
     for (int w = wid; w < nwords; w += nw) {
         const int j = w * 32 + lane;
         u32 b = __ballot_sync(FULLMASK, j < c.nn && c.error[j] != 0);
@@ -435,7 +436,9 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
             const i8 *ncn = (const i8 *)(pnode + P.node_off_cn);
             const u8 *ndg = pnode + P.node_off_deg, *nfl = pnode + P.node_off_flip;
             const double *nh = (const double *)(pnode + P.node_off_hist);
+#pragma unroll 1
             for (int j = tid; j < c.nn; j += T) { c.vn_mask[j] = nvn[j]; c.error[j] = ner[j]; }
+#pragma unroll 1
             for (int r = tid; r < c.m; r += T) { c.cn_mask[r] = ncn[r]; c.cn_deg[r] = ndg[r]; c.flip[r] = nfl[r]; }
 #pragma unroll
             for (int i = 0; i < VPT; i++)
@@ -444,11 +447,15 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
             __syncthreads();
         } else {
         if (phase != 1) {
+#pragma unroll 1
             for (int j = tid; j < c.nn; j += T) { const i8 v = snap_vn[j]; c.vn_mask[j] = v; c.error[j] = v < 0 ? 0 : v; }
+#pragma unroll 1
             for (int r = tid; r < c.m; r += T) { c.cn_mask[r] = snap_cn[r]; c.cn_deg[r] = snap_deg[r]; c.flip[r] = 0; }
         } else {
             const i8 *svn = (const i8 *)(sh + 1); const i8 *scn = svn + c.nn; const u8 *sdg = (const u8 *)(scn + c.m);
+#pragma unroll 1
             for (int j = tid; j < c.nn; j += T) { const i8 v = svn[j]; c.vn_mask[j] = v; c.error[j] = v; }   // bpgd.cpp:541
+#pragma unroll 1
             for (int r = tid; r < c.m; r += T) { c.cn_mask[r] = scn[r]; c.cn_deg[r] = sdg[r]; c.flip[r] = 0; }
         }
         __syncthreads();
@@ -557,7 +564,9 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
                         if (do_guess && st_used < P.n_side) {
                             unsigned char *sp = ws.side + ((size_t)slot * P.n_side + st_used) * P.side_stride;
                             i8 *svn = (i8 *)(sp + sizeof(SideHeader)); i8 *scn = svn + c.nn; u8 *sdg = (u8 *)(scn + c.m);
+#pragma unroll 1
                             for (int j = tid; j < c.nn; j += T) svn[j] = c.vn_mask[j];
+#pragma unroll 1
                             for (int r = tid; r < c.m; r += T) { scn[r] = c.cn_mask[r]; sdg[r] = c.cn_deg[r]; }
                             if (tid == 0) { SideHeader *q = (SideHeader *)sp; q->vn = guess; q->value = 1 - favor; q->depth = depth + 1; q->valid = 1; }
                             st_used++;
@@ -566,7 +575,9 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
                     if (role == R_MAIN && depth >= P.T && depth < P.S) {                          // :651-664
                         unsigned char *sp = ws.side + ((size_t)slot * P.n_side + (depth - P.T)) * P.side_stride;
                         i8 *svn = (i8 *)(sp + sizeof(SideHeader)); i8 *scn = svn + c.nn; u8 *sdg = (u8 *)(scn + c.m);
+#pragma unroll 1
                         for (int j = tid; j < c.nn; j += T) svn[j] = c.vn_mask[j];
+#pragma unroll 1
                         for (int r = tid; r < c.m; r += T) { scn[r] = c.cn_mask[r]; sdg[r] = c.cn_deg[r]; }
                         if (tid == 0) { SideHeader *q = (SideHeader *)sp; q->vn = guess; q->value = 1 - favor; q->depth = depth + 1; q->valid = 1; }
                     }
@@ -574,7 +585,9 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
                         if (depth < P.T) {                                                        // :464-470
                             if ((path >> (P.T - 1 - depth)) & 1) { on_side = 1; c.A = 0; c.A_sum = -10; favor = 1 - favor; }
                         } else if (depth == P.T) {                                                // :476-484
+#pragma unroll 1
                             for (int j = tid; j < c.nn; j += T) bvn[j] = c.vn_mask[j];
+#pragma unroll 1
                             for (int r = tid; r < c.m; r += T) { bcn[r] = c.cn_mask[r]; bdeg[r] = c.cn_deg[r]; }
                             bvar = guess; bval = 1 - favor; saved = 1;
                         }
@@ -595,7 +608,9 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
                     if (q.depth > st_min_depth) continue;                                         // pyx:304
                     const i8 *svn = (const i8 *)(sp + sizeof(SideHeader)); const i8 *scn = svn + c.nn; const u8 *sdg = (const u8 *)(scn + c.m);
                     __syncthreads();
+#pragma unroll 1
                     for (int j = tid; j < c.nn; j += T) { const i8 v = svn[j]; c.vn_mask[j] = v; c.error[j] = v; }   // set_masks, bpgd.cpp:241-248
+#pragma unroll 1
                     for (int r = tid; r < c.m; r += T) { c.cn_mask[r] = scn[r]; c.cn_deg[r] = sdg[r]; }
                     __syncthreads();
                     init_msgs<VPT>(c);
@@ -609,7 +624,9 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
             }
             if (role == R_TREE && stage == 0 && saved) {                                          // :490-503
                 __syncthreads();
+#pragma unroll 1
                 for (int j = tid; j < c.nn; j += T) { const i8 v = bvn[j]; c.vn_mask[j] = v; c.error[j] = v; }
+#pragma unroll 1
                 for (int r = tid; r < c.m; r += T) { c.cn_mask[r] = bcn[r]; c.cn_deg[r] = bdeg[r]; }
                 __syncthreads();
                 init_msgs<VPT>(c);
@@ -625,8 +642,11 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
             u8 *ndg = nd + P.node_off_deg, *nfl = nd + P.node_off_flip;
             double *nm = (double *)(nd + P.node_off_msg), *nh = (double *)(nd + P.node_off_hist);
             __syncthreads();
+#pragma unroll 1
             for (int j = tid; j < c.nn; j += T) { nvn[j] = c.vn_mask[j]; ner[j] = c.error[j]; }
+#pragma unroll 1
             for (int r = tid; r < c.m; r += T) { ncn[r] = c.cn_mask[r]; ndg[r] = c.cn_deg[r]; nfl[r] = c.flip[r]; }
+#pragma unroll 1
             for (int p = tid; p < c.es; p += T) nm[p] = c.msg[p];
 #pragma unroll
             for (int i = 0; i < VPT; i++)

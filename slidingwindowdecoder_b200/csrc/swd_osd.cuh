@@ -73,7 +73,6 @@ post_bp_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, in
     c.upar = (u32 *)(st + S.off_upar);
     c.red_d = (double *)(st + S.off_red); c.red_i = (int *)(c.red_d + 64); c.misc = (int *)(st + S.off_misc);
     u64 *bar = (u64 *)(st + S.off_bar);
-    const u16 *col = (const u16 *)(blob + L.off_col);
     const i8 *snap_vn = (const i8 *)(blob + L.off_vnmask), *snap_cn = (const i8 *)(blob + L.off_cnmask);
     const u8 *snap_deg = blob + L.off_cndeg;
     c.A = 0; c.A_sum = 0; c.C = 0; c.D = 0;
@@ -107,6 +106,7 @@ post_bp_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, in
         mbar_wait(bar, mphase);
         mphase ^= 1;
         c.es = gh.es; c.bad_rows = gh.bad_rows;
+        const u16 *col = (const u16 *)(gblob + LG.off_col);                 // only in the global blob (not staged)
         for (int j = tid; j < c.nn; j += T) { const i8 v = snap_vn[j]; c.vn_mask[j] = v; c.error[j] = v < 0 ? 0 : v; }
         for (int r = tid; r < c.m; r += T) { c.cn_mask[r] = snap_cn[r]; c.cn_deg[r] = snap_deg[r]; c.flip[r] = 0; }
         __syncthreads();
