@@ -128,6 +128,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, 
                  : "memory");
 }
 
+// Shared-memory array bases are kept as opaque 32-bit shared-window addresses: the empty asm stops the compiler from
+// re-deriving them from kernel parameters at every access (LDC + IADD3 + the S2R-based window base, ~40 % of the
+// instructions of the min-sum loop before), so one register per hot array holds the base and accesses are LDS/STS [R+..].
+__device__ __forceinline__ u32 pin_u32(u32 x) { asm volatile("" : "+r"(x)); return x; }
+template <typename T>
+__device__ __forceinline__ T *pinned_smem(const void *p) { return (T *)__cvta_shared_to_generic((size_t)pin_u32(smem_u32(p))); }
+
 __device__ __forceinline__ double dnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
 // lexicographic (value, index) minimum across the CTA. Result broadcast to all threads.

@@ -357,16 +357,16 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
     unsigned char *st = smem + L.blob_bytes;
     Ctx c;
     c.m = L.m; c.nn = L.nn; c.factor = P.factor; c.low_error = P.low_error;
-    c.prior = (const double *)(blob + L.off_prior);
-    c.voff = (const u16 *)(blob + L.off_voff); c.coff = (const u16 *)(blob + L.off_coff);
+    c.prior = pinned_smem<const double>(blob + L.off_prior);
+    c.voff = pinned_smem<const u16>(blob + L.off_voff); c.coff = pinned_smem<const u16>(blob + L.off_coff);
     c.crank = (const u16 *)(blob + L.off_crank);
-    c.vrow = (const u16 *)(blob + L.off_vrow); c.vpos = (const u16 *)(blob + L.off_vpos); c.cvn = (const u16 *)(blob + L.off_cvn);
-    c.vperm = (const u16 *)(blob + L.off_vperm); c.cperm = (const u16 *)(blob + L.off_cperm);
+    c.vrow = pinned_smem<const u16>(blob + L.off_vrow); c.vpos = pinned_smem<const u16>(blob + L.off_vpos); c.cvn = (const u16 *)(blob + L.off_cvn);
+    c.vperm = pinned_smem<const u16>(blob + L.off_vperm); c.cperm = pinned_smem<const u16>(blob + L.off_cperm);
     c.synd = blob + L.off_synd;
-    c.msg = (double *)(st + S.off_msg);
-    c.vn_mask = (i8 *)(st + S.off_vnmask); c.error = (i8 *)(st + S.off_error); c.dec = (i8 *)(st + S.off_dec);
-    c.cn_mask = (i8 *)(st + S.off_cnmask); c.cn_deg = st + S.off_cndeg; c.flip = st + S.off_flip;
-    c.upar = (u32 *)(st + S.off_upar);
+    c.msg = pinned_smem<double>(st + S.off_msg);
+    c.vn_mask = pinned_smem<i8>(st + S.off_vnmask); c.error = pinned_smem<i8>(st + S.off_error); c.dec = pinned_smem<i8>(st + S.off_dec);
+    c.cn_mask = pinned_smem<i8>(st + S.off_cnmask); c.cn_deg = st + S.off_cndeg; c.flip = pinned_smem<u8>(st + S.off_flip);
+    c.upar = pinned_smem<u32>(st + S.off_upar);
     c.red_d = (double *)(st + S.off_red); c.red_i = (int *)(c.red_d + 64); c.misc = (int *)(st + S.off_misc);
     i8 *bvn = (i8 *)(st + S.off_bvn); i8 *bcn = (i8 *)(st + S.off_bcn); u8 *bdeg = st + S.off_bdeg;
     u64 *bar = (u64 *)(st + S.off_bar);

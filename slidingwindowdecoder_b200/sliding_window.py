@@ -114,14 +114,17 @@ class SlidingWindowDecoder:
                                                       counts.data_ptr(), stream), "count")
         return counts, torch.stack(unconv)
 
-    def decode_device(self, det, obs, return_corrections=False, window_events=None):
+    def decode_device(self, det, obs, return_corrections=False, window_events=None, streams=None):
         """det [B, num_det], obs [B, num_obs]: torch CUDA uint8 tensors, MODIFIED IN PLACE into the residual
         syndrome / residual observables.  Returns dict with device tensors:
-          counts uint64[2] = (flagged shots, failed shots), window_unconverged int64[num_win]."""
+          counts uint64[2] = (flagged shots, failed shots), window_unconverged int64[num_win].
+        streams: use fewer concurrent sub-batches than the decoder was built with (1 = plain sequential launches)."""
         torch = self.torch
         B = det.shape[0]
         total = torch.zeros((B, self.num_col), dtype=torch.uint8, device=det.device) if return_corrections else None
-        ns = self.nstreams if (window_events is None and B >= 2 * self.nstreams) else 1
+        ns = self.nstreams if streams is None else max(1, min(int(streams), self.nstreams))
+        if window_events is not None or B < 2 * ns:
+            ns = 1
         if ns == 1:
             counts, unconv = self._run_windows(det, obs, self.decoders, total, window_events)
         else:
