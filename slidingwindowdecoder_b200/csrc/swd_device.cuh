@@ -400,6 +400,28 @@ __device__ __forceinline__ void check_update(Ctx &c, int p0, int len, int cm, do
     }
 }
 
+// one variable-node update (bpgd.cpp:151-182) for a VN of degree d <= DM: returns the posterior, writes the hard
+// decision, the parity contributions and the new bit-to-check messages
+template <int DM>
+__device__ __forceinline__ double vn_update(Ctx &c, const int j, const int e0, const int d, const int dw) {
+    double cc[DM], pre[DM]; int pp[DM];
+    double t = c.prior[j];
+#pragma unroll
+    for (int k = 0; k < DM; k++) { if (k >= dw) break; if (k < d) { pp[k] = c.vpos[e0 + k]; cc[k] = c.msg[pp[k]]; } }
+#pragma unroll
+    for (int k = 0; k < DM; k++) { if (k >= dw) break; if (k < d) { pre[k] = t; t += cc[k]; } }
+    const int hard = (t <= 0.0);
+    c.error[j] = (i8)hard;
+    if (hard) {
+#pragma unroll 1
+        for (int k = 0; k < d; k++) atomicXor(&c.upar[c.vrow[e0 + k]], 1u);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = DM - 1; k >= 0; k--) if (k < dw) { if (k < d) { c.msg[pp[k]] = pre[k] + s; s += cc[k]; } }
+    return t;
+}
+
 // BPGD::min_sum_log (bpgd.cpp:97-197) on the shortened graph, whole CTA.
 // h[i][s]: posterior history of the VN owned as slot i, ring slot s = iteration % 4.
 // Two barriers per iteration: the H*error == syndrome test of iteration `it` (bpgd.cpp:185-194;
@@ -464,31 +486,19 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
             if (!__syncthreads_or(mism)) { if (iters_done) *iters_done = it; return 1; }
         } else __syncthreads();
         if (last) break;
-        // ---- variable pass: ordered prefix / suffix sums (bpgd.cpp:151-182); predicated straight-line code per slot
+        // ---- variable pass: ordered prefix / suffix sums (bpgd.cpp:151-182); predicated straight-line code per slot.
+        //      VNs are owned in degree order, so most warps only hold VNs of degree <= 3 and take the short body.
         const int ring = it & 3;
 #pragma unroll
         for (int i = 0; i < VPT; i++) {
             const int sl = own_slot(i, tid, T);
             int j = -1, e0 = 0, d = 0;
             if (sl < c.nn) { j = c.vperm[sl]; if (c.vn_mask[j] < 0) { e0 = c.voff[j]; d = c.voff[j + 1] - e0; } else j = -1; }
+            const int dw = __reduce_max_sync(FULLMASK, d);
             if (j >= 0) {
-                double cc[DMAX], pre[DMAX]; int pp[DMAX];
-                double t = c.prior[j];
-#pragma unroll
-                for (int k = 0; k < DMAX; k++) if (k < d) { pp[k] = c.vpos[e0 + k]; cc[k] = c.msg[pp[k]]; }
-#pragma unroll
-                for (int k = 0; k < DMAX; k++) if (k < d) { pre[k] = t; t += cc[k]; }
+                const double t = vn_update<DMAX>(c, j, e0, d, dw);     // dw: warp-uniform loop bound (VNs are owned in degree order)
                 h[i][ring] = t;      // dynamic ring index: the history lives in (L1/L2-backed) local memory, written once per
                                      // iteration and read once per call by select_vn - it does not occupy 32 registers
-                const int hard = (t <= 0.0);
-                c.error[j] = (i8)hard;
-                if (hard) {
-#pragma unroll 1
-                    for (int k = 0; k < d; k++) atomicXor(&c.upar[c.vrow[e0 + k]], 1u);
-                }
-                double s = 0.0;
-#pragma unroll
-                for (int k = DMAX - 1; k >= 0; k--) if (k < d) { c.msg[pp[k]] = pre[k] + s; s += cc[k]; }
                 edge_iters += d; vn_iters++;
             }
         }

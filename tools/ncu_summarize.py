@@ -53,15 +53,20 @@ def main():
 
     def g(r, k):
         return r[col[k]] if k in col else "NA"
+    dram_total = 0.0
     with open(prefix + "_launches.txt", "w") as f:
         f.write("# idx kernel duration_ms grid block regs smem_dyn_KB warp_inst issue_active_pct warps_active dram_rd_MB dram_wr_MB\n")
         for i, r in enumerate(data):
-            unit = rows[1][col["dram__bytes_read.sum"]]
-            sc = {"Gbyte": 1e3, "Mbyte": 1.0, "Kbyte": 1e-3, "byte": 1e-6}.get(unit, 1.0)
+            scs = {"Gbyte": 1e3, "Mbyte": 1.0, "Kbyte": 1e-3, "byte": 1e-6}
+            sc = scs.get(rows[1][col["dram__bytes_read.sum"]], 1.0)
+            scw = scs.get(rows[1][col["dram__bytes_write.sum"]], 1.0)
+            dram_total += (fnum(g(r, "dram__bytes_read.sum")) * sc + fnum(g(r, "dram__bytes_write.sum")) * scw) * 1e6
             f.write(f"{i} {g(r, 'Kernel Name')[:40]} {g(r, 'gpu__time_duration.sum')} {g(r, 'launch__grid_size')} {g(r, 'launch__block_size')} "
                     f"{g(r, 'launch__registers_per_thread')} {g(r, 'launch__shared_mem_per_block_dynamic')} {g(r, 'smsp__inst_executed.sum')} "
                     f"{g(r, 'smsp__issue_active.avg.pct_of_peak_sustained_active')} {g(r, 'sm__warps_active.avg.per_cycle_active')} "
-                    f"{fnum(g(r, 'dram__bytes_read.sum')) * sc:.2f} {fnum(g(r, 'dram__bytes_write.sum')) * sc:.2f}\n")
+                    f"{fnum(g(r, 'dram__bytes_read.sum')) * sc:.2f} {fnum(g(r, 'dram__bytes_write.sum')) * scw:.2f}\n")
+    with open(prefix + "_launches.txt", "a") as f:
+        f.write(f"# DRAM read+write over the {len(data)} launches: {dram_total:.0f} bytes = {dram_total / max(1, len(data)):.0f} per launch\n")
     if launch is None:
         launch = max(range(len(data)), key=lambda i: fnum(g(data[i], "gpu__time_duration.sum")))
     r = data[launch]
