@@ -182,20 +182,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
-def gpu_sample(torch, plan, shots, seed, dev):
-    """Independent Bernoulli per DEM column on the device (what CompiledDemSampler draws, guessing.py:129-130)."""
-    g = torch.Generator(device=dev)
-    g.manual_seed(seed)
-    pri = torch.from_numpy(plan.priors).to(dev, torch.float32)
-    chkT = torch.from_numpy(np.asarray(plan.chk.T.todense(), dtype=np.float32)).to(dev)
-    obsT = torch.from_numpy(np.asarray(plan.obs.T.todense(), dtype=np.float32)).to(dev)
-    dets, obss = [], []
-    for s0 in range(0, shots, 8192):
-        nb = min(8192, shots - s0)
-        err = (torch.rand((nb, pri.numel()), generator=g, device=dev) < pri).to(torch.float32)
-        dets.append(torch.remainder(err @ chkT, 2).to(torch.uint8))
-        obss.append(torch.remainder(err @ obsT, 2).to(torch.uint8))
-    return torch.cat(dets), torch.cat(obss)
+def gpu_sample(swd, shots, seed):
+    """Independent Bernoulli per DEM column drawn on the device (what CompiledDemSampler draws, guessing.py:129-130):
+    the repository's own Philox sampler kernel (swd_window_sample), bit-identical to oracle/philox.py."""
+    return swd.sample_device(shots, seed=seed)
 
 
 def run_ours(args):
@@ -214,7 +204,7 @@ def run_ours(args):
     B, K, W = args.batch, args.steps, args.warmup
     nsteps = K + W
     torch.backends.cuda.matmul.allow_tf32 = False
-    det_all, obs_all = gpu_sample(torch, plan, B * nsteps, 1234 + rank, dev)
+    det_all, obs_all = gpu_sample(swd, B * nsteps, 1234 + rank)
     det_all = det_all.view(nsteps, B, -1); obs_all = obs_all.view(nsteps, B, -1)
     h_det = torch.empty(det_all.shape, dtype=torch.uint8, pin_memory=True); h_det.copy_(det_all)
     h_obs = torch.empty(obs_all.shape, dtype=torch.uint8, pin_memory=True); h_obs.copy_(obs_all)
@@ -356,7 +346,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD_NAME, "shots_per_step_per_gpu": B, "decoder": "bpgdg_decoder(max_iter=8, multi_thread=True, defaults)",
                    "streams": args.streams,
-                   "inputs": "DEM samples (independent Bernoulli per column); distinct batch per step, "
+                   "inputs": "DEM samples drawn on the device (Philox, independent Bernoulli per column); distinct batch per step, "
                              f"{(B * (det_all.shape[2] + obs_all.shape[2]) * nsteps) >> 20} MiB of syndromes in total (> L2), no L2 flush"},
         "e2e": {"value": round(e2e, 1), "unit": "shots/s", "h2d_bytes_per_step": int(B * (det_all.shape[2] + obs_all.shape[2])),
                 "d2h_bytes_per_step": 16, "ms_per_step": round(ms_e2e / K, 3)},

@@ -148,6 +148,14 @@ int  swd_window_commit(swd_window *w, const uint8_t *d_corr, int64_t B, int n_wi
 int  swd_window_count_failures(swd_window *w, const uint8_t *d_det, const uint8_t *d_obs, int64_t B,
                                unsigned long long *d_out2, void *stream);
 
+/* DEM sampling on the device - what CompiledDemSampler.sample draws in the reference's drivers (guessing.py:129-130):
+ * one independent Bernoulli(priors[c]) per DEM column, det = chk . e, obs = obs_mat . e (mod 2).  Philox4x32-10 keyed by
+ * `seed`, counter = (shot_offset + b, column block): shot b of a call with offset o equals shot 0 of a call with offset o + b.
+ * d_err (optional, [B, num_col]) receives the sampled error vectors. */
+int  swd_window_set_priors(swd_window *w, const double *priors /* host, [num_col] */);
+int  swd_window_sample(swd_window *w, uint64_t seed, int64_t shot_offset, int64_t B, uint8_t *d_det, uint8_t *d_obs,
+                       uint8_t *d_err, void *stream);
+
 const char *swd_strerror(int status);
 const char *swd_last_error(void);
 const char *swd_version(void);

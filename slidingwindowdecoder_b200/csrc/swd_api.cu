@@ -619,6 +619,7 @@ extern "C" int swd_new_n(swd_decoder *d) { return d ? d->nn : -1; }
 struct swd_window {
     int device, num_det, num_col, num_obs;
     int *chk_cp = nullptr, *chk_ri = nullptr, *obs_cp = nullptr, *obs_ri = nullptr;
+    u32 *thr = nullptr;          // floor(prior * 2^32) per DEM column (set by swd_window_set_priors)
 };
 
 extern "C" int swd_window_create(int device, int num_det, int num_col, const int32_t *chk_cp, const int32_t *chk_ri, int num_obs,
@@ -646,7 +647,37 @@ extern "C" void swd_window_destroy(swd_window *w) {
     if (w->chk_ri) cudaFree(w->chk_ri);
     if (w->obs_cp) cudaFree(w->obs_cp);
     if (w->obs_ri) cudaFree(w->obs_ri);
+    if (w->thr) cudaFree(w->thr);
     delete w;
+}
+extern "C" int swd_window_set_priors(swd_window *w, const double *priors) {
+    if (!w || !priors) { set_err("swd_window_set_priors: bad argument"); return SWD_ERR_INVALID; }
+    std::vector<u32> t(w->num_col);
+    for (int c = 0; c < w->num_col; c++) {
+        const double p = priors[c];
+        if (!(p >= 0.0 && p <= 1.0)) { set_err("swd_window_set_priors: prior outside [0, 1]"); return SWD_ERR_INVALID; }
+        const double x = p * 4294967296.0;
+        t[c] = x >= 4294967295.0 ? 0xffffffffu : (u32)x;
+    }
+    CK(cudaSetDevice(w->device));
+    if (w->thr) { cudaFree(w->thr); w->thr = nullptr; }
+    return upload(t, (void **)&w->thr);
+}
+extern "C" int swd_window_sample(swd_window *w, uint64_t seed, int64_t shot_offset, int64_t B, uint8_t *d_det, uint8_t *d_obs,
+                                 uint8_t *d_err, void *stream) {
+    if (!w || !d_det || B < 0 || shot_offset < 0 || (w->num_obs > 0 && !d_obs)) { set_err("swd_window_sample: bad argument"); return SWD_ERR_INVALID; }
+    if (!w->thr) { set_err("swd_window_sample: call swd_window_set_priors first"); return SWD_ERR_INVALID; }
+    if (B == 0) return SWD_OK;
+    CK(cudaSetDevice(w->device));
+    const int wpb = 8;
+    const size_t smem = (size_t)wpb * (((w->num_det + 31) >> 5) + ((w->num_obs + 31) >> 5)) * sizeof(u32);
+    if (smem > 200 * 1024) { set_err("swd_window_sample: too many detectors for the shared-memory parity words"); return SWD_ERR_UNSUPPORTED; }
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(window_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    window_sample_kernel<<<(unsigned)std::min<long long>((B + wpb - 1) / wpb, 148 * 16), wpb * 32, smem, (cudaStream_t)stream>>>(
+        w->thr, w->num_col, w->chk_cp, w->chk_ri, w->num_det, w->obs_cp, w->obs_ri, w->num_obs, (unsigned long long)seed,
+        (long long)shot_offset, (long long)B, d_det, d_obs, d_err);
+    CK(cudaGetLastError());
+    return SWD_OK;
 }
 extern "C" int swd_window_extract(swd_window *w, const uint8_t *d_det, int64_t B, int row0, int m, uint8_t *d_synd, void *stream) {
     if (!w || !d_det || !d_synd || B < 0 || row0 < 0 || m <= 0 || row0 + m > w->num_det) { set_err("swd_window_extract: bad argument"); return SWD_ERR_INVALID; }

@@ -48,3 +48,58 @@ __global__ void window_count_kernel(const u8 *__restrict__ det, int num_det, con
     }
     if (lane == 0) { if (nflag) atomicAdd(&out2[0], nflag); if (nfail) atomicAdd(&out2[1], nfail); }
 }
+
+// ----------------------------------------------------------------------------------------------
+// DEM sampling on the device: what stim's CompiledDemSampler.sample draws (guessing.py:129-130,
+// build_circuit.py:271-288) - an independent Bernoulli(prior[c]) per DEM column, det = chk . e,
+// obs = obs_mat . e (mod 2) - so that large runs never touch the host.
+// Counter-based generator: Philox4x32-10 keyed by the seed, counter = (shot, column block), four
+// columns per call; a column fires when its 32-bit draw is below floor(p * 2^32).  One warp per
+// shot; detector / observable parities are accumulated in shared-memory bit words.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1, u32 (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const u32 hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const u32 hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const u32 n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void window_sample_kernel(const u32 *__restrict__ thr, int num_col, const int *__restrict__ chk_cp, const int *__restrict__ chk_ri,
+                                     int num_det, const int *__restrict__ obs_cp, const int *__restrict__ obs_ri, int num_obs,
+                                     unsigned long long seed, long long shot0, long long B, u8 *__restrict__ det, u8 *__restrict__ obs,
+                                     u8 *__restrict__ err) {
+    extern __shared__ u32 s_bits[];                           // per warp: ceil(num_det/32) + ceil(num_obs/32) words
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int wd = (num_det + 31) >> 5, wo = (num_obs + 31) >> 5;
+    u32 *dbits = s_bits + (size_t)wid * (wd + wo), *obits = dbits + wd;
+    const int nblk = (num_col + 3) >> 2;
+    for (long long b = (long long)blockIdx.x * wpb + wid; b < B; b += (long long)gridDim.x * wpb) {
+        for (int i = lane; i < wd + wo; i += 32) dbits[i] = 0;
+        __syncwarp();
+        const unsigned long long shot = (unsigned long long)(shot0 + b);
+        for (int blk = lane; blk < nblk; blk += 32) {
+            u32 r[4];
+            philox4x32_10((u32)blk, 0u, (u32)shot, (u32)(shot >> 32), (u32)seed, (u32)(seed >> 32), r);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int c = blk * 4 + q;
+                if (c >= num_col) break;
+                const bool fire = r[q] < thr[c];
+                if (err) err[b * num_col + c] = (u8)fire;
+                if (fire) {
+                    for (int e = chk_cp[c]; e < chk_cp[c + 1]; e++) { const int row = chk_ri[e]; atomicXor(&dbits[row >> 5], 1u << (row & 31)); }
+                    if (num_obs > 0) for (int e = obs_cp[c]; e < obs_cp[c + 1]; e++) { const int row = obs_ri[e]; atomicXor(&obits[row >> 5], 1u << (row & 31)); }
+                }
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < num_det; i += 32) det[b * num_det + i] = (u8)((dbits[i >> 5] >> (i & 31)) & 1u);
+        if (obs) for (int i = lane; i < num_obs; i += 32) obs[b * num_obs + i] = (u8)((obits[i >> 5] >> (i & 31)) & 1u);
+        __syncwarp();
+    }
+}

@@ -29,7 +29,8 @@ class SlidingWindowDecoder:
     """Holds one decoder per distinct window matrix (the reference rebuilds one per window,
     guessing.py:160-174) and the device-side window bookkeeping."""
 
-    def __init__(self, plan: WindowPlan, decoder="gdg", device=0, last_window_kwargs=None, streams=1, **decoder_kwargs):
+    def __init__(self, plan: WindowPlan, decoder="gdg", device=0, last_window_kwargs=None, streams=1,
+                 last_window_osd=None, **decoder_kwargs):
         """streams > 1: every batch is split into that many sub-batches which run the window loop on their own CUDA
         streams with their own decoder workspaces, so that one sub-batch's kernel tails (a few long branch paths
         finishing) are filled by the next sub-batch's work.  Results do not depend on `streams`."""
@@ -73,12 +74,43 @@ class SlidingWindowDecoder:
             self.decoder_sets.append(decs)
         self.decoders = self.decoder_sets[0]
         self._side_streams = None
+        # guessing.py:149-158,229-236: the GDG driver decodes the LAST window a second time with BP + OSD-CS
+        # (ldpc.BpOsdDecoder there, this repository's BpOsdDecoder facade here) and reports a second set of counts.
+        # last_window_osd = True or a dict of BpOsdDecoder kwargs (defaults: the reference's max_iter=200, OSD_CS 10).
+        self.last_osd = None
+        if last_window_osd:
+            from .decoders import BpOsdDecoder
+            kw = dict(max_iter=200, bp_method="minimum_sum", ms_scaling_factor=1.0, osd_method="OSD_CS", osd_order=10)
+            if isinstance(last_window_osd, dict):
+                kw.update(last_window_osd)
+            w = plan.windows[-1]
+            self.last_osd = [BpOsdDecoder(w.mat, channel_probs=list(w.prior), device=self.device, **kw) for _ in range(self.nstreams)]
 
     def __del__(self):
         w = getattr(self, "_win", None)
         if w is not None and w.value:
             self.lib.swd_window_destroy(w)
             self._win = C.c_void_p()
+
+    def sample_device(self, shots, seed=0, shot_offset=0, return_errors=False):
+        """Draw `shots` DEM samples on the device (Philox, one Bernoulli per DEM column; the stand-in for
+        `dem.compile_sampler().sample(shots)` of guessing.py:129-130).  -> (det [shots, num_det], obs [shots, num_obs]
+        [, err [shots, num_col]]) as torch CUDA uint8 tensors.  Reproducible: shot s of the stream depends only on
+        (seed, shot_offset + s)."""
+        torch = self.torch
+        dev = torch.device("cuda", self.device)
+        if not getattr(self, "_priors_set", False):
+            pri = np.ascontiguousarray(self.plan.priors, dtype=np.float64)
+            _lib.check(self.lib.swd_window_set_priors(self._win, pri.ctypes.data_as(C.POINTER(C.c_double))), "set_priors")
+            self._priors_set = True
+        det = torch.empty((shots, self.num_det), dtype=torch.uint8, device=dev)
+        obs = torch.empty((shots, self.num_obs), dtype=torch.uint8, device=dev)
+        err = torch.empty((shots, self.num_col), dtype=torch.uint8, device=dev) if return_errors else None
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(self.lib.swd_window_sample(self._win, int(seed), int(shot_offset), int(shots), det.data_ptr(),
+                                              obs.data_ptr() if self.num_obs else None, err.data_ptr() if return_errors else None,
+                                              stream), "sample")
+        return (det, obs, err) if return_errors else (det, obs)
 
     def unique_decoders(self):
         seen, out = set(), []
@@ -88,16 +120,26 @@ class SlidingWindowDecoder:
                     seen.add(id(d)); out.append(d)
         return out
 
-    def _run_windows(self, det, obs, decs, total, window_events):
+    def _run_windows(self, det, obs, decs, total, window_events, osd_dec=None):
         """The window loop for one (sub-)batch on the current stream; det / obs are updated in place."""
         torch = self.torch
         B = det.shape[0]
         stream = C.c_void_p(torch.cuda.current_stream(det.device).cuda_stream)
         unconv = []
+        counts_osd = None
         for w, dec in zip(self.plan.windows, decs):
             m = w.row1 - w.row0
             synd = torch.empty((B, m), dtype=torch.uint8, device=det.device)
             _lib.check(self.lib.swd_window_extract(self._win, det.data_ptr(), B, w.row0, m, synd.data_ptr(), stream), "extract")
+            if w.last and osd_dec is not None:
+                # second decode of the last window with BP + OSD on the same residual syndrome (guessing.py:229-236)
+                det2, obs2 = det.clone(), obs.clone()
+                corr2, _ = osd_dec.decode_batch(synd)
+                _lib.check(self.lib.swd_window_commit(self._win, corr2.data_ptr(), B, corr2.shape[1], w.col0, w.ncommit, det2.data_ptr(),
+                                                      obs2.data_ptr() if self.num_obs else None, stream), "commit")
+                counts_osd = torch.zeros(2, dtype=torch.int64, device=det.device)
+                _lib.check(self.lib.swd_window_count_failures(self._win, det2.data_ptr(), obs2.data_ptr() if self.num_obs else None, B,
+                                                              counts_osd.data_ptr(), stream), "count")
             if window_events is not None:
                 window_events[w.index][0].record()
             corr, conv = dec.decode_batch(synd)
@@ -112,7 +154,7 @@ class SlidingWindowDecoder:
         counts = torch.zeros(2, dtype=torch.int64, device=det.device)
         _lib.check(self.lib.swd_window_count_failures(self._win, det.data_ptr(), obs.data_ptr() if self.num_obs else None, B,
                                                       counts.data_ptr(), stream), "count")
-        return counts, torch.stack(unconv)
+        return counts, torch.stack(unconv), counts_osd
 
     def decode_device(self, det, obs, return_corrections=False, window_events=None, streams=None):
         """det [B, num_det], obs [B, num_obs]: torch CUDA uint8 tensors, MODIFIED IN PLACE into the residual
@@ -126,7 +168,8 @@ class SlidingWindowDecoder:
         if window_events is not None or B < 2 * ns:
             ns = 1
         if ns == 1:
-            counts, unconv = self._run_windows(det, obs, self.decoders, total, window_events)
+            counts, unconv, counts_osd = self._run_windows(det, obs, self.decoders, total, window_events,
+                                                           self.last_osd[0] if self.last_osd else None)
         else:
             if self._side_streams is None:
                 self._side_streams = [torch.cuda.Stream(device=det.device) for _ in range(self.nstreams)]
@@ -139,7 +182,8 @@ class SlidingWindowDecoder:
                 lo, hi = bounds[i], bounds[i + 1]
                 with torch.cuda.stream(st):
                     parts.append(self._run_windows(det[lo:hi], obs[lo:hi], self.decoder_sets[i],
-                                                   None if total is None else total[lo:hi], None))
+                                                   None if total is None else total[lo:hi], None,
+                                                   self.last_osd[i] if self.last_osd else None))
                 for t in (det, obs, total):
                     if t is not None:
                         t.record_stream(st)
@@ -147,7 +191,10 @@ class SlidingWindowDecoder:
                 cur.wait_stream(st)
             counts = sum(p[0] for p in parts)
             unconv = sum(p[1] for p in parts)
+            counts_osd = sum(p[2] for p in parts) if self.last_osd else None
         out = dict(counts=counts, window_unconverged=unconv)
+        if counts_osd is not None:
+            out["counts_last_window_osd"] = counts_osd      # (flagged, failed) when the last window is decoded by BP + OSD
         if return_corrections:
             out["total_e_hat"] = total
         return out
@@ -162,6 +209,9 @@ class SlidingWindowDecoder:
         counts = out["counts"].cpu().numpy()
         res = dict(shots=int(det.shape[0]), flagged=int(counts[0]), failed=int(counts[1]),
                    window_unconverged=out["window_unconverged"].cpu().numpy().tolist())
+        if "counts_last_window_osd" in out:
+            c2 = out["counts_last_window_osd"].cpu().numpy()
+            res["flagged_last_window_osd"], res["failed_last_window_osd"] = int(c2[0]), int(c2[1])
         if return_corrections:
             res["total_e_hat"] = out["total_e_hat"].cpu().numpy()
         return res

@@ -308,3 +308,71 @@ def test_bposd_facade_matches_osd_window_semantics(oracle_mod):
         assert conv[i] == r["converge"] and np.array_equal(corr[i], r["dec"].astype(np.uint8)), i
     H = g["mat"].toarray().astype(np.int64)
     assert not ((corr.astype(np.int64) @ H.T + synd) % 2).any()
+
+
+def test_device_dem_sampler_matches_numpy_restatement():
+    """swd_window_sample (Philox4x32-10, one Bernoulli per DEM column) against oracle/philox.py: bit-exact errors,
+    detectors and observables; the stream is a pure function of (seed, absolute shot index)."""
+    import torch
+    from slidingwindowdecoder_b200.codes import bb_code
+    from slidingwindowdecoder_b200.dem import bb_memory_circuit, detector_error_model, dem_to_check_matrices
+    from slidingwindowdecoder_b200.windows import build_windows
+    from slidingwindowdecoder_b200.sliding_window import SlidingWindowDecoder
+    from oracle.philox import sample_dem
+    code, A, B = bb_code(72)
+    chk, obs, pri = dem_to_check_matrices(detector_error_model(bb_memory_circuit(code, A, B, 0.003, 6)))
+    plan = build_windows(chk, obs, pri, code.N, W=3, F=1, method=1)
+    swd = SlidingWindowDecoder(plan, decoder="gdg", max_iter=8, multi_thread=True)
+    det, ob, err = swd.sample_device(700, seed=(7 << 32) + 3, shot_offset=12345, return_errors=True)
+    rdet, rob, rerr = sample_dem(plan.chk, plan.obs, plan.priors, 700, seed=(7 << 32) + 3, shot_offset=12345)
+    assert np.array_equal(err.cpu().numpy(), rerr)
+    assert np.array_equal(det.cpu().numpy(), rdet)
+    assert np.array_equal(ob.cpu().numpy(), rob)
+    det2, ob2 = swd.sample_device(300, seed=(7 << 32) + 3, shot_offset=12345 + 400)
+    assert torch.equal(det2, det[400:]) and torch.equal(ob2, ob[400:])
+    det3, _ = swd.sample_device(300, seed=8, shot_offset=12345 + 400)
+    assert not torch.equal(det3, det2)
+    # the sampled batch decodes like any other input
+    res = swd.decode_device(det.clone(), ob.clone())
+    assert int(res["counts"][1]) <= 700
+
+
+def test_last_window_bposd_redecode_matches_reference_loop(oracle_mod):
+    """guessing.py:149-158,229-236: after the GDG pass the last window is decoded again with BP(200) + OSD-CS10 on the same
+    residual syndrome and a second pair of counts is reported.  Checked against the same loop run with the oracle
+    (osd_window semantics with new_n = n and no second BP stage, as the BpOsdDecoder facade defines them)."""
+    from slidingwindowdecoder_b200.codes import bb_code
+    from slidingwindowdecoder_b200.dem import bb_memory_circuit, detector_error_model, dem_to_check_matrices
+    from slidingwindowdecoder_b200.windows import build_windows
+    from slidingwindowdecoder_b200.sliding_window import SlidingWindowDecoder, sample_dem
+    code, A, B = bb_code(72)
+    chk, obs, pri = dem_to_check_matrices(detector_error_model(bb_memory_circuit(code, A, B, 0.004, 6)))
+    plan = build_windows(chk, obs, pri, code.N, W=3, F=1, method=1)
+    det, ob, _ = sample_dem(plan.chk, plan.obs, plan.priors, 600, np.random.default_rng(21))
+    kw = dict(max_iter=8, multi_thread=True)
+    for streams in (1, 2):
+        swd = SlidingWindowDecoder(plan, decoder="gdg", last_window_osd=True, streams=streams, **kw)
+        res = swd.decode(det, ob)
+        oracles = {}
+        state = {}
+
+        def decode_window(w, synd):
+            if w.index not in oracles:
+                oracles[w.index] = oracle_mod.Oracle(w.mat, w.prior)
+            if w.last:
+                state["synd"] = np.array(synd, dtype=np.uint8)
+            d, c, _, _ = oracles[w.index].bpgdg_batch(synd, **kw)
+            return d, c
+
+        ref = oracle_mod.sliding_window_reference(plan, det, ob, decode_window)
+        assert res["flagged"] == int(ref["flagged"].sum()) and res["failed"] == int(ref["failed"].sum())
+        w = plan.windows[-1]
+        d2, _, _, _ = oracles[w.index].osd_window_batch(state["synd"], pre_max_iter=200, post_max_iter=0, new_n=w.mat.shape[1],
+                                                        osd_method="osd_cs", osd_order=10)
+        total = ref["total_e_hat"].copy()
+        total[:, w.col0:w.col0 + w.ncommit] = d2[:, :w.ncommit]
+        chkd = np.asarray(plan.chk.todense()).astype(np.int64); obd = np.asarray(plan.obs.todense()).astype(np.int64)
+        flagged = ((det.astype(np.int64) + total @ chkd.T) % 2).any(axis=1)
+        logical = ((ob.astype(np.int64) + total @ obd.T) % 2).any(axis=1)
+        assert res["flagged_last_window_osd"] == int(flagged.sum())
+        assert res["failed_last_window_osd"] == int(np.logical_or(flagged, logical).sum())

@@ -76,6 +76,28 @@ def test_dem_sampling_consistency(dem144):
     assert np.array_equal(det, np.asarray((chk @ err.T.astype(np.int64)).T % 2).astype(np.uint8))
 
 
+def test_philox_known_answers_and_sampler_restatement(dem144):
+    """Random123 kat_vectors for philox4x32-10 pin the generator of the device DEM sampler; the numpy restatement
+    of the sampler is self-consistent (det = chk . err) and a pure function of (seed, absolute shot index)."""
+    from oracle.philox import philox4x32_10, sample_dem, thresholds
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, exp in kat:
+        got = philox4x32_10(*[np.uint32(x) for x in ctr], *key)
+        assert tuple(int(x) for x in got) == exp
+    code, chk, obs, pri = dem144
+    det, ob, err = sample_dem(chk, obs, pri, 64, seed=5, shot_offset=100)
+    assert np.array_equal(det, np.asarray((chk @ err.T.astype(np.int64)).T % 2).astype(np.uint8))
+    det2, ob2, err2 = sample_dem(chk, obs, pri, 32, seed=5, shot_offset=132)
+    assert np.array_equal(err[32:], err2) and np.array_equal(det[32:], det2) and np.array_equal(ob[32:], ob2)
+    assert thresholds([0.0, 1.0, 0.5])[1] == 0xFFFFFFFF and thresholds([0.0, 1.0, 0.5])[2] == 0x80000000
+    # error weight is statistically what the priors say (5 sigma)
+    _, _, e = sample_dem(chk, obs, pri, 4000, seed=9)
+    mean, sd = pri.sum(), np.sqrt((pri * (1 - pri)).sum() / 4000)
+    assert abs(e.sum(axis=1).mean() - mean) < 5 * sd
+
+
 def test_bb_codes():
     from slidingwindowdecoder_b200.codes import bb_code, gf2_rank
     for N, K in ((72, 12), (144, 12)):

@@ -25,7 +25,7 @@ def worker(batch, steps, env_note):
     plan = bench.build_plan()
     swd = SlidingWindowDecoder(plan, decoder="gdg", device=0, streams=int(os.environ.get("AB_STREAMS", "1")), **bench.GDG_KW)
     nsteps = steps + 2
-    det_all, obs_all = bench.gpu_sample(torch, plan, batch * nsteps, 1234, dev)
+    det_all, obs_all = bench.gpu_sample(swd, batch * nsteps, 1234)
     det_all = det_all.view(nsteps, batch, -1); obs_all = obs_all.view(nsteps, batch, -1)
     out = swd.decode_device(det_all[0].clone(), obs_all[0].clone(), return_corrections=True)
     torch.cuda.synchronize()
