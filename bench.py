@@ -23,30 +23,52 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(N=144, p=0.003, rounds=12, W=3, F=1, method=1)
-GDG_KW = dict(max_iter=8, max_iter_per_step=6, max_step=25, max_tree_depth=3, max_side_depth=10,
-              max_tree_branch_step=10, max_side_branch_step=10, multi_thread=True, low_error_mode=False)
-WORKLOAD_NAME = "[[144,12,12]] circuit-level p=0.003, 12 rounds, sliding window W=3 F=1 (11 windows), GDG per window"
+WORKLOADS = {
+    # BASELINE.json configs[2] - the configuration the metric is quoted on (default)
+    "c3_gdg": dict(N=144, p=0.003, rounds=12, W=3, F=1, method=1, decoder="gdg",
+                   kw=dict(max_iter=8, max_iter_per_step=6, max_step=25, max_tree_depth=3, max_side_depth=10,
+                           max_tree_branch_step=10, max_side_branch_step=10, multi_thread=True, low_error_mode=False),
+                   name="[[144,12,12]] circuit-level p=0.003, 12 rounds, sliding window W=3 F=1 (11 windows), GDG per window",
+                   decoder_name="bpgdg_decoder(max_iter=8, multi_thread=True, defaults)"),
+    # configs[1]: BP + OSD-CS10 per window (osd_window, the reference's own BP+OSD)
+    "c2_osd": dict(N=72, p=0.003, rounds=6, W=3, F=1, method=1, decoder="osd",
+                   kw=dict(pre_max_iter=8, post_max_iter=200, osd_method="osd_cs", osd_order=10),
+                   name="[[72,12,6]] circuit-level p=0.003, 6 rounds, sliding window W=3 F=1 (5 windows), BP+OSD-CS10 per window",
+                   decoder_name="osd_window(pre_max_iter=8, post_max_iter=200, osd_cs, order 10)"),
+    # configs[3]: large windows (576 x 4896), BP + OSD
+    "c4_osd": dict(N=288, p=0.003, rounds=18, W=4, F=1, method=1, decoder="osd",
+                   kw=dict(pre_max_iter=8, post_max_iter=200, osd_method="osd_cs", osd_order=10),
+                   name="[[288,12,18]] circuit-level p=0.003, 18 rounds, sliding window W=4 F=1 (16 windows), BP+OSD-CS10 per window",
+                   decoder_name="osd_window(pre_max_iter=8, post_max_iter=200, osd_cs, order 10)"),
+}
+WL = WORKLOADS["c3_gdg"]
+METRIC = {"gdg": "decoded shots/sec (sliding-window GDG)", "osd": "decoded shots/sec (sliding-window BP+OSD)"}
+
+
+def select_workload(key):
+    global WL
+    WL = WORKLOADS[key]
 
 
 def build_plan():
     from slidingwindowdecoder_b200.codes import bb_code
     from slidingwindowdecoder_b200.dem import bb_memory_circuit, detector_error_model, dem_to_check_matrices
     from slidingwindowdecoder_b200.windows import build_windows
-    code, A, B = bb_code(WORKLOAD["N"])
-    circ = bb_memory_circuit(code, A, B, WORKLOAD["p"], WORKLOAD["rounds"], z_basis=True)
+    code, A, B = bb_code(WL["N"])
+    circ = bb_memory_circuit(code, A, B, WL["p"], WL["rounds"], z_basis=True)
     chk, obs, pri = dem_to_check_matrices(detector_error_model(circ))
-    return build_windows(chk, obs, pri, code.N, W=WORKLOAD["W"], F=WORKLOAD["F"], method=WORKLOAD["method"])
+    return build_windows(chk, obs, pri, code.N, W=WL["W"], F=WL["F"], method=WL["method"])
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
 _CPU = {}
 
 
-def _cpu_init(plan_blob, use_ref=False):
+def _cpu_init(plan_blob, use_ref=False, wl_key="c3_gdg"):
     """use_ref: decode with oracle/_ref (the reference's own bpgd.cpp, 15 std::threads per shot) instead of the C port."""
     import ctypes as C
     from oracle.oracle import Oracle, ref_lib, _p
+    select_workload(wl_key)
     _CPU["plan"] = plan_blob
     _CPU["orc"] = [Oracle(w.mat, w.prior) for w in plan_blob.windows]
     _CPU["chkT"] = plan_blob.chk.T.tocsr()
@@ -55,11 +77,12 @@ def _cpu_init(plan_blob, use_ref=False):
     if use_ref:
         lib = ref_lib()
         lib.ref_gdg_create.restype = C.c_void_p
+        kw = WL["kw"]
         hs = []
         for o in _CPU["orc"]:
-            h = lib.ref_gdg_create(o.m, o.n, _p(o.cp, C.c_int), _p(o.cr, C.c_int), _p(o.llr, C.c_double), GDG_KW["max_iter"],
-                                   C.c_double(1.0), GDG_KW["max_iter_per_step"], GDG_KW["max_step"], GDG_KW["max_tree_depth"],
-                                   GDG_KW["max_side_depth"], GDG_KW["max_tree_branch_step"], GDG_KW["max_side_branch_step"],
+            h = lib.ref_gdg_create(o.m, o.n, _p(o.cp, C.c_int), _p(o.cr, C.c_int), _p(o.llr, C.c_double), kw["max_iter"],
+                                   C.c_double(1.0), kw["max_iter_per_step"], kw["max_step"], kw["max_tree_depth"],
+                                   kw["max_side_depth"], kw["max_tree_branch_step"], kw["max_side_branch_step"],
                                    C.c_double(1.0), 0, 0)
             hs.append(C.c_void_p(h))
         _CPU["ref"] = (lib, hs)
@@ -69,7 +92,10 @@ def _decode_window(i, synd):
     import ctypes as C
     from oracle.oracle import _p
     if _CPU["ref"] is None:
-        dec, conv, _, _ = _CPU["orc"][i].bpgdg_batch(synd, **GDG_KW)
+        if WL["decoder"] == "osd":
+            dec, conv, _, _ = _CPU["orc"][i].osd_window_batch(synd, **WL["kw"])
+        else:
+            dec, conv, _, _ = _CPU["orc"][i].bpgdg_batch(synd, **WL["kw"])
         return dec
     lib, hs = _CPU["ref"]
     o = _CPU["orc"][i]
@@ -111,7 +137,8 @@ class CpuArm:
         self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         self.procs = procs or self.cores
         self.plan = plan
-        self.pool = mp.get_context("fork").Pool(self.procs, initializer=_cpu_init, initargs=(plan, use_ref))
+        key = next(k for k, v in WORKLOADS.items() if v is WL)
+        self.pool = mp.get_context("fork").Pool(self.procs, initializer=_cpu_init, initargs=(plan, use_ref, key))
 
     def run(self, det, obs):
         B = det.shape[0]
@@ -200,7 +227,7 @@ def run_ours(args):
     from slidingwindowdecoder_b200.sliding_window import SlidingWindowDecoder
     from slidingwindowdecoder_b200.distributed import reduce_counters, max_over_ranks
     plan = build_plan()
-    swd = SlidingWindowDecoder(plan, decoder="gdg", device=local, streams=args.streams, **GDG_KW)
+    swd = SlidingWindowDecoder(plan, decoder=WL["decoder"], device=local, streams=args.streams, **WL["kw"])
     B, K, W = args.batch, args.steps, args.warmup
     nsteps = K + W
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -301,8 +328,10 @@ def run_ours(args):
         peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
-    path_ms = sum(ktimes.get(k, [0, 0])[0] for k in ("path_main", "path_side", "path_trunk"))
-    path_launches = sum(ktimes.get(k, [0, 0])[1] for k in ("path_main", "path_side", "path_trunk"))
+    gdg = WL["decoder"] == "gdg"
+    dom = ("path_main", "path_side", "path_trunk") if gdg else ("post_bp",)   # osd_window: masked min-sum on the shortened graph
+    path_ms = sum(ktimes.get(k, [0, 0])[0] for k in dom)
+    path_launches = sum(ktimes.get(k, [0, 0])[1] for k in dom)
     # B_iter = 4 E w + 2 n_a w + (n_a + m_a)/8 with w = 8, summed over executed iterations
     path_bytes = 32.0 * ctr["path_edge_iters"] + 16.0 * ctr["path_vn_iters"] + (ctr["path_vn_iters"] + ctr["path_cn_iters"]) / 8.0
     pre_bytes = 32.0 * ctr["pre_bp_edge_iters"]
@@ -310,12 +339,14 @@ def run_ours(args):
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
-        tj = json.load(open(tpath)).get("path_kernel", {})
+        tj = json.load(open(tpath)).get("path_kernel" if gdg else "osd_pipeline", {})
         if tj.get("batch") == B:                 # the capture was taken at this batch size
             traffic = int(tj["dram_bytes_per_launch_avg"]); traffic_src = tj.get("source")
     kernel_ms = {k: round(v[0], 3) for k, v in ktimes.items() if v[1]}
     tot_k = sum(kernel_ms.values()) or 1.0
-    roofline = {"kernel": "path_kernel (GDG branch paths: shared-prefix nodes + main/tree + side launches)", "bound": "hbm", "achieved": round(achieved, 1),
+    roofline = {"kernel": "path_kernel (GDG branch paths: shared-prefix nodes + main/tree + side launches)" if gdg else
+                          "post_bp_kernel (masked min-sum on the shortened graph; the bit-packed GF(2) osd_kernel is timed separately in kernel_ms)",
+                "bound": "hbm", "achieved": round(achieved, 1),
                 "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": round(path_bytes / max(1, path_launches)),
                 "avg_launch_ms": round(path_ms / max(1, path_launches), 4), "launches": path_launches,
@@ -337,14 +368,14 @@ def run_ours(args):
         dt, cflag, cfail = arm.run(cdet, cobs)
         arm.close()
         cpu_baseline = {"value": round(nsample / dt, 2), "unit": "shots/s", "cores": arm.cores, "kind": "port",
-                        "sample": f"{nsample} shots x 11 windows through the oracle port (C restatement, gcc -O2), "
+                        "sample": f"{nsample} shots x {len(plan.windows)} windows through the oracle port (C restatement, gcc -O2), "
                                   f"one process per core, {dt:.1f} s; failed {cfail}/{nsample}"}
     launches = ctr_timed["kernel_launches"] + K * args.streams * (2 * len(plan.windows) + 1)
     line = {
-        "metric": "decoded shots/sec (sliding-window GDG)", "value": round(value, 1), "unit": "shots/s", "n_gpus": world,
+        "metric": METRIC[WL["decoder"]], "value": round(value, 1), "unit": "shots/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": round(ms_res / K, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAME, "shots_per_step_per_gpu": B, "decoder": "bpgdg_decoder(max_iter=8, multi_thread=True, defaults)",
+        "config": {"workload": WL["name"], "shots_per_step_per_gpu": B, "decoder": WL["decoder_name"],
                    "streams": args.streams,
                    "inputs": "DEM samples drawn on the device (Philox, independent Bernoulli per column); distinct batch per step, "
                              f"{(B * (det_all.shape[2] + obs_all.shape[2]) * nsteps) >> 20} MiB of syndromes in total (> L2), no L2 flush"},
@@ -369,7 +400,7 @@ def run_reference(args):
     # (i) the reference as shipped: ONE process, bpgd.cpp's own 15 std::threads per decode (oracle/_ref), if it was built
     as_shipped = None
     from oracle.oracle import ref_lib
-    if ref_lib() is not None:
+    if ref_lib() is not None and WL["decoder"] == "gdg":
         devnull = os.open(os.devnull, os.O_WRONLY)
         saved = os.dup(2); os.dup2(devnull, 2)          # "Error setting thread affinity" spam on hosts with < 15 cores
         try:
@@ -393,12 +424,12 @@ def run_reference(args):
             times.append(dt); fails += fa; n += nsample
     arm.close()
     v = n / sum(times)
-    line = {"impl": "reference", "metric": "decoded shots/sec (sliding-window GDG)", "value": round(v, 2), "unit": "shots/s",
+    line = {"impl": "reference", "metric": METRIC[WL["decoder"]], "value": round(v, 2), "unit": "shots/s",
             "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": K, "warmup": W, "ms_per_step": round(1e3 * sum(times) / K, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME, "shots_per_step": nsample},
+            "config": {"workload": WL["name"], "shots_per_step": nsample},
             "cpu_baseline": {"value": round(v, 2), "unit": "shots/s", "cores": arm.cores, "kind": "port",
-                             "sample": f"{nsample} shots x 11 windows per step, oracle port (C restatement), one process per core",
+                             "sample": f"{nsample} shots x {len(plan.windows)} windows per step, oracle port (C restatement), one process per core",
                              "reference_as_shipped_shots_per_s": as_shipped,
                              "reference_as_shipped_note": "oracle/_ref = the reference's own bpgd.cpp/mod2sparse.c, one process, "
                                                           "15 std::threads per decode, 48 shots" if as_shipped else "oracle/_ref not built"},
@@ -414,10 +445,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=16384)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3_gdg", choices=sorted(WORKLOADS), help="default: BASELINE.json configs[2], the metric's configuration")
     ap.add_argument("--streams", type=int, default=2, help="concurrent sub-batches per GPU (fills kernel tails)")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: do not time the CPU baseline")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
+    select_workload(args.workload)
     if args.impl == "reference":
         run_reference(args)
     else:

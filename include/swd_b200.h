@@ -96,8 +96,9 @@ typedef struct swd_counters {
 #define SWD_K_PATH_MAIN  2   /* path_kernel phase 0: main + tree branches (or the single GD / post-BP path) */
 #define SWD_K_PATH_SIDE  3   /* path_kernel phase 1: side branches                                         */
 #define SWD_K_SELECT     4
-#define SWD_K_OSD        5
+#define SWD_K_OSD        5   /* osd_window: osd_kernel + finish / path-metric kernels */
 #define SWD_K_PATH_TRUNK 6   /* path_kernel on shared-prefix nodes (decimation depths < max_tree_depth)                 */
+#define SWD_K_POST_BP    7   /* osd_window: masked min-sum on the shortened graph (post_bp_kernel)                               */
 #define SWD_K_COUNT      8
 
 /* pcm as CSC: colptr[n+1], rowidx[nnz] (any order inside a column; sorted internally, as

@@ -29,7 +29,7 @@ class SwdCounters(C.Structure):
 
 
 KIND_BPGDG, KIND_BPGD, KIND_OSD_WINDOW = 0, 1, 2
-KERNEL_CLASSES = ["pre_bp", "sort_reset", "path_main", "path_side", "select", "osd", "path_trunk", "k7"]
+KERNEL_CLASSES = ["pre_bp", "sort_reset", "path_main", "path_side", "select", "osd", "path_trunk", "post_bp"]
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4
 
 EXPORTS = ["swd_create", "swd_destroy", "swd_decode_batch_host", "swd_decode_batch_device", "swd_osd_last_outputs",

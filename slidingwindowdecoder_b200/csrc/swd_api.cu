@@ -317,9 +317,17 @@ static int setup_kernels(swd_decoder *d) {
     S1.off_misc = o; o += 64; S1.total = o;
     if (S1.total > 227 * 1024) { set_err("window graph does not fit in shared memory (nnz too large)"); return SWD_ERR_UNSUPPORTED; }
     int occ = 0, st;
-    d->pre_fn = d->max_col_deg <= 6 ? pre_bp_kernel<6> : (d->max_col_deg <= 8 ? pre_bp_kernel<8> : pre_bp_kernel<16>);
+    d->pre_fn = d->max_col_deg <= 6 ? pre_bp_kernel<6, 256, SWD_PRE_MINB> : (d->max_col_deg <= 8 ? pre_bp_kernel<8, 256, SWD_PRE_MINB> : pre_bp_kernel<16, 256, 2>);
     st = occupancy(d->pre_fn, d->T1, S1.total, &occ);
     if (st) return st;
+    if (occ * d->T1 < 512 && !getenv("SWD_T1")) {
+        // shared memory allows fewer than 16 warps per SM with 256-thread CTAs: use one large CTA per SM instead
+        const int want = std::min(1024, std::max(256, r32up(std::max((n + 3) / 4, m))));
+        pre_fn_t big = d->max_col_deg <= 6 ? pre_bp_kernel<6, 1024, 1> : (d->max_col_deg <= 8 ? pre_bp_kernel<8, 1024, 1> : pre_bp_kernel<16, 1024, 1>);
+        int occ_big = 0;
+        if ((st = occupancy(big, want, S1.total, &occ_big))) return st;
+        if (occ_big * want > occ * d->T1) { d->pre_fn = big; d->T1 = want; occ = occ_big; }
+    }
     if (occ < 1) { set_err("pre_bp_kernel does not fit"); return SWD_ERR_UNSUPPORTED; }
     d->grid1 = d->num_sm * occ;
     // ---- K2
@@ -484,11 +492,13 @@ static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_cor
     const int g3 = d->grid3;
     const int phases = (c.kind == SWD_KIND_BPGDG && c.multi_thread && d->P.n_side > 0) ? 2 : 1;
     if (c.kind == SWD_KIND_OSD_WINDOW) {
-        KTimer kt(d, s, SWD_K_OSD);
-        int st = osd_launch(d->g, d_synd, d->ws, d->L, d->LsA, d->LsB, d->PS, d->PSB, d->es_capA, d->grid3B, smem3B, d->P, d->OS, d->ow, d->dmax, d->T3, g3, smem3, d->T5, d->grid5,
-                            c.osd_method, c.osd_order, d->rank, d_corr, d_conv, d_pm, B, chunk_base, s, &d->ctr.kernel_launches,
-                            d->ow.need_osd + d->cap);
-        if (st) { set_err("osd launch failed"); return st; }
+        for (int stage = 0; stage < 2; stage++) {
+            KTimer kt(d, s, stage == 0 ? SWD_K_POST_BP : SWD_K_OSD);
+            int st = osd_launch(d->g, d_synd, d->ws, d->L, d->LsA, d->LsB, d->PS, d->PSB, d->es_capA, d->grid3B, smem3B, d->P, d->OS, d->ow, d->dmax, d->T3, g3, smem3, d->T5, d->grid5,
+                                c.osd_method, c.osd_order, d->rank, d_corr, d_conv, d_pm, B, chunk_base, s, &d->ctr.kernel_launches,
+                                d->ow.need_osd + d->cap, stage);
+            if (st) { set_err("osd launch failed"); return st; }
+        }
     } else {
         for (int lv = 0; lv < d->P.shared_T; lv++) {       // shared-prefix nodes, level by level
             KTimer kt(d, s, SWD_K_PATH_TRUNK);

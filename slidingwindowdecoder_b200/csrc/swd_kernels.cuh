@@ -23,8 +23,10 @@ struct PreSmem { int off_msg, off_upar, off_synd, off_dec, off_misc, total; };
 #ifndef SWD_PRE_MINB
 #define SWD_PRE_MINB 3
 #endif
-template <int DMAX>
-__global__ void __launch_bounds__(256, SWD_PRE_MINB)
+// MAXT = 256: several CTAs per SM (small windows).  MAXT = 1024: windows whose messages leave room for one CTA per
+// SM only (e.g. 576 x 4896, 136 KB) get one large CTA instead of eight warps per SM.
+template <int DMAX, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter, double alpha,
               u8 *__restrict__ dec_out, u8 *__restrict__ conv_out, Workspace ws, double *hscratch,
               int full_hist, PreSmem S, int *iter_out, double *lpr_out) {

@@ -472,16 +472,20 @@ static inline int osd_launch(const GraphDev &g, const u8 *d_synd, const Workspac
                              const SubLayout &LsB, const PathSmem &PS, const PathSmem &PSB, int capA, int grid3B, size_t smem3B,
                              const GdgDev &P, const OsdSmem &OS, const OsdWork &ow, int dmax, int T3, int grid3, size_t smem3,
                              int T5, int grid5, int method, int order_w, int rank, u8 *d_corr, u8 *d_conv, double *d_pm,
-                             long long B, long long chunk_base, cudaStream_t s, uint64_t *launches, u8 *in_list) {
-    post_fn_t post = pick_post_kernel(dmax, T3);
-    if (cudaFuncSetAttribute(post, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -3;
-    post<<<grid3, T3, smem3, s>>>(ws, L, LsA, PS, P, g.n, ow, chunk_base, 0, capA);
-    if (capA < L.es_max) { post<<<grid3B, T3, smem3B, s>>>(ws, L, LsB, PSB, P, g.n, ow, chunk_base, 1, capA); *launches += 1; }
+                             long long B, long long chunk_base, cudaStream_t s, uint64_t *launches, u8 *in_list, int stage) {
+    if (stage == 0) {        // post-BP on the shortened graph
+        post_fn_t post = pick_post_kernel(dmax, T3);
+        if (cudaFuncSetAttribute(post, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -3;
+        post<<<grid3, T3, smem3, s>>>(ws, L, LsA, PS, P, g.n, ow, chunk_base, 0, capA);
+        *launches += 1;
+        if (capA < L.es_max) { post<<<grid3B, T3, smem3B, s>>>(ws, L, LsB, PSB, P, g.n, ow, chunk_base, 1, capA); *launches += 1; }
+        return cudaGetLastError() == cudaSuccess ? 0 : -3;
+    }
     osd_kernel<<<grid5, T5, OS.total, s>>>(g, d_synd, ws, L, P, OS, ow, method, order_w, rank, d_corr, d_pm, chunk_base);
     osd_finish_kernel<<<grid5, 128, 0, s>>>(ws, L, P, ow, g.n, d_corr, d_conv, chunk_base);
     cudaMemsetAsync(in_list, 0, (size_t)B, s);
     osd_mark_list_kernel<<<64, 256, 0, s>>>(ws, in_list);
     osd_pm_kernel<<<(unsigned)((B + 7) / 8 < 1 ? 1 : ((B + 7) / 8 > 65535 ? 65535 : (B + 7) / 8)), 256, 0, s>>>(g.llr, g.n, d_corr, d_conv, B, d_pm, ow, chunk_base, in_list);
-    *launches += 5;
+    *launches += 4;
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

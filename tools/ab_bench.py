@@ -22,8 +22,9 @@ def worker(batch, steps, env_note):
     import bench
     from slidingwindowdecoder_b200.sliding_window import SlidingWindowDecoder
     dev = torch.device("cuda", 0)
+    bench.select_workload(os.environ.get("AB_WORKLOAD", "c3_gdg"))
     plan = bench.build_plan()
-    swd = SlidingWindowDecoder(plan, decoder="gdg", device=0, streams=int(os.environ.get("AB_STREAMS", "1")), **bench.GDG_KW)
+    swd = SlidingWindowDecoder(plan, decoder=bench.WL["decoder"], device=0, streams=int(os.environ.get("AB_STREAMS", "1")), **bench.WL["kw"])
     nsteps = steps + 2
     det_all, obs_all = bench.gpu_sample(swd, batch * nsteps, 1234)
     det_all = det_all.view(nsteps, batch, -1); obs_all = obs_all.view(nsteps, batch, -1)
