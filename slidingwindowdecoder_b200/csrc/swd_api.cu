@@ -335,6 +335,7 @@ static int setup_kernels(swd_decoder *d) {
     int np2 = 64; while (np2 < n) np2 <<= 1;
     S2.np2 = np2;
     d->T2 = std::min(1024, std::max(128, np2 / 8));
+    if (const char *e = getenv("SWD_T2")) d->T2 = std::min(1024, std::max(64, r32up(atoi(e))));
     o = 0; S2.off_key = o; o += 8 * np2; S2.off_idx = o; o += 2 * np2; o = r16(o);
     S2.off_posof = o; o += 2 * n; o = r16(o);
     S2.off_blob = o; o += d->L.blob_bytes;

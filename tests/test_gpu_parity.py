@@ -376,3 +376,54 @@ def test_last_window_bposd_redecode_matches_reference_loop(oracle_mod):
         logical = ((ob.astype(np.int64) + total @ obd.T) % 2).any(axis=1)
         assert res["flagged_last_window_osd"] == int(flagged.sum())
         assert res["failed_last_window_osd"] == int(np.logical_or(flagged, logical).sum())
+
+
+def test_full_size_pipeline_properties_and_logical_error_rate(oracle_mod):
+    """BASELINE configs[2] at bench size: [[144,12,12]] p=0.003, 12 rounds, (3,1), 65536 device-sampled shots.
+    Size-independent properties: (i) the residual syndrome after all commits equals det + chk . total_e_hat, and a shot
+    is flagged exactly when that residual is non-zero; (ii) results do not depend on the number of streams nor on the
+    workspace chunking; (iii) the failure rate lies inside the 95 % binomial interval around the CPU oracle's rate on an
+    independent sample (north_star: logical error rates inside the reference's CI)."""
+    import torch
+    import bench
+    from slidingwindowdecoder_b200.sliding_window import SlidingWindowDecoder
+    bench.select_workload("c3_gdg")
+    plan = bench.build_plan()
+    kw = bench.WL["kw"]
+    swd = SlidingWindowDecoder(plan, decoder="gdg", streams=2, **kw)
+    shots = 65536
+    det, obs = swd.sample_device(shots, seed=2024)
+    d1, o1 = det.clone(), obs.clone()
+    out = swd.decode_device(d1, o1, return_corrections=True)
+    torch.cuda.synchronize()
+    counts = out["counts"].cpu().numpy()
+    # (i) residuals recomputed densely on the device for a slice
+    sl = slice(0, 8192)
+    chk = torch.from_numpy(np.asarray(plan.chk.todense(), dtype=np.float32)).cuda()
+    tot = out["total_e_hat"][sl].to(torch.float32)
+    resid = torch.remainder(det[sl].to(torch.float32) + tot @ chk.T, 2).to(torch.uint8)
+    assert torch.equal(resid, d1[sl])
+    flagged = (d1 != 0).any(dim=1)
+    assert int(flagged.sum()) == int(counts[0])
+    logical = (o1 != 0).any(dim=1)
+    assert int((flagged | logical).sum()) == int(counts[1])
+    # (ii) one stream, same answer
+    d2, o2 = det.clone(), obs.clone()
+    out2 = swd.decode_device(d2, o2, return_corrections=True, streams=1)
+    assert torch.equal(out2["total_e_hat"], out["total_e_hat"]) and torch.equal(out2["counts"], out["counts"])
+    # (iii) failure rate vs the CPU oracle on an independent host sample (800 shots, the reference's loop)
+    hdet, hobs = bench.sample_host(plan, 800, 77)
+    oracles = [oracle_mod.Oracle(w.mat, w.prior) for w in plan.windows]
+
+    def decode_window(w, synd):
+        d, c, _, _ = oracles[w.index].bpgdg_batch(synd, **kw)
+        return d, c
+
+    ref = oracle_mod.sliding_window_reference(plan, hdet, hobs, decode_window)
+    p_gpu = counts[1] / shots
+    k, n = int(ref["failed"].sum()), 800
+    # Wilson 95 % interval of the oracle's rate, widened by the GPU estimate's own standard error
+    z = 1.96
+    centre = (k + z * z / 2) / (n + z * z)
+    half = z * np.sqrt(k * (n - k) / n + z * z / 4) / (n + z * z)
+    assert centre - half - 3 * np.sqrt(p_gpu / shots) <= p_gpu <= centre + half + 3 * np.sqrt(p_gpu / shots), (p_gpu, k, n)
