@@ -72,7 +72,12 @@ typedef struct swd_config {
     int    post_max_iter;
     int    osd_method;            /* SWD_OSD_*                                                    */
     int    osd_order;
+    /* BP flavour of the full-window BP: SWD_BP_MIN_SUM (the reference's own decoders) or SWD_BP_PRODUCT_SUM (what the
+     * drivers can ask of ldpc.BpOsdDecoder via bp_method="product_sum", osd.py:142-150; third-party, parity unpinned). */
+    int    bp_method;
 } swd_config;
+#define SWD_BP_MIN_SUM      0
+#define SWD_BP_PRODUCT_SUM  1
 
 typedef struct swd_decoder swd_decoder;
 

@@ -64,6 +64,12 @@ def ref_lib():
     return _ref
 
 
+def set_bp_method(method):
+    """Flavour of the full-window BP of every oracle decode that follows: 'minimum_sum' (the reference) or 'product_sum'
+    (restated from ldpc's published algorithm; parity unpinned).  Remember to switch back."""
+    lib().orc_set_bp_method(1 if str(method).lower() in ("product_sum", "ps", "1") else 0)
+
+
 def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 

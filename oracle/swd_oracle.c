@@ -141,6 +141,41 @@ static int64_t ms_iteration(const graph *g, const int8_t *vmask, const int8_t *c
     return edges;
 }
 
+/* Product-sum check update for the unmasked pre-BP (NOT part of the reference's own sources: it exists only in the
+ * third-party `ldpc` package the drivers call as BpOsdDecoder(bp_method="product_sum"), un-vendored and unpinned;
+ * this restates its published forward / backward tanh-product form):
+ *   c2b[k] = s_c * log((1 + P_k) / (1 - P_k)),  P_k = prod_{j != k} tanh(b2c[j] / 2),  s_c = -1 if the syndrome bit is set,
+ * with P_k saturated to +-(1 - 2^-52) so that the logarithm stays finite (|c2b| <= ~36.7).  The variable update is the
+ * reference's prefix / suffix form.  PARITY UNPINNED. */
+static int g_bp_method = 0;       /* 0 = min-sum (reference), 1 = product-sum */
+void orc_set_bp_method(int method) { g_bp_method = method; }
+static int64_t ps_iteration(const graph *g, const int8_t *sseed, const double *prior,
+                            double *b2c, double *c2b, double *hist, int slot, int8_t *dec) {
+    const double PMAX = 1.0 - 2.220446049250313e-16;
+    int64_t edges = 0;
+    for (int c = 0; c < g->m; c++) {
+        double tmp = 1.0;
+        for (int p = g->rp[c]; p < g->rp[c + 1]; p++) { c2b[p] = tmp; tmp *= tanh(b2c[p] * 0.5); }
+        tmp = 1.0;
+        const double sg = (sseed[c] == 1) ? -1.0 : 1.0;
+        for (int p = g->rp[c + 1] - 1; p >= g->rp[c]; p--) {
+            double P = c2b[p] * tmp;
+            if (P > PMAX) P = PMAX; else if (P < -PMAX) P = -PMAX;
+            c2b[p] = sg * log((1.0 + P) / (1.0 - P));
+            tmp *= tanh(b2c[p] * 0.5);
+        }
+    }
+    for (int v = 0; v < g->n; v++) {
+        double t = prior[v];
+        for (int e = g->cp[v]; e < g->cp[v + 1]; e++) { int p = g->c2r[e]; b2c[p] = t; t += c2b[p]; edges++; }
+        hist[4 * v + slot] = t;
+        dec[v] = (t <= 0) ? 1 : 0;
+        t = 0.0;
+        for (int e = g->cp[v + 1] - 1; e >= g->cp[v]; e--) { int p = g->c2r[e]; b2c[p] += t; t += c2b[p]; }
+    }
+    return edges;
+}
+
 /* H*dec == synd over all rows / all columns (mod2sparse_mulvec + compare,
  * bpgd.cpp:185-194; pyx:129-137). tsynd receives H*dec. */
 static int synd_match(const graph *g, const int8_t *dec, const int8_t *synd, int8_t *tsynd) {
@@ -164,7 +199,8 @@ static int bp_pre(const graph *g, const double *llr, const int8_t *synd, int max
         for (int e = g->cp[v]; e < g->cp[v + 1]; e++) b2c[g->c2r[e]] = llr[v];   /* pyx:55-60 */
     int conv = 0, it;
     for (it = 0; it < max_iter; it++) {
-        int64_t ed = ms_iteration(g, NULL, NULL, synd, llr, alpha, b2c, c2b, hist, it % 4, dec);
+        int64_t ed = g_bp_method ? ps_iteration(g, synd, llr, b2c, c2b, hist, it % 4, dec)
+                                 : ms_iteration(g, NULL, NULL, synd, llr, alpha, b2c, c2b, hist, it % 4, dec);
         if (edge_iters) *edge_iters += ed;
         if (synd_match(g, dec, synd, ts)) { conv = 1; it++; break; }
     }
@@ -892,7 +928,8 @@ int orc_osd_window_decode(int m, int n, const int *cp, const int *cr, const doub
     if (st) st->stage = 0;
     for (int it = 0; it < P->pre_max_iter; it++) {
         bp_iter++;
-        int64_t ed = ms_iteration(g, cur_vn, cur_cn, cur_cn, llr, P->ms_scaling_factor, b2c, c2b, hist, it % 4, bpd);
+        int64_t ed = g_bp_method ? ps_iteration(g, synd, llr, b2c, c2b, hist, it % 4, bpd)       /* nothing is masked before the shortening */
+                                 : ms_iteration(g, cur_vn, cur_cn, cur_cn, llr, P->ms_scaling_factor, b2c, c2b, hist, it % 4, bpd);
         if (st) { st->edge_iters += ed; st->pre_iters++; }
         if (synd_match(g, bpd, synd, ts)) { conv = 1; break; }
     }

@@ -17,7 +17,7 @@ class SwdConfig(C.Structure):
                 ("max_tree_branch_step", C.c_int), ("max_side_branch_step", C.c_int),
                 ("gdg_factor", C.c_double), ("new_n", C.c_int),
                 ("multi_thread", C.c_int), ("low_error_mode", C.c_int),
-                ("post_max_iter", C.c_int), ("osd_method", C.c_int), ("osd_order", C.c_int)]
+                ("post_max_iter", C.c_int), ("osd_method", C.c_int), ("osd_order", C.c_int), ("bp_method", C.c_int)]
 
 
 class SwdCounters(C.Structure):

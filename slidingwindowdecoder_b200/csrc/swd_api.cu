@@ -140,6 +140,7 @@ extern "C" int swd_create(const swd_config *cfg, int m, int n, const int32_t *co
                           const double *channel_llr, swd_decoder **out) {
     if (!cfg || !colptr || !rowidx || !channel_llr || !out || m <= 0 || n <= 0) { set_err("swd_create: null/empty argument"); return SWD_ERR_INVALID; }
     if (cfg->kind < 0 || cfg->kind > 2) { set_err("swd_create: bad kind"); return SWD_ERR_INVALID; }
+    if (cfg->bp_method != SWD_BP_MIN_SUM && cfg->bp_method != SWD_BP_PRODUCT_SUM) { set_err("swd_create: bad bp_method"); return SWD_ERR_INVALID; }
     const int nnz = colptr[n];
     if (colptr[0] != 0 || nnz < 0) { set_err("swd_create: bad colptr"); return SWD_ERR_INVALID; }
     if (n > 65534 || m > 65534 || nnz > 65535) { set_err("swd_create: graph too large for 16-bit indices"); return SWD_ERR_UNSUPPORTED; }
@@ -314,16 +315,22 @@ static int setup_kernels(swd_decoder *d) {
     S1.off_upar = o; o += 4 * m; o = r16(o);
     S1.off_synd = o; o += m; o = r16(o);
     S1.off_dec = o; o += n; o = r16(o);
-    S1.off_misc = o; o += 64; S1.total = o;
+    S1.off_misc = o; o += 64;
+    S1.off_fwd = o;
+    const bool ps = (c.bp_method == SWD_BP_PRODUCT_SUM);
+    if (ps) { o = r16(o); S1.off_fwd = o; o += 8 * std::max(d->nnz, 1); }
+    S1.total = o;
     if (S1.total > 227 * 1024) { set_err("window graph does not fit in shared memory (nnz too large)"); return SWD_ERR_UNSUPPORTED; }
     int occ = 0, st;
-    d->pre_fn = d->max_col_deg <= 6 ? pre_bp_kernel<6, 256, SWD_PRE_MINB> : (d->max_col_deg <= 8 ? pre_bp_kernel<8, 256, SWD_PRE_MINB> : pre_bp_kernel<16, 256, 2>);
+    if (ps) d->pre_fn = d->max_col_deg <= 8 ? pre_bp_kernel<8, 256, 2, true> : pre_bp_kernel<16, 256, 2, true>;
+    else d->pre_fn = d->max_col_deg <= 6 ? pre_bp_kernel<6, 256, SWD_PRE_MINB, false> : (d->max_col_deg <= 8 ? pre_bp_kernel<8, 256, SWD_PRE_MINB, false> : pre_bp_kernel<16, 256, 2, false>);
     st = occupancy(d->pre_fn, d->T1, S1.total, &occ);
     if (st) return st;
     if (occ * d->T1 < 512 && !getenv("SWD_T1")) {
         // shared memory allows fewer than 16 warps per SM with 256-thread CTAs: use one large CTA per SM instead
         const int want = std::min(1024, std::max(256, r32up(std::max((n + 3) / 4, m))));
-        pre_fn_t big = d->max_col_deg <= 6 ? pre_bp_kernel<6, 1024, 1> : (d->max_col_deg <= 8 ? pre_bp_kernel<8, 1024, 1> : pre_bp_kernel<16, 1024, 1>);
+        pre_fn_t big = ps ? (d->max_col_deg <= 8 ? pre_bp_kernel<8, 1024, 1, true> : pre_bp_kernel<16, 1024, 1, true>)
+                          : (d->max_col_deg <= 6 ? pre_bp_kernel<6, 1024, 1, false> : (d->max_col_deg <= 8 ? pre_bp_kernel<8, 1024, 1, false> : pre_bp_kernel<16, 1024, 1, false>));
         int occ_big = 0;
         if ((st = occupancy(big, want, S1.total, &occ_big))) return st;
         if (occ_big * want > occ * d->T1) { d->pre_fn = big; d->T1 = want; occ = occ_big; }

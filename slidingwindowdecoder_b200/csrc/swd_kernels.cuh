@@ -18,14 +18,15 @@
 // ----------------------------------------------------------------------------------------------
 // K1: full-window BP
 // ----------------------------------------------------------------------------------------------
-struct PreSmem { int off_msg, off_upar, off_synd, off_dec, off_misc, total; };
+struct PreSmem { int off_msg, off_upar, off_synd, off_dec, off_misc, total; int off_fwd; };   // off_fwd: product-sum forward products
 
 #ifndef SWD_PRE_MINB
 #define SWD_PRE_MINB 3
 #endif
 // MAXT = 256: several CTAs per SM (small windows).  MAXT = 1024: windows whose messages leave room for one CTA per
 // SM only (e.g. 576 x 4896, 136 KB) get one large CTA instead of eight warps per SM.
-template <int DMAX, int MAXT, int MINB>
+// PS = true: product-sum check update (tanh products, forward / backward) instead of normalised min-sum.
+template <int DMAX, int MAXT, int MINB, bool PS>
 __global__ void __launch_bounds__(MAXT, MINB)
 pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter, double alpha,
               u8 *__restrict__ dec_out, u8 *__restrict__ conv_out, Workspace ws, double *hscratch,
@@ -54,6 +55,27 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
         int conv = 0, it = 0;
         for (; it < max_iter; it++) {
             // ---- check pass: min1/min2/argmin/parity with plain compares, sign applied by xor (all edges live)
+            if (PS) {
+                // product-sum (restated from the published ldpc BpOsdDecoder algorithm, parity unpinned): forward products
+                // in `fwd`, backward sweep writes c2b = s * log((1 + P) / (1 - P)), P saturated to +-(1 - 2^-52)
+                double *fwd = (double *)(smem + S.off_fwd);
+                const double PMAX = 1.0 - 2.220446049250313e-16;
+                for (int r = tid; r < m; r += T) {
+                    upar[r] = 0;
+                    const int p0 = g.rp[r], p1 = g.rp[r + 1];
+                    double tmp = 1.0;
+                    for (int p = p0; p < p1; p++) { fwd[p] = tmp; tmp *= tanh(msg[p] * 0.5); }
+                    tmp = 1.0;
+                    const double sg = s_synd[r] ? -1.0 : 1.0;
+                    for (int p = p1 - 1; p >= p0; p--) {
+                        const double b = msg[p];
+                        double P = fwd[p] * tmp;
+                        P = (P > PMAX) ? PMAX : ((P < -PMAX) ? -PMAX : P);
+                        msg[p] = sg * log((1.0 + P) / (1.0 - P));
+                        tmp *= tanh(b * 0.5);
+                    }
+                }
+            } else
             for (int r = tid; r < m; r += T) {
                 upar[r] = 0;
                 const int p0 = g.rp[r], p1 = g.rp[r + 1];

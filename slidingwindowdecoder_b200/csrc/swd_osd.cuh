@@ -54,7 +54,8 @@ static inline void osd_free_outputs(OsdWork *ow) {
 // ----------------------------------------------------------------------------------------------
 template <int VPT, int DMAX, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
-post_bp_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int n, OsdWork ow, long long chunk_base, int tier, int capA) {
+post_bp_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int n, OsdWork ow, long long chunk_base, int tier, int capA,
+               const u8 *__restrict__ dec_in) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
     unsigned char *blob = smem;
@@ -107,7 +108,9 @@ post_bp_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, in
         mphase ^= 1;
         c.es = gh.es; c.bad_rows = gh.bad_rows;
         const u16 *col = (const u16 *)(gblob + LG.off_col);                 // only in the global blob (not staged)
-        for (int j = tid; j < c.nn; j += T) { const i8 v = snap_vn[j]; c.vn_mask[j] = v; c.error[j] = v < 0 ? 0 : v; }
+        // undecided VNs start from the pre-BP hard decision (bp_decoding persists across the two BP stages,
+        // osd_window.pyx:381-485; visible when post_max_iter = 0 or the first iteration converges nothing)
+        for (int j = tid; j < c.nn; j += T) { const i8 v = snap_vn[j]; c.vn_mask[j] = v; c.error[j] = v < 0 ? (i8)dec_in[(size_t)gh.shot * n + col[j]] : v; }
         for (int r = tid; r < c.m; r += T) { c.cn_mask[r] = snap_cn[r]; c.cn_deg[r] = snap_deg[r]; c.flip[r] = 0; }
         __syncthreads();
         init_msgs<VPT>(c);                                                  // bp_init, osd_window.pyx:370-379
@@ -456,7 +459,7 @@ static inline int osd_setup(int m, int n, int nn, int rank, int method, int orde
     return 0;
 }
 
-typedef void (*post_fn_t)(Workspace, SubLayout, SubLayout, PathSmem, GdgDev, int, OsdWork, long long, int, int);
+typedef void (*post_fn_t)(Workspace, SubLayout, SubLayout, PathSmem, GdgDev, int, OsdWork, long long, int, int, const u8 *);
 static inline post_fn_t pick_post_kernel(int dmax, int T) {
     if (dmax == 6) {
         if (T <= 128) return post_bp_kernel<4, 6, 128, 5>;
@@ -476,9 +479,9 @@ static inline int osd_launch(const GraphDev &g, const u8 *d_synd, const Workspac
     if (stage == 0) {        // post-BP on the shortened graph
         post_fn_t post = pick_post_kernel(dmax, T3);
         if (cudaFuncSetAttribute(post, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -3;
-        post<<<grid3, T3, smem3, s>>>(ws, L, LsA, PS, P, g.n, ow, chunk_base, 0, capA);
+        post<<<grid3, T3, smem3, s>>>(ws, L, LsA, PS, P, g.n, ow, chunk_base, 0, capA, d_corr);
         *launches += 1;
-        if (capA < L.es_max) { post<<<grid3B, T3, smem3B, s>>>(ws, L, LsB, PSB, P, g.n, ow, chunk_base, 1, capA); *launches += 1; }
+        if (capA < L.es_max) { post<<<grid3B, T3, smem3B, s>>>(ws, L, LsB, PSB, P, g.n, ow, chunk_base, 1, capA, d_corr); *launches += 1; }
         return cudaGetLastError() == cudaSuccess ? 0 : -3;
     }
     osd_kernel<<<grid5, T5, OS.total, s>>>(g, d_synd, ws, L, P, OS, ow, method, order_w, rank, d_corr, d_pm, chunk_base);

@@ -22,6 +22,10 @@ _OSD_METHODS = {"osd_0": 0, "0": 0, "osd0": 0,
                 "osd_cs": 2, "2": 2, "osdcs": 2, "combination_sweep": 2, "cs": 2}
 
 
+_BP_METHODS = {"minimum_sum": 0, "ms": 0, "min_sum": 0, "msl": 0, "0": 0,
+               "product_sum": 1, "ps": 1, "prod_sum": 1, "psl": 1, "1": 1}
+
+
 def _libm_llr(channel_probs, n):
     # log((1-p)/p) with libm's log, as bp_guessing_decoder.pyx:46 (numpy's vector log differs by ulps)
     return np.array([math.log((1.0 - float(channel_probs[v])) / float(channel_probs[v])) for v in range(n)],
@@ -54,6 +58,7 @@ class _window_decoder_base:
         self.channel_llr = _libm_llr(channel_probs, self.n)
         cfg.kind = self._kind
         cfg.device = int(device)
+        cfg.bp_method = _BP_METHODS[str(getattr(self, "_bp_method", "minimum_sum")).lower()]
         self._cfg = cfg
         self._device = int(device)
         self._handle = C.c_void_p()
@@ -275,8 +280,9 @@ class BpOsdDecoder(osd_window):
 
     def __init__(self, parity_check_matrix, **kwargs):
         method = str(kwargs.get("bp_method", "minimum_sum")).lower()
-        if method not in ("minimum_sum", "ms", "min_sum", "msl"):
-            raise ValueError("only bp_method='minimum_sum' is implemented (product-sum is not part of the reference's own code)")
+        if method not in _BP_METHODS:
+            raise ValueError(f"bp_method '{method}' invalid: choose 'minimum_sum' or 'product_sum'")
+        self._bp_method = method        # product-sum: restated from ldpc's published algorithm, parity unpinned
         n = parity_check_matrix.shape[1]
         super().__init__(parity_check_matrix, channel_probs=kwargs.get("channel_probs"),
                          pre_max_iter=int(kwargs.get("max_iter", 0)) or n, post_max_iter=0,

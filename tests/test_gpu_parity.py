@@ -427,3 +427,34 @@ def test_full_size_pipeline_properties_and_logical_error_rate(oracle_mod):
     centre = (k + z * z / 2) / (n + z * z)
     half = z * np.sqrt(k * (n - k) / n + z * z / 4) / (n + z * z)
     assert centre - half - 3 * np.sqrt(p_gpu / shots) <= p_gpu <= centre + half + 3 * np.sqrt(p_gpu / shots), (p_gpu, k, n)
+
+
+def test_product_sum_bposd_matches_oracle_within_tolerance(oracle_mod):
+    """BpOsdDecoder(bp_method="product_sum"): tanh / log come from libdevice on the GPU and from libm in the oracle, so the
+    bar is the floating-point one of north_star - posterior LLRs within 1e-6 relative, decisions equal on >= 99.9 % of
+    the shots (parity with the third-party ldpc package itself is unpinned)."""
+    from slidingwindowdecoder_b200 import BpOsdDecoder
+    g = load_golden("c2_w1_osdw_cs10")
+    H, pri, synd = g["mat"], g["priors"], g["synd"][:400]
+    dec = BpOsdDecoder(H, channel_probs=list(pri), max_iter=30, bp_method="product_sum", osd_method="OSD_CS", osd_order=10)
+    corr, conv = dec.decode_batch(synd)
+    out = dec.last_outputs(len(synd))
+    orc = oracle_mod.Oracle(H, pri)
+    oracle_mod.set_bp_method("product_sum")
+    try:
+        same_bp, same_final, worst = 0, 0, 0.0
+        for i in range(len(synd)):
+            r = orc.osd_window(synd[i], pre_max_iter=30, post_max_iter=0, new_n=H.shape[1], osd_method="osd_cs", osd_order=10)
+            assert int(r["bp_iteration"]) == int(out["bp_iteration"][i]) or abs(int(r["bp_iteration"]) - int(out["bp_iteration"][i])) <= 1
+            if int(r["bp_iteration"]) == int(out["bp_iteration"][i]):
+                a, b = out["log_prob_ratios"][i], r["log_prob_ratios"]
+                worst = max(worst, float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))))
+            same_bp += int(np.array_equal(out["bp_decoding"][i], r["bp_decoding"].astype(np.uint8)))
+            same_final += int(np.array_equal(corr[i], r["dec"].astype(np.uint8)) and int(conv[i]) == int(r["converge"]))
+        assert worst < 1e-6, worst
+        assert same_bp >= 0.999 * len(synd) and same_final >= 0.999 * len(synd), (same_bp, same_final)
+    finally:
+        oracle_mod.set_bp_method("minimum_sum")
+    # every OSD output reproduces its syndrome (window matrices have full row rank)
+    resid = np.asarray((H @ corr.T.astype(np.int32)).T % 2).astype(np.uint8)
+    assert np.array_equal(resid, synd)
