@@ -50,7 +50,7 @@ struct swd_decoder {
     int m = 0, n = 0, nnz = 0, nn = 0, max_col_deg = 0, max_row_deg = 0, es_max = 0, rank = -1;
     int device = 0, num_sm = 0;
     GraphDev g{};
-    void *d_graph[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *d_graph[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     SubLayout L{}, LsA{}, LsB{};
     PathSmem PS{}, PSB{};
     int es_capA = 0, grid3B = 0;
@@ -197,16 +197,23 @@ extern "C" int swd_create(const swd_config *cfg, int m, int n, const int32_t *co
         std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return cp[a + 1] - cp[a] > cp[b + 1] - cp[b]; });
         for (int c = 0; c < n; c++) vord[c] = (u16)idx[c];
     }
+    std::vector<u32> vrec(n);          // per ownership slot of the pre-BP kernel: first CSC entry | degree << 16
+    std::vector<double> llr_s(n);
+    for (int sl = 0; sl < n; sl++) {
+        const int v = vord[sl];
+        vrec[sl] = (u32)cp[v] | ((u32)(cp[v + 1] - cp[v]) << 16);
+        llr_s[sl] = llr[v];
+    }
     int st;
     if ((st = upload(rp, &d->d_graph[0])) || (st = upload(rc16, &d->d_graph[1])) || (st = upload(cp, &d->d_graph[2])) ||
         (st = upload(cr16, &d->d_graph[3])) || (st = upload(cpos16, &d->d_graph[4])) || (st = upload(llr, &d->d_graph[5])) ||
-        (st = upload(vord, &d->d_graph[6]))) {
+        (st = upload(vord, &d->d_graph[6])) || (st = upload(vrec, &d->d_graph[7])) || (st = upload(llr_s, &d->d_graph[8]))) {
         swd_destroy(d); return st;
     }
     d->g.m = m; d->g.n = n; d->g.nnz = nnz;
     d->g.rp = (const int *)d->d_graph[0]; d->g.rc = (const u16 *)d->d_graph[1]; d->g.cp = (const int *)d->d_graph[2];
     d->g.cr = (const u16 *)d->d_graph[3]; d->g.cpos = (const u16 *)d->d_graph[4]; d->g.llr = (const double *)d->d_graph[5];
-    d->g.vord = (const u16 *)d->d_graph[6];
+    d->g.vord = (const u16 *)d->d_graph[6]; d->g.vrec = (const u32 *)d->d_graph[7]; d->g.llr_s = (const double *)d->d_graph[8];
     if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) { swd_destroy(d); set_err("stream create failed"); return SWD_ERR_CUDA; }
     if ((st = setup_kernels(d)) != SWD_OK) { swd_destroy(d); return st; }
     *out = d;
@@ -319,22 +326,32 @@ static int setup_kernels(swd_decoder *d) {
     S1.off_fwd = o;
     const bool ps = (c.bp_method == SWD_BP_PRODUCT_SUM);
     if (ps) { o = r16(o); S1.off_fwd = o; o += 8 * std::max(d->nnz, 1); }
-    S1.total = o;
+    S1.total = o; S1.off_vrec = o; S1.off_cpos = o;
     if (S1.total > 227 * 1024) { set_err("window graph does not fit in shared memory (nnz too large)"); return SWD_ERR_UNSUPPORTED; }
+    // staged static graph info (per-slot records + CSC->CSR map) if it still fits next to the messages
+    bool staged = false;
+    {
+        int q = r16(o); const int ov = q; q += 4 * n; q = r16(q); const int oc = q; q += 2 * std::max(d->nnz, 1); q = r16(q);
+        // staging must not cost occupancy: 256-thread CTAs are register limited to 3 per SM, so compare at that count
+        const int occ_unstaged = std::min(3, (int)(233472 / (S1.total + 1024))), occ_staged = std::min(3, (int)(233472 / (q + 1024)));
+        if (q <= 227 * 1024 && occ_staged >= occ_unstaged && !getenv("SWD_PRE_UNSTAGED")) { staged = true; S1.off_vrec = ov; S1.off_cpos = oc; S1.total = q; }
+    }
     int occ = 0, st;
-    if (ps) d->pre_fn = d->max_col_deg <= 8 ? pre_bp_kernel<8, 256, 2, true> : pre_bp_kernel<16, 256, 2, true>;
-    else d->pre_fn = d->max_col_deg <= 6 ? pre_bp_kernel<6, 256, SWD_PRE_MINB, false> : (d->max_col_deg <= 8 ? pre_bp_kernel<8, 256, SWD_PRE_MINB, false> : pre_bp_kernel<16, 256, 2, false>);
+#define SWD_PRE_PICK(D, MT, MB) (ps ? (staged ? pre_bp_kernel<D, MT, MB, true, true> : pre_bp_kernel<D, MT, MB, true, false>) \
+                                    : (staged ? pre_bp_kernel<D, MT, MB, false, true> : pre_bp_kernel<D, MT, MB, false, false>))
+    if (ps) d->pre_fn = d->max_col_deg <= 8 ? SWD_PRE_PICK(8, 256, 2) : SWD_PRE_PICK(16, 256, 2);
+    else d->pre_fn = d->max_col_deg <= 6 ? SWD_PRE_PICK(6, 256, SWD_PRE_MINB) : (d->max_col_deg <= 8 ? SWD_PRE_PICK(8, 256, SWD_PRE_MINB) : SWD_PRE_PICK(16, 256, 2));
     st = occupancy(d->pre_fn, d->T1, S1.total, &occ);
     if (st) return st;
     if (occ * d->T1 < 512 && !getenv("SWD_T1")) {
         // shared memory allows fewer than 16 warps per SM with 256-thread CTAs: use one large CTA per SM instead
         const int want = std::min(1024, std::max(256, r32up(std::max((n + 3) / 4, m))));
-        pre_fn_t big = ps ? (d->max_col_deg <= 8 ? pre_bp_kernel<8, 1024, 1, true> : pre_bp_kernel<16, 1024, 1, true>)
-                          : (d->max_col_deg <= 6 ? pre_bp_kernel<6, 1024, 1, false> : (d->max_col_deg <= 8 ? pre_bp_kernel<8, 1024, 1, false> : pre_bp_kernel<16, 1024, 1, false>));
+        pre_fn_t big = d->max_col_deg <= 6 && !ps ? SWD_PRE_PICK(6, 1024, 1) : (d->max_col_deg <= 8 ? SWD_PRE_PICK(8, 1024, 1) : SWD_PRE_PICK(16, 1024, 1));
         int occ_big = 0;
         if ((st = occupancy(big, want, S1.total, &occ_big))) return st;
         if (occ_big * want > occ * d->T1) { d->pre_fn = big; d->T1 = want; occ = occ_big; }
     }
+#undef SWD_PRE_PICK
     if (occ < 1) { set_err("pre_bp_kernel does not fit"); return SWD_ERR_UNSUPPORTED; }
     d->grid1 = d->num_sm * occ;
     // ---- K2

@@ -66,6 +66,8 @@ struct GraphDev {               // static window graph (device pointers)
     const u16 *cpos;            // [nnz]  CSC entry -> CSR position
     const u16 *vord;            // [n]    columns in descending degree order (ownership order of the pre-BP kernel)
     const double *llr;          // [n]
+    const u32 *vrec;            // [n]    per ownership slot: first CSC entry | degree << 16   (pre-BP kernel)
+    const double *llr_s;        // [n]    llr in ownership-slot order
 };
 
 struct GdgDev {                 // parameters of the decimation tree

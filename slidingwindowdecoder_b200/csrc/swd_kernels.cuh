@@ -18,38 +18,75 @@
 // ----------------------------------------------------------------------------------------------
 // K1: full-window BP
 // ----------------------------------------------------------------------------------------------
-struct PreSmem { int off_msg, off_upar, off_synd, off_dec, off_misc, total; int off_fwd; };   // off_fwd: product-sum forward products
+struct PreSmem { int off_msg, off_upar, off_synd, off_dec, off_misc, total; int off_fwd; int off_vrec, off_cpos; };
+// off_fwd: product-sum forward products; off_vrec / off_cpos: staged copies of the static per-slot records and CSC->CSR map
 
 #ifndef SWD_PRE_MINB
 #define SWD_PRE_MINB 3
 #endif
+// one variable-node update of the full-window BP (bp_guessing_decoder.pyx:98-127): ordered prefix / suffix sums; the
+// hard decision goes to s_dec[sl] (ownership-slot order), parity contributions to upar
+template <int DM>
+__device__ __forceinline__ double pre_vn_update(double *msg, u32 *upar, const u16 *cpos, const u16 *__restrict__ cr, const double prior,
+                                                const int e0, const int d, const int dw, u8 *dec_slot) {
+    double cc[DM], pre[DM]; int pp[DM];
+    double t = prior;
+#pragma unroll
+    for (int k = 0; k < DM; k++) { if (k >= dw) break; if (k < d) { pp[k] = cpos[e0 + k]; cc[k] = msg[pp[k]]; } }
+#pragma unroll
+    for (int k = 0; k < DM; k++) { if (k >= dw) break; if (k < d) { pre[k] = t; t += cc[k]; } }
+    const int hard = (t <= 0.0);
+    *dec_slot = (u8)hard;
+    if (hard) {
+#pragma unroll 1
+        for (int k = 0; k < d; k++) atomicXor(&upar[cr[e0 + k]], 1u);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = DM - 1; k >= 0; k--) if (k < dw) { if (k < d) { msg[pp[k]] = pre[k] + s; s += cc[k]; } }
+    return t;
+}
+
 // MAXT = 256: several CTAs per SM (small windows).  MAXT = 1024: windows whose messages leave room for one CTA per
 // SM only (e.g. 576 x 4896, 136 KB) get one large CTA instead of eight warps per SM.
 // PS = true: product-sum check update (tanh products, forward / backward) instead of normalised min-sum.
-template <int DMAX, int MAXT, int MINB, bool PS>
+// STAGED = true: the per-slot records (first edge, degree) and the CSC->CSR map live in shared memory (copied once per
+// persistent CTA): the variable pass then chases vrec -> cpos -> msg through shared memory instead of
+// vord -> cp -> cpos through L1 (ncu r1g: long_scoreboard was the second largest stall of this kernel).
+template <int DMAX, int MAXT, int MINB, bool PS, bool STAGED>
 __global__ void __launch_bounds__(MAXT, MINB)
 pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter, double alpha,
               u8 *__restrict__ dec_out, u8 *__restrict__ conv_out, Workspace ws, double *hscratch,
               int full_hist, PreSmem S, int *iter_out, double *lpr_out) {
     extern __shared__ __align__(16) unsigned char smem[];
-    double *msg = (double *)(smem + S.off_msg);
-    u32 *upar = (u32 *)(smem + S.off_upar);
-    u8 *s_synd = smem + S.off_synd;
-    u8 *s_dec = smem + S.off_dec;
+    double *msg = pinned_smem<double>(smem + S.off_msg);
+    u32 *upar = pinned_smem<u32>(smem + S.off_upar);
+    u8 *s_synd = pinned_smem<u8>(smem + S.off_synd);
+    u8 *s_dec = pinned_smem<u8>(smem + S.off_dec);                 // hard decisions in ownership-slot order
     int *misc = (int *)(smem + S.off_misc);
     const int T = blockDim.x, tid = threadIdx.x;
     const int m = g.m, n = g.n;
-    double *hs = hscratch + (size_t)blockIdx.x * 4 * n;
+    double *hs = hscratch + (size_t)blockIdx.x * 4 * n;           // last four posteriors, ownership-slot order (coalesced)
     const double fpos = alpha;
     u64 edge_iters = 0;
+    const u32 *vrec = g.vrec; const u16 *cpos = g.cpos;
+    if (STAGED) {
+        u32 *sv = pinned_smem<u32>(smem + S.off_vrec); u16 *sc = pinned_smem<u16>(smem + S.off_cpos);
+        for (int i = tid; i < n; i += T) sv[i] = g.vrec[i];
+        for (int i = tid; i < g.nnz; i += T) sc[i] = g.cpos[i];
+        vrec = sv; cpos = sc;
+        __syncthreads();
+    }
 
     for (long long shot = blockIdx.x; shot < B; shot += gridDim.x) {
         for (int r = tid; r < m; r += T) s_synd[r] = synd[shot * m + r];
-        for (int v = tid; v < n; v += T) {                    // pyx:55-60
-            const int e0 = g.cp[v], e1 = g.cp[v + 1];
-            const double l = g.llr[v];
-            for (int e = e0; e < e1; e++) msg[g.cpos[e]] = l;
-            s_dec[v] = 0;
+        for (int sl = tid; sl < n; sl += T) {                  // pyx:55-60
+            const u32 vr = vrec[sl];
+            const int e0 = (int)(vr & 0xffffu), d = (int)(vr >> 16);
+            const double l = g.llr_s[sl];
+#pragma unroll 1
+            for (int k = 0; k < d; k++) msg[cpos[e0 + k]] = l;
+            s_dec[sl] = 0;
         }
         __syncthreads();
         int conv = 0, it = 0;
@@ -99,26 +136,15 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
             }
             __syncthreads();
             const bool keep = full_hist || (it >= max_iter - 4);
-            // ---- variable pass: columns are owned in degree order (g.vord), so a warp's loop bound is uniform
+            // ---- variable pass: columns are owned in degree order, so a warp's loop bound is uniform
             for (int base = 0; base < n; base += T) {
                 const int sl = base + tid;
-                int v = -1, e0 = 0, d = 0;
-                if (sl < n) { v = g.vord[sl]; e0 = g.cp[v]; d = g.cp[v + 1] - e0; }
+                int e0 = 0, d = 0;
+                if (sl < n) { const u32 vr = vrec[sl]; e0 = (int)(vr & 0xffffu); d = (int)(vr >> 16); }
                 const int dw = __reduce_max_sync(FULLMASK, d);
-                if (v >= 0) {
-                    double cc[DMAX], pre[DMAX]; int pp[DMAX];
-                    double t = g.llr[v];
-#pragma unroll
-                    for (int k = 0; k < DMAX; k++) { if (k >= dw) break; if (k < d) { pp[k] = g.cpos[e0 + k]; cc[k] = msg[pp[k]]; } }
-#pragma unroll
-                    for (int k = 0; k < DMAX; k++) { if (k >= dw) break; if (k < d) { pre[k] = t; t += cc[k]; } }
-                    if (keep) hs[(size_t)(it & 3) * n + v] = t;
-                    const int hard = (t <= 0.0);
-                    s_dec[v] = (u8)hard;
-                    if (hard) for (int k = 0; k < d; k++) atomicXor(&upar[g.cr[e0 + k]], 1u);
-                    double s = 0.0;
-#pragma unroll
-                    for (int k = DMAX - 1; k >= 0; k--) if (k < d) { msg[pp[k]] = pre[k] + s; s += cc[k]; }
+                if (sl < n) {
+                    const double t = pre_vn_update<DMAX>(msg, upar, cpos, g.cr, g.llr_s[sl], e0, d, dw, s_dec + sl);
+                    if (keep) hs[(size_t)(it & 3) * n + sl] = t;
                 }
             }
             edge_iters += 1;
@@ -127,7 +153,7 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
             for (int r = tid; r < m; r += T) mism |= (upar[r] != (u32)s_synd[r]);
             if (!__syncthreads_or(mism)) { conv = 1; it++; break; }
         }
-        for (int v = tid; v < n; v += T) dec_out[shot * n + v] = s_dec[v];
+        for (int sl = tid; sl < n; sl += T) dec_out[shot * n + g.vord[sl]] = s_dec[sl];
         if (tid == 0) {
             conv_out[shot] = (u8)conv;
             if (iter_out) iter_out[shot] = it;
@@ -136,14 +162,15 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
         __syncthreads();
         if (!conv || lpr_out) {
             const int slot = misc[0];
-            for (int v = tid; v < n; v += T) {
+            for (int sl = tid; sl < n; sl += T) {
+                const int v = g.vord[sl];
                 double h4[4];
 #pragma unroll
                 for (int s = 0; s < 4; s++) {
                     // slots never written in this call are 0 (fresh ring); `it` iterations were executed
                     // (with full_hist all of them were stored, otherwise only the last four of max_iter).
                     const bool written = (s < it);
-                    h4[s] = written ? hs[(size_t)s * n + v] : 0.0;
+                    h4[s] = written ? hs[(size_t)s * n + sl] : 0.0;
                 }
                 if (!conv) {
                     ws.sum[(size_t)slot * n + v] = ((h4[0] + h4[1]) + h4[2]) + h4[3];
