@@ -40,6 +40,16 @@ WORKLOADS = {
                    kw=dict(pre_max_iter=8, post_max_iter=200, osd_method="osd_cs", osd_order=10),
                    name="[[288,12,18]] circuit-level p=0.003, 18 rounds, sliding window W=4 F=1 (16 windows), BP+OSD-CS10 per window",
                    decoder_name="osd_window(pre_max_iter=8, post_max_iter=200, osd_cs, order 10)"),
+    # configs[4]: SHYPS r=3 memory experiment (SHYPS.ipynb cell 1: windows without merged identity columns), GDG and BP+OSD
+    "c5_gdg": dict(code="shyps", r=3, p=0.003, rounds=6, W=3, F=1, method=0, decoder="gdg",
+                   kw=dict(max_iter=8, max_iter_per_step=6, max_step=25, max_tree_depth=3, max_side_depth=10,
+                           max_tree_branch_step=10, max_side_branch_step=10, multi_thread=True, low_error_mode=False),
+                   name="SHYPS r=3 memory experiment p=0.003, 6 rounds, sliding window W=3 F=1, GDG per window",
+                   decoder_name="bpgdg_decoder(max_iter=8, multi_thread=True, defaults)"),
+    "c5_osd": dict(code="shyps", r=3, p=0.003, rounds=6, W=3, F=1, method=0, decoder="osd",
+                   kw=dict(pre_max_iter=8, post_max_iter=100, osd_method="osd_cs", osd_order=10),
+                   name="SHYPS r=3 memory experiment p=0.003, 6 rounds, sliding window W=3 F=1, BP+OSD-CS10 per window",
+                   decoder_name="osd_window(pre_max_iter=8, post_max_iter=100, osd_cs, order 10)"),
 }
 WL = WORKLOADS["c3_gdg"]
 METRIC = {"gdg": "decoded shots/sec (sliding-window GDG)", "osd": "decoded shots/sec (sliding-window BP+OSD)"}
@@ -54,6 +64,11 @@ def build_plan():
     from slidingwindowdecoder_b200.codes import bb_code
     from slidingwindowdecoder_b200.dem import bb_memory_circuit, detector_error_model, dem_to_check_matrices
     from slidingwindowdecoder_b200.windows import build_windows
+    if WL.get("code") == "shyps":
+        from slidingwindowdecoder_b200.dem import shyps_memory_circuit
+        r = WL["r"]
+        chk, obs, pri = dem_to_check_matrices(detector_error_model(shyps_memory_circuit(r, WL["p"], WL["rounds"])))
+        return build_windows(chk, obs, pri, h=r * (2 ** r - 1), W=WL["W"], F=WL["F"], method=WL["method"])
     code, A, B = bb_code(WL["N"])
     circ = bb_memory_circuit(code, A, B, WL["p"], WL["rounds"], z_basis=True)
     chk, obs, pri = dem_to_check_matrices(detector_error_model(circ))

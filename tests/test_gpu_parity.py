@@ -458,3 +458,35 @@ def test_product_sum_bposd_matches_oracle_within_tolerance(oracle_mod):
     # every OSD output reproduces its syndrome (window matrices have full row rank)
     resid = np.asarray((H @ corr.T.astype(np.int32)).T % 2).astype(np.uint8)
     assert np.array_equal(resid, synd)
+
+
+@pytest.mark.parametrize("decoder", ["gdg", "osd"])
+def test_shyps_sliding_window_driver_matches_reference_loop(decoder, oracle_mod):
+    """BASELINE configs[4]: SHYPS r=3 memory experiment, (3,1) windows without merged identity columns (SHYPS.ipynb cell 1),
+    GDG and BP+OSD-CS10 per window: device pipeline vs the reference's loop run with the oracle, exact."""
+    import bench
+    from slidingwindowdecoder_b200.sliding_window import SlidingWindowDecoder, sample_dem
+    bench.select_workload("c5_gdg" if decoder == "gdg" else "c5_osd")
+    try:
+        plan = bench.build_plan()
+        kw = bench.WL["kw"]
+        det, ob, _ = sample_dem(plan.chk, plan.obs, plan.priors, 1200, np.random.default_rng(31))
+        swd = SlidingWindowDecoder(plan, decoder=decoder, streams=2, **kw)
+        res = swd.decode(det, ob, return_corrections=True)
+        oracles = {}
+
+        def decode_window(w, synd):
+            if w.index not in oracles:
+                oracles[w.index] = oracle_mod.Oracle(w.mat, w.prior)
+            if decoder == "gdg":
+                d, c, _, _ = oracles[w.index].bpgdg_batch(synd, **kw)
+            else:
+                d, c, _, _ = oracles[w.index].osd_window_batch(synd, **kw)
+            return d, c
+
+        ref = oracle_mod.sliding_window_reference(plan, det, ob, decode_window)
+        assert np.array_equal(res["total_e_hat"], ref["total_e_hat"].astype(np.uint8))
+        assert res["flagged"] == int(ref["flagged"].sum()) and res["failed"] == int(ref["failed"].sum())
+        assert res["window_unconverged"] == ref["window_unconverged"]
+    finally:
+        bench.select_workload("c3_gdg")
