@@ -490,3 +490,37 @@ def test_shyps_sliding_window_driver_matches_reference_loop(decoder, oracle_mod)
         assert res["window_unconverged"] == ref["window_unconverged"]
     finally:
         bench.select_workload("c3_gdg")
+
+
+def test_x_basis_osd_windows_match_reference_loop(oracle_mod):
+    """osd.py:83,106: x-basis memory experiment, windows keep n (not 3h) un-merged columns of the next round; BP+OSD-CS10
+    per window through the device pipeline vs the reference loop with the oracle, exact.  Also covers the
+    single-tier launch sequence used for small batches (latency mode): a batch of 8 shots gives identical corrections."""
+    from slidingwindowdecoder_b200.codes import bb_code
+    from slidingwindowdecoder_b200.dem import bb_memory_circuit, detector_error_model, dem_to_check_matrices
+    from slidingwindowdecoder_b200.windows import build_windows
+    from slidingwindowdecoder_b200.sliding_window import SlidingWindowDecoder, sample_dem
+    code, A, B = bb_code(72)
+    chk, obs, pri = dem_to_check_matrices(detector_error_model(bb_memory_circuit(code, A, B, 0.003, 6, z_basis=False)))
+    plan = build_windows(chk, obs, pri, code.N, W=3, F=1, method=1, keep_cols=code.N)
+    det, ob, _ = sample_dem(plan.chk, plan.obs, plan.priors, 1000, np.random.default_rng(41))
+    kw = dict(pre_max_iter=8, post_max_iter=200, osd_method="osd_cs", osd_order=10)
+    swd = SlidingWindowDecoder(plan, decoder="osd", **kw)
+    res = swd.decode(det, ob, return_corrections=True)
+    oracles = {}
+
+    def decode_window(w, synd):
+        if w.index not in oracles:
+            oracles[w.index] = oracle_mod.Oracle(w.mat, w.prior)
+        d, c, _, _ = oracles[w.index].osd_window_batch(synd, **kw)
+        return d, c
+
+    ref = oracle_mod.sliding_window_reference(plan, det, ob, decode_window)
+    assert np.array_equal(res["total_e_hat"], ref["total_e_hat"].astype(np.uint8))
+    assert res["failed"] == int(ref["failed"].sum())
+    small = swd.decode(det[:8], ob[:8], return_corrections=True)
+    assert np.array_equal(small["total_e_hat"], res["total_e_hat"][:8])
+    gdg = SlidingWindowDecoder(plan, decoder="gdg", max_iter=8, multi_thread=True)
+    big = gdg.decode(det, ob, return_corrections=True)
+    few = gdg.decode(det[:8], ob[:8], return_corrections=True)
+    assert np.array_equal(few["total_e_hat"], big["total_e_hat"][:8])
