@@ -40,6 +40,14 @@ WORKLOADS = {
                    kw=dict(pre_max_iter=8, post_max_iter=200, osd_method="osd_cs", osd_order=10),
                    name="[[288,12,18]] circuit-level p=0.003, 18 rounds, sliding window W=4 F=1 (16 windows), BP+OSD-CS10 per window",
                    decoder_name="osd_window(pre_max_iter=8, post_max_iter=200, osd_cs, order 10)"),
+    # configs[0]: code capacity, the reference's own CPU-runnable case (src/simulation.py:10-99 with its GDG kwargs :66-82);
+    # one "window" = the whole hx, observables = hz_perp (logical check of simulation.py:90-91)
+    "c1_gdg": dict(code="capacity", N=72, p=0.05, decoder="gdg",
+                   kw=dict(max_iter_per_step=6, gdg_factor=0.625, max_step=40, max_tree_depth=4, max_side_depth=20,
+                           max_tree_branch_step=30, max_side_branch_step=20, multi_thread=True, low_error_mode=True,
+                           max_iter=24, ms_scaling_factor=0.625, new_n=72),
+                   name="[[72,12,6]] BB code, code-capacity data-qubit noise p=0.05, GDG decode via simulation.py",
+                   decoder_name="bpgdg_decoder(simulation.py:66-82 kwargs, multi_thread=True)"),
     # configs[4]: SHYPS r=3 memory experiment (SHYPS.ipynb cell 1: windows without merged identity columns), GDG and BP+OSD
     "c5_gdg": dict(code="shyps", r=3, p=0.003, rounds=6, W=3, F=1, method=0, decoder="gdg",
                    kw=dict(max_iter=8, max_iter_per_step=6, max_step=25, max_tree_depth=3, max_side_depth=10,
@@ -64,6 +72,14 @@ def build_plan():
     from slidingwindowdecoder_b200.codes import bb_code
     from slidingwindowdecoder_b200.dem import bb_memory_circuit, detector_error_model, dem_to_check_matrices
     from slidingwindowdecoder_b200.windows import build_windows
+    if WL.get("code") == "capacity":
+        from scipy.sparse import csc_matrix
+        from slidingwindowdecoder_b200.windows import WindowPlan, Window
+        code, _, _ = bb_code(WL["N"])
+        hx, lz = csc_matrix(code.hx), csc_matrix(code.hz_perp)
+        pri = np.full(code.N, WL["p"])
+        win = Window(0, hx, pri, 0, hx.shape[0], 0, code.N, code.N, True)
+        return WindowPlan(hx, lz, pri, [(0, 0), (hx.shape[0], code.N)], [win], code.N // 2, 1, 1)
     if WL.get("code") == "shyps":
         from slidingwindowdecoder_b200.dem import shyps_memory_circuit
         r = WL["r"]
