@@ -94,8 +94,36 @@ def shyps_section(bpgdg_decoder, osd_window):
         save(f"c5_w{wi}_gdg_mt1", w.mat, w.prior, s, kw, dec=d, conv=c)
 
 
+def c4_section(bpgdg_decoder, osd_window):
+    """C4: [[288,12,18]] circuit level p = 0.003, 18 rounds, (4,1): a middle window 576 x 4896 (BASELINE configs[3]),
+    BP+OSD-CS10 (the configuration's decoder) and multi-thread GDG."""
+    from slidingwindowdecoder_b200.codes import bb_code
+    from slidingwindowdecoder_b200.dem import bb_memory_circuit, detector_error_model, dem_to_check_matrices
+    from slidingwindowdecoder_b200.windows import build_windows
+    from slidingwindowdecoder_b200.sliding_window import sample_dem
+    code, A, B = bb_code(288)
+    chk, obs, pri = dem_to_check_matrices(detector_error_model(bb_memory_circuit(code, A, B, 0.003, 18, z_basis=True)))
+    plan = build_windows(chk, obs, pri, code.N, W=4, F=1, method=1)
+    det, ob, _ = sample_dem(plan.chk, plan.obs, plan.priors, 400, np.random.default_rng(288))
+    w = plan.windows[7]
+    s = det[:, w.row0:w.row1]
+    s = s[np.nonzero(s.any(axis=1))[0][:120]]
+    kw = dict(pre_max_iter=8, post_max_iter=200, ms_scaling_factor=1.0, osd_method="osd_cs", osd_order=10)
+    save("c4_w7_osdw_cs10", w.mat, w.prior, s, kw, **run_osd(osd_window, w.mat, w.prior, s, kw))
+    kw = dict(max_iter=8, multi_thread=True)
+    d, c = run_gdg(bpgdg_decoder, w.mat, w.prior, s[:80], kw)
+    save("c4_w7_gdg_mt1", w.mat, w.prior, s[:80], kw, dec=d, conv=c)
+
+
 def main():
     build_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "c4":
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 2)
+        from src.bp_guessing_decoder import bpgdg_decoder
+        from src.osd_window import osd_window
+        c4_section(bpgdg_decoder, osd_window)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "shyps":
         devnull = os.open(os.devnull, os.O_WRONLY)
         os.dup2(devnull, 2)
@@ -179,6 +207,7 @@ def main():
     kw = dict(pre_max_iter=8, post_max_iter=100, ms_scaling_factor=1.0, osd_method="osd_cs", osd_order=10)
     save("c3_w5_osdw_cs10", w.mat, w.prior, s, kw, **run_osd(osd_window, w.mat, w.prior, s, kw))
     shyps_section(bpgdg_decoder, osd_window)
+    c4_section(bpgdg_decoder, osd_window)
 
 
 if __name__ == "__main__":
