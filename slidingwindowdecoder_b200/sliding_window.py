@@ -91,6 +91,10 @@ class SlidingWindowDecoder:
         if w is not None and w.value:
             self.lib.swd_window_destroy(w)
             self._win = C.c_void_p()
+        for h, _, _ in getattr(self, "_res_win", {}).values():
+            if h.value:
+                self.lib.swd_window_destroy(h)
+        self.__dict__["_res_win"] = {}
 
     def sample_device(self, shots, seed=0, shot_offset=0, return_errors=False):
         """Draw `shots` DEM samples on the device (Philox, one Bernoulli per DEM column; the stand-in for
@@ -120,12 +124,27 @@ class SlidingWindowDecoder:
                     seen.add(id(d)); out.append(d)
         return out
 
-    def _run_windows(self, det, obs, decs, total, window_events, osd_dec=None):
+    def _residual_window(self, w, dec):
+        """swd_window handle over one window matrix (cached per decoder): lets the commit / count kernels evaluate
+        `(mat @ e_hat + detector_win) % 2` of osd.py:168."""
+        cache = self.__dict__.setdefault("_res_win", {})
+        if id(dec) not in cache:
+            A = w.mat.tocsc(); A.sort_indices()
+            cp = np.ascontiguousarray(A.indptr, dtype=np.int32); ri = np.ascontiguousarray(A.indices, dtype=np.int32)
+            h = C.c_void_p()
+            i32p = C.POINTER(C.c_int32)
+            _lib.check(self.lib.swd_window_create(self.device, A.shape[0], A.shape[1], cp.ctypes.data_as(i32p), ri.ctypes.data_as(i32p),
+                                                  0, None, None, C.byref(h)), "swd_window_create")
+            cache[id(dec)] = (h, cp, ri)
+        return cache[id(dec)][0]
+
+    def _run_windows(self, det, obs, decs, total, window_events, osd_dec=None, residuals=False):
         """The window loop for one (sub-)batch on the current stream; det / obs are updated in place."""
         torch = self.torch
         B = det.shape[0]
         stream = C.c_void_p(torch.cuda.current_stream(det.device).cuda_stream)
         unconv = []
+        flagged = []
         counts_osd = None
         for w, dec in zip(self.plan.windows, decs):
             m = w.row1 - w.row0
@@ -146,6 +165,13 @@ class SlidingWindowDecoder:
             if window_events is not None:
                 window_events[w.index][1].record()
             n_win = corr.shape[1]
+            if residuals:                       # shots whose correction does not reproduce the window syndrome (osd.py:168)
+                rw = self._residual_window(w, dec)
+                resid = synd.clone()
+                _lib.check(self.lib.swd_window_commit(rw, corr.data_ptr(), B, n_win, 0, n_win, resid.data_ptr(), None, stream), "residual")
+                c2 = torch.zeros(2, dtype=torch.int64, device=det.device)
+                _lib.check(self.lib.swd_window_count_failures(rw, resid.data_ptr(), None, B, c2.data_ptr(), stream), "residual count")
+                flagged.append(c2[0])
             _lib.check(self.lib.swd_window_commit(self._win, corr.data_ptr(), B, n_win, w.col0, w.ncommit, det.data_ptr(),
                                                   obs.data_ptr() if self.num_obs else None, stream), "commit")
             unconv.append((B - conv.sum(dtype=torch.int64)))
@@ -154,9 +180,9 @@ class SlidingWindowDecoder:
         counts = torch.zeros(2, dtype=torch.int64, device=det.device)
         _lib.check(self.lib.swd_window_count_failures(self._win, det.data_ptr(), obs.data_ptr() if self.num_obs else None, B,
                                                       counts.data_ptr(), stream), "count")
-        return counts, torch.stack(unconv), counts_osd
+        return counts, torch.stack(unconv), counts_osd, (torch.stack(flagged) if residuals else None)
 
-    def decode_device(self, det, obs, return_corrections=False, window_events=None, streams=None):
+    def decode_device(self, det, obs, return_corrections=False, window_events=None, streams=None, window_residuals=False):
         """det [B, num_det], obs [B, num_obs]: torch CUDA uint8 tensors, MODIFIED IN PLACE into the residual
         syndrome / residual observables.  Returns dict with device tensors:
           counts uint64[2] = (flagged shots, failed shots), window_unconverged int64[num_win].
@@ -168,8 +194,8 @@ class SlidingWindowDecoder:
         if window_events is not None or B < 2 * ns:
             ns = 1
         if ns == 1:
-            counts, unconv, counts_osd = self._run_windows(det, obs, self.decoders, total, window_events,
-                                                           self.last_osd[0] if self.last_osd else None)
+            counts, unconv, counts_osd, wflag = self._run_windows(det, obs, self.decoders, total, window_events,
+                                                                  self.last_osd[0] if self.last_osd else None, window_residuals)
         else:
             if self._side_streams is None:
                 self._side_streams = [torch.cuda.Stream(device=det.device) for _ in range(self.nstreams)]
@@ -183,7 +209,7 @@ class SlidingWindowDecoder:
                 with torch.cuda.stream(st):
                     parts.append(self._run_windows(det[lo:hi], obs[lo:hi], self.decoder_sets[i],
                                                    None if total is None else total[lo:hi], None,
-                                                   self.last_osd[i] if self.last_osd else None))
+                                                   self.last_osd[i] if self.last_osd else None, window_residuals))
                 for t in (det, obs, total):
                     if t is not None:
                         t.record_stream(st)
@@ -192,7 +218,10 @@ class SlidingWindowDecoder:
             counts = sum(p[0] for p in parts)
             unconv = sum(p[1] for p in parts)
             counts_osd = sum(p[2] for p in parts) if self.last_osd else None
+            wflag = sum(p[3] for p in parts) if window_residuals else None
         out = dict(counts=counts, window_unconverged=unconv)
+        if window_residuals:
+            out["window_flagged"] = wflag                   # per window: shots with mat @ e_hat != window syndrome
         if counts_osd is not None:
             out["counts_last_window_osd"] = counts_osd      # (flagged, failed) when the last window is decoded by BP + OSD
         if return_corrections:

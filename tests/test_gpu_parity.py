@@ -524,3 +524,49 @@ def test_x_basis_osd_windows_match_reference_loop(oracle_mod):
     big = gdg.decode(det, ob, return_corrections=True)
     few = gdg.decode(det[:8], ob[:8], return_corrections=True)
     assert np.array_equal(few["total_e_hat"], big["total_e_hat"][:8])
+
+
+def test_reference_driver_functions(oracle_mod, capsys):
+    """guessing.py / osd.py as functions with their own signatures (drivers.py): the printed statistics equal what the
+    reference's loops give when run with the oracle on the same (device-sampled) shots."""
+    from slidingwindowdecoder_b200.drivers import sliding_window_decoder, sliding_window_osd_decoder, _plan
+    from oracle.philox import sample_dem
+    shots, seed = 500, 5
+    res = sliding_window_decoder(72, p=0.004, num_repeat=5, num_shots=shots, max_iter=8, W=3, F=1, seed=seed)
+    text = capsys.readouterr().out
+    assert "Window 0, flagged Errors:" in text and "last round osd True" in text and "logical error per round:" in text
+    code, plan = _plan(72, 0.004, 5, 3, 1, True, None, 1)
+    det, ob, _ = sample_dem(plan.chk, plan.obs, plan.priors, shots, seed=seed)
+    kw = dict(max_iter=8, multi_thread=True, max_tree_branch_step=10)
+    oracles = {}
+
+    def decode_window(w, synd):
+        if w.index not in oracles:
+            oracles[w.index] = oracle_mod.Oracle(w.mat, w.prior)
+        d, c, _, _ = oracles[w.index].bpgdg_batch(synd, **kw)
+        return d, c
+
+    ref = oracle_mod.sliding_window_reference(plan, det, ob, decode_window)
+    assert res["gdg"]["num_flagged"] == int(ref["flagged"].sum()) and res["gdg"]["num_logical"] == int(ref["failed"].sum())
+    assert res["window_flagged"] == ref["window_unconverged"]
+    assert sliding_window_decoder(73) is None                              # "unsupported N"
+    # osd.py, shorten=True: osd_window(pre 8, post max_iter, osd_cs, order 0) per window, W=2, method=0
+    r2 = sliding_window_osd_decoder(72, p=0.004, num_repeat=5, num_shots=shots, max_iter=50, W=2, F=1, method=0, shorten=True, seed=seed)
+    code, plan2 = _plan(72, 0.004, 5, 2, 1, True, None, 0)
+    det2, ob2, _ = sample_dem(plan2.chk, plan2.obs, plan2.priors, shots, seed=seed)
+    kw2 = dict(pre_max_iter=8, post_max_iter=50, ms_scaling_factor=1.0, osd_method="osd_cs", osd_order=0)
+    orc2, flagged = {}, []
+
+    def decode_window2(w, synd):
+        if w.index not in orc2:
+            orc2[w.index] = oracle_mod.Oracle(w.mat, w.prior)
+        d, c, _, _ = orc2[w.index].osd_window_batch(synd, **kw2)
+        H = np.asarray(w.mat.todense()).astype(np.int64)
+        flagged.append(int((((d.astype(np.int64) @ H.T) + np.asarray(synd).astype(np.int64)) % 2).any(axis=1).sum()))
+        return d, c
+
+    ref2 = oracle_mod.sliding_window_reference(plan2, det2, ob2, decode_window2)
+    assert r2["num_logical"] == int(ref2["failed"].sum()) and r2["num_flagged"] == int(ref2["flagged"].sum())
+    assert r2["window_flagged"] == flagged
+    r3 = sliding_window_osd_decoder(72, p=0.004, num_repeat=5, num_shots=shots, max_iter=30, W=2, F=1, method=0, shorten=False, seed=seed)
+    assert r3["window_flagged"] == [0] * len(plan2.windows)                   # OSD always reproduces the window syndrome
