@@ -211,6 +211,41 @@ class Oracle:
         return dec, conv, pm, st
 
 
+class Bp4Oracle:
+    """bp4_osd (bp4_osd.pyx) on the CPU: quaternary BP over (Hx, Hz) + OSD per basis."""
+
+    def __init__(self, Hx, Hz, channel_probs_x, channel_probs_y, channel_probs_z):
+        import math
+        self.mx, self.n, self.cpx, self.crx = csc_arrays(Hx)
+        self.mz, n2, self.cpz, self.crz = csc_arrays(Hz)
+        assert n2 == self.n
+        px, py, pz = (np.asarray(a, dtype=np.float64) for a in (channel_probs_x, channel_probs_y, channel_probs_z))
+        self.llrx = np.array([math.log((1.0 - (px[v] + py[v] + pz[v])) / px[v]) for v in range(self.n)])
+        self.llry = np.array([math.log((1.0 - (px[v] + py[v] + pz[v])) / py[v]) for v in range(self.n)])
+        self.llrz = np.array([math.log((1.0 - (px[v] + py[v] + pz[v])) / pz[v]) for v in range(self.n)])
+        self.prior_x = np.array([math.log((1.0 - (px[v] + py[v])) / (px[v] + py[v])) for v in range(self.n)])
+        self.prior_z = np.array([math.log((1.0 - (pz[v] + py[v])) / (pz[v] + py[v])) for v in range(self.n)])
+        L = lib()
+        self.rank_x = L.orc_gf2_rank(self.mx, self.n, _p(self.cpx, C.c_int), _p(self.crx, C.c_int))
+        self.rank_z = L.orc_gf2_rank(self.mz, self.n, _p(self.cpz, C.c_int), _p(self.crz, C.c_int))
+
+    def decode(self, synd_x, synd_z, max_iter=32, ms_scaling_factor=1.0, osd_method="osd_0", osd_order=0):
+        """-> dict(dec [2, n], converge, bp_decoding [2, n], osd0 [2, n], log_prob_ratios [n, 3], bp_iteration)"""
+        sx = np.ascontiguousarray(np.asarray(synd_x).astype(np.int8)); sz = np.ascontiguousarray(np.asarray(synd_z).astype(np.int8))
+        meth = _OSD_METHODS[str(osd_method).lower()]
+        n = self.n
+        dec, bp, o0 = (np.zeros(2 * n, dtype=np.int8) for _ in range(3))
+        lpr = np.zeros((n, 3)); it = C.c_int(0)
+        conv = lib().orc_bp4_osd_decode(self.mx, self.mz, n, _p(self.cpx, C.c_int), _p(self.crx, C.c_int), _p(self.cpz, C.c_int),
+                                        _p(self.crz, C.c_int), _p(self.llrx, C.c_double), _p(self.llry, C.c_double),
+                                        _p(self.llrz, C.c_double), _p(self.prior_x, C.c_double), _p(self.prior_z, C.c_double),
+                                        _p(sx, C.c_int8), _p(sz, C.c_int8), int(max_iter), C.c_double(ms_scaling_factor), meth,
+                                        0 if meth == 0 else int(osd_order), self.rank_x, self.rank_z, _p(dec, C.c_int8),
+                                        _p(bp, C.c_int8), _p(o0, C.c_int8), _p(lpr, C.c_double), C.byref(it))
+        return dict(dec=dec.reshape(2, n), converge=int(conv), bp_decoding=bp.reshape(2, n), osd0=o0.reshape(2, n),
+                    log_prob_ratios=lpr, bp_iteration=it.value)
+
+
 def sliding_window_reference(plan, det, obs, decode_window):
     """The reference's window loop (guessing.py:141-227) in dense numpy, for tests.
     decode_window(window, synd[B, m]) -> (corr[B, n_win], conv[B]).

@@ -810,17 +810,26 @@ static void basis_solve(const gf2_basis *b, const uint64_t *g, int8_t *x, uint64
 
 /* osd_window.osd, osd_window.pyx:201-284 (+ mod2sparse_extra.cpp:78-376).
  * cur_vn: -1 undecided / 0 / 1.  Writes osd0 and osdw, returns min_pm. */
+static double osd_run_keys(const graph *g, const double *llr, const int8_t *synd, double *key,
+                           const orc_osd_params *P, int rank, int nn, int8_t *osd0, int8_t *osdw);
 static double osd_run(const graph *g, const double *llr, const int8_t *synd, const int8_t *cur_vn,
                       const double *hist, const orc_osd_params *P, int rank, int nn,
                       int8_t *osd0, int8_t *osdw) {
-    int m = g->m, n = g->n;
+    int n = g->n;
     double *key = (double *)malloc(sizeof(double) * (n + 1));
-    int *order = (int *)malloc(sizeof(int) * (n + 1));
     for (int v = 0; v < n; v++) {
         if (cur_vn[v] == 1) key[v] = -1000;
         else if (cur_vn[v] == 0) key[v] = 1000;
         else key[v] = hist[4 * v] + hist[4 * v + 1] + hist[4 * v + 2] + hist[4 * v + 3];
     }
+    return osd_run_keys(g, llr, synd, key, P, rank, nn, osd0, osdw);     /* frees key */
+}
+/* the OSD proper for a given column ranking key (ascending = most likely in error first); also what bp4_osd.osd
+ * does (bp4_osd.pyx:261-368) with key = llr_post */
+static double osd_run_keys(const graph *g, const double *llr, const int8_t *synd, double *key,
+                           const orc_osd_params *P, int rank, int nn, int8_t *osd0, int8_t *osdw) {
+    int m = g->m, n = g->n;
+    int *order = (int *)malloc(sizeof(int) * (n + 1));
     orc_index_sort(key, n, order);
     gf2_basis *b = basis_new(m, rank);
     uint64_t *tv = (uint64_t *)malloc(8 * (b->W + 1)), *tc = (uint64_t *)malloc(8 * (b->R + 1));
@@ -831,7 +840,7 @@ static double osd_run(const graph *g, const double *llr, const int8_t *synd, con
         if (basis_add(b, g->cr + g->cp[c], g->cp[c + 1] - g->cp[c], c, tv, tc)) is_piv[c] = 1;
     }
     for (int c = 0; c < m; c++) if (synd[c]) sv[c >> 6] |= 1ull << (c & 63);
-    memset(osd0, 0, n);
+    memset(osd0, 0, (size_t)(n > 0 ? n : 0));
     basis_solve(b, sv, osd0, tv, tc);
     double min_pm = 0.0;
     for (int v = 0; v < n; v++) { if (osd0[v]) min_pm += llr[v]; osdw[v] = osd0[v]; }
@@ -1009,4 +1018,112 @@ void orc_osd_window_decode_batch(int m, int n, const int *cp, const int *cr, con
         if (pm) pm[b] = p;
         if (sum) stats_add(sum, &s);
     }
+}
+
+/* ------------------------------------------------------------ bp4_osd -- */
+/* bpgd.cpp:399-416 */
+static double b4_log1pexp(double x) {
+    if (x > -log(2.220446049250313e-16)) return x + log1p(exp(-x));
+    return log1p(exp(x));
+}
+static double b4_logaddexp(double x, double y) {
+    const double tmp = x - y;
+    if (x == y) return x + 0.69314718055994530942;      /* M_LN2 */
+    if (tmp > 0) return x + b4_log1pexp(-tmp);
+    else if (tmp <= 0) return y + b4_log1pexp(tmp);
+    return tmp;
+}
+/* bp4_osd.cn_update_all (bp4_osd.pyx:483-529): unmasked normalised min-sum on one of the two graphs */
+static void b4_cn_update(const graph *g, const int8_t *synd, double alpha, double *b2c, double *c2b) {
+    for (int c = 0; c < g->m; c++) {
+        double m1 = BIG, m2 = BIG; int arg = -1; int par = (synd[c] == 1);
+        for (int p = g->rp[c]; p < g->rp[c + 1]; p++) {
+            double b = b2c[p];
+            if (b > CLIP) b = CLIP; else if (b < -CLIP) b = -CLIP;
+            b2c[p] = b;
+            double a = fabs(b);
+            if (a < m1) { m2 = m1; m1 = a; arg = p; } else if (a < m2) m2 = a;
+            if (b <= 0) par ^= 1;
+        }
+        for (int p = g->rp[c]; p < g->rp[c + 1]; p++) {
+            double mag = (p == arg) ? m2 : m1;
+            int sg = par ^ (b2c[p] <= 0);
+            c2b[p] = mag * ((sg ? -1.0 : 1.0) * alpha);
+        }
+    }
+}
+/* bp4_osd.decode (bp4_osd.pyx:197-221): quaternary BP over (Hx, Hz) + one OSD per basis.
+ * llr*: channel LLRs log((1-px-py-pz)/p*), prior_llr_x/z: log((1-(px+py))/(px+py)) resp. (pz+py) (pyx:123-133),
+ * computed by the caller with libm.  dec / bp_dec / osd0: [2n] = x part then z part.  lpr: [n][3] (x, y, z).
+ * Returns converge.  camel_decode is not restated. */
+int orc_bp4_osd_decode(int mx, int mz, int n, const int *cpx, const int *crx, const int *cpz, const int *crz,
+                       const double *llrx, const double *llry, const double *llrz,
+                       const double *prior_llr_x, const double *prior_llr_z,
+                       const int8_t *synd_x, const int8_t *synd_z, int max_iter, double alpha,
+                       int osd_method, int osd_order, int rank_x, int rank_z,
+                       int8_t *dec, int8_t *bp_dec, int8_t *osd0, double *lpr, int *bp_iter_out) {
+    graph *gx = graph_build(mx, n, cpx, crx, NULL), *gz = graph_build(mz, n, cpz, crz, NULL);
+    double *b2cx = (double *)calloc(gx->nnz + 1, 8), *c2bx = (double *)calloc(gx->nnz + 1, 8);
+    double *b2cz = (double *)calloc(gz->nnz + 1, 8), *c2bz = (double *)calloc(gz->nnz + 1, 8);
+    int8_t *bx = bp_dec, *bz = bp_dec + n;
+    int8_t *tsx = (int8_t *)malloc(mx + 1), *tsz = (int8_t *)malloc(mz + 1);
+    memset(bp_dec, 0, 2 * (size_t)n); memset(osd0, 0, 2 * (size_t)n);
+    for (int v = 0; v < n; v++) {                                   /* bp_init, pyx:425-442 */
+        double msg_x = b4_log1pexp(-1. * llrx[v]) - b4_logaddexp(-1. * llry[v], -1. * llrz[v]);
+        double msg_z = b4_log1pexp(-1. * llrz[v]) - b4_logaddexp(-1. * llry[v], -1. * llrz[v]);   /* sic (pyx:438) */
+        for (int e = gx->cp[v]; e < gx->cp[v + 1]; e++) b2cx[gx->c2r[e]] = msg_x;
+        for (int e = gz->cp[v]; e < gz->cp[v + 1]; e++) b2cz[gz->c2r[e]] = msg_z;
+    }
+    int conv = 0, it = 0;
+    for (int iter = 0; iter < max_iter; iter++) {
+        it++;
+        b4_cn_update(gx, synd_x, alpha, b2cx, c2bx);
+        b4_cn_update(gz, synd_z, alpha, b2cz, c2bz);
+        for (int v = 0; v < n; v++) {                               /* vn_update, pyx:533-591 */
+            double llrx_hx = 0.0, llrz_hz = 0.0;
+            for (int e = gz->cp[v]; e < gz->cp[v + 1]; e++) llrx_hx += c2bz[gz->c2r[e]];
+            for (int e = gx->cp[v]; e < gx->cp[v + 1]; e++) llrz_hz += c2bx[gx->c2r[e]];
+            double llry_all = llrx_hx + llrz_hz + llry[v];
+            llrx_hx = llrx_hx + llrx[v];
+            llrz_hz = llrz_hz + llrz[v];
+            lpr[3 * v] = llrx_hx; lpr[3 * v + 1] = llry_all; lpr[3 * v + 2] = llrz_hz;
+            int idx;
+            if (0 < llrx_hx && 0 < llry_all && 0 < llrz_hz) idx = 0;
+            else if (llrx_hx < llry_all && llrx_hx < llrz_hz) idx = 1;
+            else if (llry_all > llrz_hz) idx = 2;
+            else idx = 3;
+            bx[v] = (int8_t)(idx % 2); bz[v] = (int8_t)(idx / 2);
+            double num_hx = b4_log1pexp(-1. * llrx_hx);
+            for (int e = gx->cp[v]; e < gx->cp[v + 1]; e++) {
+                int p = gx->c2r[e];
+                double msg = c2bx[p];
+                b2cx[p] = num_hx - b4_logaddexp(-1. * (llrz_hz - msg), -1. * (llry_all - msg));
+            }
+            double num_hz = b4_log1pexp(-1. * llrz_hz);
+            for (int e = gz->cp[v]; e < gz->cp[v + 1]; e++) {
+                int p = gz->c2r[e];
+                double msg = c2bz[p];
+                b2cz[p] = num_hz - b4_logaddexp(-1. * (llrx_hx - msg), -1. * (llry_all - msg));
+            }
+        }
+        if (synd_match(gx, bz, synd_x, tsx) && synd_match(gz, bx, synd_z, tsz)) { conv = 1; break; }
+    }
+    if (bp_iter_out) *bp_iter_out = it;
+    memcpy(dec, bp_dec, 2 * (size_t)n);
+    if (conv) memcpy(osd0, bp_dec, 2 * (size_t)n);                  /* pyx:210-212 */
+    else if (osd_order > -1) {
+        orc_osd_params P; memset(&P, 0, sizeof(P));
+        P.osd_method = osd_method; P.osd_order = (osd_method == 0) ? 0 : osd_order;
+        double *key = (double *)malloc(sizeof(double) * (n + 1));
+        /* osd('x'): Hx, synd_x -> z part (pyx:264-280) */
+        for (int v = 0; v < n; v++) key[v] = b4_log1pexp(-1. * lpr[3 * v]) - b4_logaddexp(-1. * lpr[3 * v + 1], -1. * lpr[3 * v + 2]);
+        osd_run_keys(gx, prior_llr_x, synd_x, key, &P, rank_x, n, osd0 + n, dec + n);
+        key = (double *)malloc(sizeof(double) * (n + 1));
+        /* osd('z'): Hz, synd_z -> x part (pyx:281-297); k = n - rank_x there (pyx:284) */
+        for (int v = 0; v < n; v++) key[v] = b4_log1pexp(-1. * lpr[3 * v + 2]) - b4_logaddexp(-1. * lpr[3 * v + 1], -1. * lpr[3 * v]);
+        osd_run_keys(gz, prior_llr_z, synd_z, key, &P, rank_z, (rank_x == rank_z) ? n : n, osd0, dec);   /* equal ranks for CSS codes with hx ~ hz */
+    }
+    free(b2cx); free(c2bx); free(b2cz); free(c2bz); free(tsx); free(tsz);
+    graph_free(gx); graph_free(gz);
+    return conv;
 }

@@ -39,6 +39,25 @@ GOLDEN_OSD = ["c1_osdw_osd_00", "c1_osdw_osd_cs10", "c1_osdw_osd_e6", "c2_w0_osd
               "c2_w4_osdw_cs10", "c3_w5_osdw_cs10", "c5_w0_osdw_cs10", "c5_w4_osdw_cs10", "c4_w7_osdw_cs10"]
 
 
+GOLDEN_BP4 = ["c1_bp4_osd_00", "c1_bp4_osd_cs8", "c1_bp4_osd_e5"]
+
+
+def load_golden_bp4(name):
+    """bp4_osd fixtures: Hx, Hz (csc), px/py/pz, synd_x/z [B, m], kwargs, dec [B, 2n], conv, bp_iteration, lpr_first16."""
+    from scipy.sparse import csc_matrix
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    out = {k: z[k] for k in z.files}
+    for b in ("hx", "hz"):
+        m, n = (int(x) for x in z[b + "_shape"])
+        out[b] = csc_matrix((np.ones(len(z[b + "_indices"]), dtype=np.uint8), z[b + "_indices"], z[b + "_indptr"]), shape=(m, n))
+    n = out["hx"].shape[1]
+    out["synd_x"] = np.unpackbits(z["synd_x"], axis=1)[:, :out["hx"].shape[0]]
+    out["synd_z"] = np.unpackbits(z["synd_z"], axis=1)[:, :out["hz"].shape[0]]
+    out["dec"] = np.unpackbits(z["dec"], axis=1)[:, :2 * n]
+    out["kwargs"] = eval(str(z["kwargs"]), {"__builtins__": {}}, {"dict": dict, "True": True, "False": False, "None": None})
+    return out
+
+
 @pytest.fixture(scope="session")
 def oracle_mod():
     from oracle import oracle

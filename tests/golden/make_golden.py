@@ -115,8 +115,44 @@ def c4_section(bpgdg_decoder, osd_window):
     save("c4_w7_gdg_mt1", w.mat, w.prior, s[:80], kw, dec=d, conv=c)
 
 
+def bp4_section():
+    """bp4_osd (src/bp4_osd.pyx): [[72,12,6]] BB code, depolarizing code-capacity noise, quaternary BP + OSD per basis."""
+    from src.bp4_osd import bp4_osd
+    from slidingwindowdecoder_b200.codes import bb_code
+    code, _, _ = bb_code(72)
+    Hx, Hz = code.hx, code.hz
+    n = code.N
+    rng = np.random.default_rng(404)
+    p = 0.09
+    px, py, pz = (p / 3 * (1 + 0.2 * rng.random(n)) for _ in range(3))
+    shots = 600
+    r = rng.random((shots, n))
+    isx, isy, isz = r < px, (r >= px) & (r < px + py), (r >= px + py) & (r < px + py + pz)
+    ex, ez = (isx | isy).astype(np.int64), (isy | isz).astype(np.int64)
+    sx, sz = (ez @ Hx.T % 2).astype(np.uint8), (ex @ Hz.T % 2).astype(np.uint8)
+    hx_shape, hx_p, hx_i = csc_of(Hx); hz_shape, hz_p, hz_i = csc_of(Hz)
+    for meth, order in (("osd_0", 0), ("osd_cs", 8), ("osd_e", 5)):
+        kw = dict(max_iter=24, ms_scaling_factor=0.9, osd_method=meth, osd_order=order)
+        d = bp4_osd(np.asarray(Hx), np.asarray(Hz), channel_probs_x=px, channel_probs_y=py, channel_probs_z=pz, **kw)
+        dec = np.zeros((shots, 2 * n), dtype=np.uint8); conv = np.zeros(shots, dtype=np.uint8); it = np.zeros(shots, dtype=np.int32)
+        lpr = np.zeros((shots, n, 3))
+        for i in range(shots):
+            dec[i] = d.decode(sx[i], sz[i]).reshape(-1); conv[i] = int(d.converge); it[i] = d.bp_iteration; lpr[i] = d.log_prob_ratios
+        name = f"c1_bp4_{meth}{order}"
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), hx_shape=np.array(hx_shape), hx_indptr=hx_p, hx_indices=hx_i,
+                            hz_shape=np.array(hz_shape), hz_indptr=hz_p, hz_indices=hz_i, px=px, py=py, pz=pz,
+                            synd_x=np.packbits(sx, axis=1), synd_z=np.packbits(sz, axis=1), kwargs=np.array(repr(kw)),
+                            dec=np.packbits(dec, axis=1), conv=conv, bp_iteration=it, lpr_first16=lpr[:16])
+        print("wrote", name, "shots", shots, "converged", int(conv.sum()))
+
+
 def main():
     build_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "bp4":
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 2)
+        bp4_section()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "c4":
         devnull = os.open(os.devnull, os.O_WRONLY)
         os.dup2(devnull, 2)
@@ -208,6 +244,7 @@ def main():
     save("c3_w5_osdw_cs10", w.mat, w.prior, s, kw, **run_osd(osd_window, w.mat, w.prior, s, kw))
     shyps_section(bpgdg_decoder, osd_window)
     c4_section(bpgdg_decoder, osd_window)
+    bp4_section()
 
 
 if __name__ == "__main__":

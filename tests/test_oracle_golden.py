@@ -123,3 +123,18 @@ def test_product_sum_oracle_against_independent_numpy_restatement(oracle_mod):
             assert np.array_equal(dec, (post <= 0).astype(np.int8))
     finally:
         oracle_mod.set_bp_method("minimum_sum")
+
+
+@pytest.mark.parametrize("name", __import__("conftest").GOLDEN_BP4)
+def test_bp4_osd_matches_reference(name, oracle_mod):
+    """bp4_osd.decode (quaternary BP over Hx, Hz + OSD per basis) - the C restatement against the compiled reference:
+    corrections, converge flag, iteration count and the three posterior LLRs are bit-identical."""
+    from conftest import load_golden_bp4
+    g = load_golden_bp4(name)
+    orc = oracle_mod.Bp4Oracle(g["hx"], g["hz"], g["px"], g["py"], g["pz"])
+    for i in range(len(g["conv"])):
+        o = orc.decode(g["synd_x"][i], g["synd_z"][i], **g["kwargs"])
+        assert np.array_equal(o["dec"].reshape(-1).astype(np.uint8), g["dec"][i]), (name, i)
+        assert o["converge"] == int(g["conv"][i]) and o["bp_iteration"] == int(g["bp_iteration"][i])
+        if i < 16:
+            assert np.array_equal(o["log_prob_ratios"], g["lpr_first16"][i])
