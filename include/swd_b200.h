@@ -162,6 +162,22 @@ int  swd_window_set_priors(swd_window *w, const double *priors /* host, [num_col
 int  swd_window_sample(swd_window *w, uint64_t seed, int64_t shot_offset, int64_t B, uint8_t *d_det, uint8_t *d_obs,
                        uint8_t *d_err, void *stream);
 
+/* ---- bp4_osd (src/bp4_osd.pyx:6-684): quaternary min-sum BP over the pair (Hx, Hz) of a CSS code under depolarizing
+ * noise, then one OSD per basis for shots whose BP did not converge.  Replaces bp4_osd.__cinit__ / decode (pyx:8-221);
+ * camel_decode (pyx:223-248) is not provided.  llr_*: log((1-px-py-pz)/p_*) per qubit, prior_llr_x / _z:
+ * log((1-(px+py))/(px+py)) and log((1-(pz+py))/(pz+py)) (pyx:123-133), computed by the caller with libm.
+ * decode: synd_x[B*mx] (syndrome of Hx, i.e. of the Z part), synd_z[B*mz]; dec[B*2n] = x part then z part per shot
+ * (stackchar2numpy); optional bp_dec / osd0 [B*2n], log_prob_ratios [B*n*3] (x, y, z), bp_iteration [B]. */
+typedef struct swd_bp4 swd_bp4;
+int  swd_bp4_create(int device, int mx, int mz, int n, const int32_t *hx_colptr, const int32_t *hx_rowidx,
+                    const int32_t *hz_colptr, const int32_t *hz_rowidx, const double *llr_x, const double *llr_y,
+                    const double *llr_z, const double *prior_llr_x, const double *prior_llr_z, int max_iter,
+                    double ms_scaling_factor, int osd_method, int osd_order, swd_bp4 **out);
+void swd_bp4_destroy(swd_bp4 *b);
+int  swd_bp4_rank(swd_bp4 *b, int which /* 0: Hx, 1: Hz */);
+int  swd_bp4_decode_batch_host(swd_bp4 *b, const uint8_t *synd_x, const uint8_t *synd_z, int64_t B, uint8_t *dec, uint8_t *converge,
+                               uint8_t *bp_dec, uint8_t *osd0, double *log_prob_ratios, int32_t *bp_iteration);
+
 const char *swd_strerror(int status);
 const char *swd_last_error(void);
 const char *swd_version(void);

@@ -13,6 +13,7 @@
 #include "swd_kernels.cuh"
 #include "swd_osd.cuh"
 #include "swd_window.cuh"
+#include "swd_bp4.cuh"
 
 static thread_local std::string g_last_error;
 static void set_err(const std::string &s) { g_last_error = s; }
@@ -753,5 +754,131 @@ extern "C" int swd_window_count_failures(swd_window *w, const uint8_t *d_det, co
     window_count_kernel<<<(unsigned)std::min<long long>((B + wpb - 1) / wpb, 1 << 20), wpb * 32, 0, (cudaStream_t)stream>>>(
         d_det, w->num_det, d_obs, w->num_obs, B, d_out2);
     CK(cudaGetLastError());
+    return SWD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bp4_osd: quaternary BP over (Hx, Hz) + one OSD per basis (src/bp4_osd.pyx)
+// ------------------------------------------------------------------------------------------------
+struct swd_bp4 {
+    int device = 0, n = 0, mx = 0, mz = 0, max_iter = 32, num_sm = 0;
+    double alpha = 1.0;
+    swd_decoder *dx = nullptr, *dz = nullptr;      // osd_window-kind decoders over Hx / Hz: graph upload, rank, OSD machinery
+    double *llr = nullptr;                         // device: llr_x | llr_y | llr_z, n each
+    Bp4Smem S{};
+    int grid = 0;
+    // per-batch device buffers
+    long long cap = 0;
+    u8 *synd_x = nullptr, *synd_z = nullptr, *bp_dec = nullptr, *conv = nullptr, *dec = nullptr, *osd0 = nullptr, *tmp = nullptr;
+    int *iters = nullptr;
+    double *lpr = nullptr, *key_x = nullptr, *key_z = nullptr;
+    cudaStream_t stream = nullptr;
+};
+
+static void bp4_free_buffers(swd_bp4 *b) {
+    void *ptrs[] = {b->synd_x, b->synd_z, b->bp_dec, b->conv, b->dec, b->osd0, b->tmp, b->iters, b->lpr, b->key_x, b->key_z};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    b->synd_x = b->synd_z = b->bp_dec = b->conv = b->dec = b->osd0 = b->tmp = nullptr; b->iters = nullptr;
+    b->lpr = b->key_x = b->key_z = nullptr; b->cap = 0;
+}
+
+extern "C" void swd_bp4_destroy(swd_bp4 *b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    bp4_free_buffers(b);
+    if (b->llr) cudaFree(b->llr);
+    if (b->dx) swd_destroy(b->dx);
+    if (b->dz) swd_destroy(b->dz);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+extern "C" int swd_bp4_create(int device, int mx, int mz, int n, const int32_t *hx_colptr, const int32_t *hx_rowidx,
+                              const int32_t *hz_colptr, const int32_t *hz_rowidx, const double *llr_x, const double *llr_y,
+                              const double *llr_z, const double *prior_llr_x, const double *prior_llr_z, int max_iter,
+                              double ms_scaling_factor, int osd_method, int osd_order, swd_bp4 **out) {
+    if (!hx_colptr || !hx_rowidx || !hz_colptr || !hz_rowidx || !llr_x || !llr_y || !llr_z || !prior_llr_x || !prior_llr_z || !out ||
+        mx <= 0 || mz <= 0 || n <= 0 || max_iter < 0) { set_err("swd_bp4_create: bad argument"); return SWD_ERR_INVALID; }
+    swd_bp4 *b = new swd_bp4();
+    b->device = device; b->n = n; b->mx = mx; b->mz = mz; b->max_iter = max_iter; b->alpha = ms_scaling_factor;
+    swd_config cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.kind = SWD_KIND_OSD_WINDOW; cfg.device = device; cfg.max_iter = 1; cfg.ms_scaling_factor = 1.0; cfg.new_n = n;
+    cfg.post_max_iter = 0; cfg.osd_method = osd_method; cfg.osd_order = osd_order; cfg.max_iter_per_step = 6; cfg.max_step = 1;
+    int st;
+    if ((st = swd_create(&cfg, mx, n, hx_colptr, hx_rowidx, prior_llr_x, &b->dx)) != SWD_OK) { swd_bp4_destroy(b); return st; }
+    if ((st = swd_create(&cfg, mz, n, hz_colptr, hz_rowidx, prior_llr_z, &b->dz)) != SWD_OK) { swd_bp4_destroy(b); return st; }
+    b->num_sm = b->dx->num_sm;
+    std::vector<double> l(3 * (size_t)n);
+    for (int v = 0; v < n; v++) { l[v] = llr_x[v]; l[n + v] = llr_y[v]; l[2 * (size_t)n + v] = llr_z[v]; }
+    if ((st = upload(l, (void **)&b->llr)) != SWD_OK) { swd_bp4_destroy(b); return st; }
+    int o = 0;
+    b->S.off_mx = o; o += 8 * std::max(1, b->dx->nnz); o = r16(o);
+    b->S.off_mz = o; o += 8 * std::max(1, b->dz->nnz); o = r16(o);
+    b->S.off_ux = o; o += 4 * mx; o = r16(o);
+    b->S.off_uz = o; o += 4 * mz; o = r16(o);
+    b->S.off_sx = o; o += mx; o = r16(o);
+    b->S.off_sz = o; o += mz; o = r16(o);
+    b->S.total = o;
+    if (o > 227 * 1024) { swd_bp4_destroy(b); set_err("bp4: the two message arrays do not fit in shared memory"); return SWD_ERR_UNSUPPORTED; }
+    int occ = 0;
+    if ((st = occupancy(bp4_kernel, 256, b->S.total, &occ)) != SWD_OK || occ < 1) { swd_bp4_destroy(b); if (!st) { set_err("bp4_kernel does not fit"); st = SWD_ERR_UNSUPPORTED; } return st; }
+    b->grid = b->num_sm * occ;
+    if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) { swd_bp4_destroy(b); set_err("stream create failed"); return SWD_ERR_CUDA; }
+    *out = b;
+    return SWD_OK;
+}
+
+extern "C" int swd_bp4_rank(swd_bp4 *b, int which) { return !b ? -1 : (which == 0 ? b->dx->rank : b->dz->rank); }
+
+// OSD-only pass of an osd_window-kind decoder: ranking keys are supplied, converged shots are skipped
+static int bp4_osd_pass(swd_decoder *d, const u8 *d_synd, const double *d_keys, const u8 *d_conv, long long B, u8 *d_tmp, cudaStream_t s) {
+    int st = alloc_workspace(d, B);
+    if (st) return st;
+    if ((st = osd_reserve_outputs(&d->ow, B, d->n))) { set_err("osd output alloc failed"); return SWD_ERR_NOMEM; }
+    for (long long b0 = 0; b0 < B; b0 += d->cap) {
+        const long long nb = std::min<long long>(d->cap, B - b0);
+        CK(cudaMemsetAsync(d->ws.counters, 0, 64 * sizeof(int), s));
+        bp4_osd_setup_kernel<<<(unsigned)std::min<long long>((nb * d->n + 255) / 256, 4096), 256, 0, s>>>(d->ws, d->ow.need_osd, d_keys + b0 * d->n, d_conv + b0, nb, d->n);
+        osd_kernel<<<d->grid5, d->T5, d->OS.total, s>>>(d->g, d_synd + b0 * d->m, d->ws, d->L, d->P, d->OS, d->ow, d->cfg.osd_method, d->cfg.osd_order,
+                                                        d->rank, d_tmp + b0 * d->n, nullptr, b0);
+        d->ctr.kernel_launches += 2;
+    }
+    CK(cudaGetLastError());
+    return SWD_OK;
+}
+
+extern "C" int swd_bp4_decode_batch_host(swd_bp4 *b, const uint8_t *synd_x, const uint8_t *synd_z, int64_t B, uint8_t *dec, uint8_t *conv,
+                                         uint8_t *bp_dec, uint8_t *osd0, double *lpr, int32_t *bp_iteration) {
+    if (!b || B < 0 || (B > 0 && (!synd_x || !synd_z || !dec || !conv))) { set_err("swd_bp4_decode_batch_host: null argument"); return SWD_ERR_INVALID; }
+    if (B == 0) return SWD_OK;
+    CK(cudaSetDevice(b->device));
+    const size_t n = b->n;
+    if (B > b->cap) {
+        bp4_free_buffers(b);
+        CK(cudaMalloc(&b->synd_x, (size_t)B * b->mx)); CK(cudaMalloc(&b->synd_z, (size_t)B * b->mz));
+        CK(cudaMalloc(&b->bp_dec, (size_t)B * 2 * n)); CK(cudaMalloc(&b->conv, (size_t)B)); CK(cudaMalloc(&b->dec, (size_t)B * 2 * n));
+        CK(cudaMalloc(&b->osd0, (size_t)B * 2 * n)); CK(cudaMalloc(&b->tmp, (size_t)B * n)); CK(cudaMalloc(&b->iters, (size_t)B * 4));
+        CK(cudaMalloc(&b->lpr, (size_t)B * n * 24)); CK(cudaMalloc(&b->key_x, (size_t)B * n * 8)); CK(cudaMalloc(&b->key_z, (size_t)B * n * 8));
+        b->cap = B;
+    }
+    cudaStream_t s = b->stream;
+    CK(cudaMemcpyAsync(b->synd_x, synd_x, (size_t)B * b->mx, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b->synd_z, synd_z, (size_t)B * b->mz, cudaMemcpyHostToDevice, s));
+    bp4_kernel<<<(int)std::min<long long>(B, b->grid), 256, b->S.total, s>>>(b->dx->g, b->dz->g, b->llr, b->llr + n, b->llr + 2 * n, b->synd_x, b->synd_z, B,
+                                                                             b->max_iter, b->alpha, b->bp_dec, b->conv, b->iters, b->lpr, b->key_x, b->key_z, b->S);
+    CK(cudaGetLastError());
+    int st;
+    if ((st = bp4_osd_pass(b->dx, b->synd_x, b->key_x, b->conv, B, b->tmp, s))) return st;      // osd('x') -> z part
+    if ((st = bp4_osd_pass(b->dz, b->synd_z, b->key_z, b->conv, B, b->tmp, s))) return st;      // osd('z') -> x part
+    bp4_finish_kernel<<<(unsigned)std::min<long long>((B * 2 * (long long)n + 255) / 256, 8192), 256, 0, s>>>(
+        b->bp_dec, b->conv, b->dx->ow.osdw, b->dx->ow.osd0, b->dz->ow.osdw, b->dz->ow.osd0, B, (int)n, b->dec, b->osd0);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dec, b->dec, (size_t)B * 2 * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(conv, b->conv, (size_t)B, cudaMemcpyDeviceToHost, s));
+    if (bp_dec) CK(cudaMemcpyAsync(bp_dec, b->bp_dec, (size_t)B * 2 * n, cudaMemcpyDeviceToHost, s));
+    if (osd0) CK(cudaMemcpyAsync(osd0, b->osd0, (size_t)B * 2 * n, cudaMemcpyDeviceToHost, s));
+    if (lpr) CK(cudaMemcpyAsync(lpr, b->lpr, (size_t)B * n * 24, cudaMemcpyDeviceToHost, s));
+    if (bp_iteration) CK(cudaMemcpyAsync(bp_iteration, b->iters, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     return SWD_OK;
 }

@@ -289,3 +289,99 @@ class BpOsdDecoder(osd_window):
                          ms_scaling_factor=float(kwargs.get("ms_scaling_factor", 1.0)), new_n=n,
                          osd_method=kwargs.get("osd_method", "osd_0"), osd_order=kwargs.get("osd_order", 0),
                          device=kwargs.get("device", 0))
+
+
+class bp4_osd:
+    """Quaternary BP + OSD for CSS codes under depolarizing noise (src/bp4_osd.pyx): same constructor kwargs
+    (`channel_probs_x/y/z`, `max_iter=32`, `ms_scaling_factor=1.0`, `osd_method="osd_0"`, `osd_order=0`),
+    `decode(synd_x, synd_z) -> np.int64[2, n]` (row 0: X part, row 1: Z part), `.converge`, `.bp_iteration`, `.min_pm`
+    (0.0, as in the reference whose decode never updates it), `.bp_decoding_x/z`, `.osd0_decoding_x/z`,
+    `.osdw_decoding_x/z`, `.log_prob_ratios` [n, 3].  Added: `decode_batch(synd_x[B, mx], synd_z[B, mz])`.
+    `camel_decode` (pyx:223-248) is not provided."""
+
+    def __init__(self, Hx, Hz, **kwargs):
+        if not (isinstance(Hx, np.ndarray) or isinstance(Hx, spmatrix)):
+            raise TypeError("The input matrix is of an invalid type. Please input a np.ndarray or scipy.sparse.spmatrix object.")
+        if Hx.shape[1] != Hz.shape[1]:
+            raise ValueError("Hx, Hz blocklength does not match!")
+        self.mx, self.n = Hx.shape
+        self.mz = Hz.shape[0]
+        px, py, pz = kwargs.get("channel_probs_x"), kwargs.get("channel_probs_y"), kwargs.get("channel_probs_z")
+        if px is None or py is None or pz is None:
+            raise TypeError("channel_probs_x, channel_probs_y and channel_probs_z are required")
+        if len(px) != self.n:
+            raise ValueError(f"The length of the channel probability vector must be eqaul to the block length n={self.n}.")
+        osd_method = kwargs.get("osd_method", "osd_0")
+        key = str(osd_method).lower()
+        if key not in _OSD_METHODS:
+            raise ValueError(f"ERROR: OSD method '{osd_method}' invalid. Please choose from the following methods: "
+                             "'OSD_0', 'OSD_E' or 'OSD_CS'.")
+        meth = _OSD_METHODS[key]
+        order = 0 if meth == 0 else int(kwargs.get("osd_order", 0))
+        n = self.n
+        llr = np.empty((5, n))
+        for v in range(n):                                                   # pyx:123-133, libm log
+            num = 1.0 - (float(px[v]) + float(py[v]) + float(pz[v]))
+            llr[0, v] = math.log(num / float(px[v])); llr[1, v] = math.log(num / float(py[v])); llr[2, v] = math.log(num / float(pz[v]))
+            den = float(px[v]) + float(py[v]); llr[3, v] = math.log((1.0 - den) / den)
+            den = float(pz[v]) + float(py[v]); llr[4, v] = math.log((1.0 - den) / den)
+        self._llr = np.ascontiguousarray(llr)
+        A, Bz = csc_matrix(Hx), csc_matrix(Hz)
+        for M in (A, Bz):
+            M.eliminate_zeros(); M.sort_indices()
+        self._hx = (np.ascontiguousarray(A.indptr, dtype=np.int32), np.ascontiguousarray(A.indices, dtype=np.int32))
+        self._hz = (np.ascontiguousarray(Bz.indptr, dtype=np.int32), np.ascontiguousarray(Bz.indices, dtype=np.int32))
+        lib = _lib.load()
+        self._lib = lib
+        self._handle = C.c_void_p()
+        i32p, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+        st = lib.swd_bp4_create(int(kwargs.get("device", 0)), self.mx, self.mz, n, self._hx[0].ctypes.data_as(i32p),
+                                self._hx[1].ctypes.data_as(i32p), self._hz[0].ctypes.data_as(i32p), self._hz[1].ctypes.data_as(i32p),
+                                *[self._llr[i].ctypes.data_as(dp) for i in range(5)], int(kwargs.get("max_iter", 32)),
+                                float(kwargs.get("ms_scaling_factor", 1.0)), meth, order, C.byref(self._handle))
+        try:
+            _lib.check(st, "swd_bp4_create")
+        except ValueError as e:
+            if "osd_order" in str(e):
+                raise ValueError("For this code, the OSD order should be set in the range 0<=osd_oder<=n-rank.") from e
+            raise
+        self.rank_x, self.rank_z = lib.swd_bp4_rank(self._handle, 0), lib.swd_bp4_rank(self._handle, 1)
+        self.osd_method, self.osd_order = meth, order
+        self.converge, self.bp_iteration, self.min_pm = 0, 0, 0.0
+        self._last = None
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            self._lib.swd_bp4_destroy(h)
+            self._handle = C.c_void_p()
+
+    def decode_batch(self, synd_x, synd_z):
+        """-> dict(dec [B, 2, n] uint8, converge [B], bp_decoding [B, 2, n], osd0 [B, 2, n], log_prob_ratios [B, n, 3],
+        bp_iteration [B])"""
+        sx = np.ascontiguousarray(np.asarray(synd_x), dtype=np.uint8); sz = np.ascontiguousarray(np.asarray(synd_z), dtype=np.uint8)
+        if sx.ndim != 2 or sz.ndim != 2 or sx.shape[1] != self.mx or sz.shape[1] != self.mz or sx.shape[0] != sz.shape[0]:
+            raise ValueError(f"decode_batch expects syndromes of shape [B, {self.mx}] and [B, {self.mz}]")
+        B, n = sx.shape[0], self.n
+        dec = np.empty((B, 2, n), dtype=np.uint8); bp = np.empty_like(dec); o0 = np.empty_like(dec)
+        conv = np.empty(B, dtype=np.uint8); lpr = np.empty((B, n, 3)); it = np.empty(B, dtype=np.int32)
+        st = self._lib.swd_bp4_decode_batch_host(self._handle, sx.ctypes.data, sz.ctypes.data, B, dec.ctypes.data, conv.ctypes.data,
+                                                 bp.ctypes.data, o0.ctypes.data, lpr.ctypes.data, it.ctypes.data)
+        _lib.check(st, "swd_bp4_decode_batch_host")
+        return dict(dec=dec, converge=conv, bp_decoding=bp, osd0=o0, log_prob_ratios=lpr, bp_iteration=it)
+
+    def decode(self, input_vector_x, input_vector_z):
+        if input_vector_x.shape[0] != self.mx or input_vector_z.shape[0] != self.mz:
+            raise ValueError(f"The input to the bp4_osd.decode must be a syndrome (of length={self.mx}).")
+        out = self.decode_batch(np.asarray(input_vector_x).reshape(1, -1), np.asarray(input_vector_z).reshape(1, -1))
+        self._last = {k: v[0] for k, v in out.items()}
+        self.converge = int(self._last["converge"]); self.bp_iteration = int(self._last["bp_iteration"])
+        return self._last["dec"].astype(np.int64)
+
+    bp_decoding_x = property(lambda self: self._last["bp_decoding"][0].astype(np.int64))
+    bp_decoding_z = property(lambda self: self._last["bp_decoding"][1].astype(np.int64))
+    osd0_decoding_x = property(lambda self: self._last["osd0"][0].astype(np.int64))
+    osd0_decoding_z = property(lambda self: self._last["osd0"][1].astype(np.int64))
+    osdw_decoding_x = property(lambda self: self._last["dec"][0].astype(np.int64))
+    osdw_decoding_z = property(lambda self: self._last["dec"][1].astype(np.int64))
+    log_prob_ratios = property(lambda self: self._last["log_prob_ratios"].copy())
