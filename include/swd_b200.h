@@ -164,7 +164,8 @@ int  swd_window_sample(swd_window *w, uint64_t seed, int64_t shot_offset, int64_
 
 /* ---- bp4_osd (src/bp4_osd.pyx:6-684): quaternary min-sum BP over the pair (Hx, Hz) of a CSS code under depolarizing
  * noise, then one OSD per basis for shots whose BP did not converge.  Replaces bp4_osd.__cinit__ / decode (pyx:8-221);
- * camel_decode (pyx:223-248) is not provided.  llr_*: log((1-px-py-pz)/p_*) per qubit, prior_llr_x / _z:
+ * swd_bp4_camel_decode_batch_host replaces camel_decode (pyx:223-248).  The two graphs have no column- / row-weight limit
+ * (CAMEL codes tie every check to the last qubit).  llr_*: log((1-px-py-pz)/p_*) per qubit, prior_llr_x / _z:
  * log((1-(px+py))/(px+py)) and log((1-(pz+py))/(pz+py)) (pyx:123-133), computed by the caller with libm.
  * decode: synd_x[B*mx] (syndrome of Hx, i.e. of the Z part), synd_z[B*mz]; dec[B*2n] = x part then z part per shot
  * (stackchar2numpy); optional bp_dec / osd0 [B*2n], log_prob_ratios [B*n*3] (x, y, z), bp_iteration [B]. */
@@ -177,6 +178,12 @@ void swd_bp4_destroy(swd_bp4 *b);
 int  swd_bp4_rank(swd_bp4 *b, int which /* 0: Hx, 1: Hz */);
 int  swd_bp4_decode_batch_host(swd_bp4 *b, const uint8_t *synd_x, const uint8_t *synd_z, int64_t B, uint8_t *dec, uint8_t *converge,
                                uint8_t *bp_dec, uint8_t *osd0, double *log_prob_ratios, int32_t *bp_iteration);
+/* camel_decode (pyx:223-248): four BP runs per shot with the last qubit pinned to I / X / Z / Y (vn_set_value, pyx:389-423), the
+ * converged run with the smallest path metric (cal_pm, pyx:250-259) wins, ties to the earlier value.  dec[B*2n], converge[B];
+ * optional min_pm[B] (10000.0 and dec = 0 when no run converged - the reference returns an earlier call's buffer there),
+ * log_prob_ratios [B*n*3] and bp_iteration [B] of the last run, as the reference's properties hold after the call. */
+int  swd_bp4_camel_decode_batch_host(swd_bp4 *b, const uint8_t *synd_x, const uint8_t *synd_z, int64_t B, uint8_t *dec,
+                                     uint8_t *converge, double *min_pm, double *log_prob_ratios, int32_t *bp_iteration);
 
 const char *swd_strerror(int status);
 const char *swd_last_error(void);

@@ -246,6 +246,18 @@ class Bp4Oracle:
                     log_prob_ratios=lpr, bp_iteration=it.value)
 
 
+    def camel_decode(self, synd_x, synd_z, max_iter=32, ms_scaling_factor=1.0):
+        """-> dict(dec [2, n], converge, min_pm, log_prob_ratios [n, 3] (last run), bp_iteration (last run))"""
+        sx = np.ascontiguousarray(np.asarray(synd_x).astype(np.int8)); sz = np.ascontiguousarray(np.asarray(synd_z).astype(np.int8))
+        n = self.n
+        dec = np.zeros(2 * n, dtype=np.int8); lpr = np.zeros((n, 3)); it = C.c_int(0); pm = C.c_double(0)
+        conv = lib().orc_bp4_camel_decode(self.mx, self.mz, n, _p(self.cpx, C.c_int), _p(self.crx, C.c_int), _p(self.cpz, C.c_int),
+                                          _p(self.crz, C.c_int), _p(self.llrx, C.c_double), _p(self.llry, C.c_double),
+                                          _p(self.llrz, C.c_double), _p(sx, C.c_int8), _p(sz, C.c_int8), int(max_iter),
+                                          C.c_double(ms_scaling_factor), _p(dec, C.c_int8), _p(lpr, C.c_double), C.byref(pm), C.byref(it))
+        return dict(dec=dec.reshape(2, n), converge=int(conv), min_pm=pm.value, log_prob_ratios=lpr, bp_iteration=it.value)
+
+
 def sliding_window_reference(plan, det, obs, decode_window):
     """The reference's window loop (guessing.py:141-227) in dense numpy, for tests.
     decode_window(window, synd[B, m]) -> (corr[B, n_win], conv[B]).

@@ -1052,6 +1052,99 @@ static void b4_cn_update(const graph *g, const int8_t *synd, double alpha, doubl
         }
     }
 }
+/* one BP4 run (bp4_decode_llr, pyx:444-481) from initialised messages; fix_vn >= 0: that qubit is decided (pyx:389-423)
+ * and skipped by the variable pass, its messages stay at their initial value; seeds = current_cn (syndrome with the
+ * decided qubit's contribution toggled).  Returns converge. */
+static int b4_run(const graph *gx, const graph *gz, const double *llrx, const double *llry, const double *llrz,
+                  const int8_t *synd_x, const int8_t *synd_z, const int8_t *seed_x, const int8_t *seed_z, int fix_vn,
+                  int max_iter, double alpha, double *b2cx, double *c2bx, double *b2cz, double *c2bz,
+                  int8_t *bx, int8_t *bz, double *lpr, int8_t *tsx, int8_t *tsz, int *iters) {
+    int n = gx->n, it = 0, conv = 0;
+    for (int iter = 0; iter < max_iter; iter++) {
+        it++;
+        b4_cn_update(gx, seed_x, alpha, b2cx, c2bx);
+        b4_cn_update(gz, seed_z, alpha, b2cz, c2bz);
+        for (int v = 0; v < n; v++) {
+            if (v == fix_vn) continue;
+            double llrx_hx = 0.0, llrz_hz = 0.0;
+            for (int e = gz->cp[v]; e < gz->cp[v + 1]; e++) llrx_hx += c2bz[gz->c2r[e]];
+            for (int e = gx->cp[v]; e < gx->cp[v + 1]; e++) llrz_hz += c2bx[gx->c2r[e]];
+            double llry_all = llrx_hx + llrz_hz + llry[v];
+            llrx_hx = llrx_hx + llrx[v];
+            llrz_hz = llrz_hz + llrz[v];
+            lpr[3 * v] = llrx_hx; lpr[3 * v + 1] = llry_all; lpr[3 * v + 2] = llrz_hz;
+            int idx;
+            if (0 < llrx_hx && 0 < llry_all && 0 < llrz_hz) idx = 0;
+            else if (llrx_hx < llry_all && llrx_hx < llrz_hz) idx = 1;
+            else if (llry_all > llrz_hz) idx = 2;
+            else idx = 3;
+            bx[v] = (int8_t)(idx % 2); bz[v] = (int8_t)(idx / 2);
+            double num_hx = b4_log1pexp(-1. * llrx_hx);
+            for (int e = gx->cp[v]; e < gx->cp[v + 1]; e++) {
+                int p = gx->c2r[e];
+                double msg = c2bx[p];
+                b2cx[p] = num_hx - b4_logaddexp(-1. * (llrz_hz - msg), -1. * (llry_all - msg));
+            }
+            double num_hz = b4_log1pexp(-1. * llrz_hz);
+            for (int e = gz->cp[v]; e < gz->cp[v + 1]; e++) {
+                int p = gz->c2r[e];
+                double msg = c2bz[p];
+                b2cz[p] = num_hz - b4_logaddexp(-1. * (llrx_hx - msg), -1. * (llry_all - msg));
+            }
+        }
+        if (synd_match(gx, bz, synd_x, tsx) && synd_match(gz, bx, synd_z, tsz)) { conv = 1; break; }
+    }
+    *iters = it;
+    return conv;
+}
+static void b4_init(const graph *gx, const graph *gz, const double *llrx, const double *llry, const double *llrz, double *b2cx, double *b2cz) {
+    for (int v = 0; v < gx->n; v++) {                               /* bp_init, pyx:425-442 */
+        double msg_x = b4_log1pexp(-1. * llrx[v]) - b4_logaddexp(-1. * llry[v], -1. * llrz[v]);
+        double msg_z = b4_log1pexp(-1. * llrz[v]) - b4_logaddexp(-1. * llry[v], -1. * llrz[v]);   /* sic (pyx:438) */
+        for (int e = gx->cp[v]; e < gx->cp[v + 1]; e++) b2cx[gx->c2r[e]] = msg_x;
+        for (int e = gz->cp[v]; e < gz->cp[v + 1]; e++) b2cz[gz->c2r[e]] = msg_z;
+    }
+}
+/* bp4_osd.camel_decode (pyx:223-248): four BP runs with the last qubit pinned to I / X / Z / Y, keep the converged run
+ * with the smallest path metric (cal_pm, pyx:250-259; strict <, value order 0..3).  dec [2n] (zeros if no run converged;
+ * the reference leaves the previous call's buffer), lpr / bp_iter of the last run.  Returns converge. */
+int orc_bp4_camel_decode(int mx, int mz, int n, const int *cpx, const int *crx, const int *cpz, const int *crz,
+                         const double *llrx, const double *llry, const double *llrz,
+                         const int8_t *synd_x, const int8_t *synd_z, int max_iter, double alpha,
+                         int8_t *dec, double *lpr, double *min_pm_out, int *bp_iter_out) {
+    graph *gx = graph_build(mx, n, cpx, crx, NULL), *gz = graph_build(mz, n, cpz, crz, NULL);
+    double *b2cx = (double *)calloc(gx->nnz + 1, 8), *c2bx = (double *)calloc(gx->nnz + 1, 8);
+    double *b2cz = (double *)calloc(gz->nnz + 1, 8), *c2bz = (double *)calloc(gz->nnz + 1, 8);
+    int8_t *bp = (int8_t *)calloc(2 * (size_t)n + 1, 1), *bx = bp, *bz = bp + n;
+    int8_t *tsx = (int8_t *)malloc(mx + 1), *tsz = (int8_t *)malloc(mz + 1);
+    int8_t *cx = (int8_t *)malloc(mx + 1), *cz = (int8_t *)malloc(mz + 1);
+    double min_pm = 10000.0; int it = 0;
+    memset(dec, 0, 2 * (size_t)n); memset(lpr, 0, sizeof(double) * 3 * (size_t)n);
+    for (int value = 0; value < 4; value++) {
+        memset(bp, 0, 2 * (size_t)n);
+        memcpy(cx, synd_x, mx); memcpy(cz, synd_z, mz);
+        b4_init(gx, gz, llrx, llry, llrz, b2cx, b2cz);
+        int vn = n - 1, x = value % 2, z = value / 2;                /* vn_set_value, pyx:389-423 */
+        bx[vn] = (int8_t)x; bz[vn] = (int8_t)z;
+        if (z) for (int e = gx->cp[vn]; e < gx->cp[vn + 1]; e++) cx[gx->cr[e]] = 1 - cx[gx->cr[e]];
+        if (x) for (int e = gz->cp[vn]; e < gz->cp[vn + 1]; e++) cz[gz->cr[e]] = 1 - cz[gz->cr[e]];
+        if (b4_run(gx, gz, llrx, llry, llrz, synd_x, synd_z, cx, cz, vn, max_iter, alpha, b2cx, c2bx, b2cz, c2bz, bx, bz, lpr, tsx, tsz, &it)) {
+            double pm = 0.0;                                            /* cal_pm */
+            for (int v = 0; v < n; v++) {
+                if (bx[v] && bz[v]) pm += llry[v];
+                else if (bx[v]) pm += llrx[v];
+                else if (bz[v]) pm += llrz[v];
+            }
+            if (pm < min_pm) { min_pm = pm; memcpy(dec, bp, 2 * (size_t)n); }
+        }
+    }
+    if (min_pm_out) *min_pm_out = min_pm;
+    if (bp_iter_out) *bp_iter_out = it;
+    free(b2cx); free(c2bx); free(b2cz); free(c2bz); free(bp); free(tsx); free(tsz); free(cx); free(cz);
+    graph_free(gx); graph_free(gz);
+    return min_pm < 9999.0;
+}
+
 /* bp4_osd.decode (bp4_osd.pyx:197-221): quaternary BP over (Hx, Hz) + one OSD per basis.
  * llr*: channel LLRs log((1-px-py-pz)/p*), prior_llr_x/z: log((1-(px+py))/(px+py)) resp. (pz+py) (pyx:123-133),
  * computed by the caller with libm.  dec / bp_dec / osd0: [2n] = x part then z part.  lpr: [n][3] (x, y, z).

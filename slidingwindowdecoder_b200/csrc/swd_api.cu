@@ -49,6 +49,7 @@ struct swd_decoder {
     path_fn_t path_fn = nullptr;
     pre_fn_t pre_fn = nullptr;
     int m = 0, n = 0, nnz = 0, nn = 0, max_col_deg = 0, max_row_deg = 0, es_max = 0, rank = -1;
+    bool osd_only = false;
     int device = 0, num_sm = 0;
     GraphDev g{};
     void *d_graph[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -137,8 +138,18 @@ static int host_rank(int m, int n, const std::vector<int> &cp, const std::vector
 static int setup_kernels(swd_decoder *d);
 static int alloc_workspace(swd_decoder *d, long long want_cap);
 
+static int create_impl(const swd_config *cfg, int m, int n, const int32_t *colptr, const int32_t *rowidx,
+                       const double *channel_llr, swd_decoder **out, bool osd_only);
+
 extern "C" int swd_create(const swd_config *cfg, int m, int n, const int32_t *colptr, const int32_t *rowidx,
                           const double *channel_llr, swd_decoder **out) {
+    return create_impl(cfg, m, n, colptr, rowidx, channel_llr, out, false);
+}
+
+// osd_only: the graph is used by osd_kernel alone (bp4_osd runs its own BP kernel) - no pre-BP / sort / path set-up and no
+// column- or row-weight limit (CAMEL codes tie every check to the last qubit)
+static int create_impl(const swd_config *cfg, int m, int n, const int32_t *colptr, const int32_t *rowidx,
+                       const double *channel_llr, swd_decoder **out, bool osd_only) {
     if (!cfg || !colptr || !rowidx || !channel_llr || !out || m <= 0 || n <= 0) { set_err("swd_create: null/empty argument"); return SWD_ERR_INVALID; }
     if (cfg->kind < 0 || cfg->kind > 2) { set_err("swd_create: bad kind"); return SWD_ERR_INVALID; }
     if (cfg->bp_method != SWD_BP_MIN_SUM && cfg->bp_method != SWD_BP_PRODUCT_SUM) { set_err("swd_create: bad bp_method"); return SWD_ERR_INVALID; }
@@ -146,7 +157,7 @@ extern "C" int swd_create(const swd_config *cfg, int m, int n, const int32_t *co
     if (colptr[0] != 0 || nnz < 0) { set_err("swd_create: bad colptr"); return SWD_ERR_INVALID; }
     if (n > 65534 || m > 65534 || nnz > 65535) { set_err("swd_create: graph too large for 16-bit indices"); return SWD_ERR_UNSUPPORTED; }
     swd_decoder *d = new swd_decoder();
-    d->cfg = *cfg; d->m = m; d->n = n; d->nnz = nnz; d->device = cfg->device;
+    d->cfg = *cfg; d->m = m; d->n = n; d->nnz = nnz; d->device = cfg->device; d->osd_only = osd_only;
     // ---- flat graph: CSC with ascending rows, CSR with ascending columns (mod2sparse.c:358-432)
     std::vector<int> cp(colptr, colptr + n + 1), cr(nnz), rp(m + 1, 0), rc(nnz), cpos(nnz);
     for (int c = 0; c < n; c++) {
@@ -164,8 +175,9 @@ extern "C" int swd_create(const swd_config *cfg, int m, int n, const int32_t *co
         std::vector<int> fill(rp.begin(), rp.end() - 1);
         for (int c = 0; c < n; c++) for (int e = cp[c]; e < cp[c + 1]; e++) { int p = fill[cr[e]]++; rc[p] = c; cpos[e] = p; }
     }
-    if (d->max_col_deg > 16) { delete d; set_err("swd_create: column weight > 16 unsupported"); return SWD_ERR_UNSUPPORTED; }
-    if (d->max_row_deg > 255) { delete d; set_err("swd_create: row weight > 255 unsupported"); return SWD_ERR_UNSUPPORTED; }
+    if (osd_only && cfg->kind != SWD_KIND_OSD_WINDOW) { delete d; set_err("swd_create: bad kind"); return SWD_ERR_INVALID; }
+    if (!osd_only && d->max_col_deg > 16) { delete d; set_err("swd_create: column weight > 16 unsupported"); return SWD_ERR_UNSUPPORTED; }
+    if (!osd_only && d->max_row_deg > 255) { delete d; set_err("swd_create: row weight > 255 unsupported"); return SWD_ERR_UNSUPPORTED; }
     d->dmax = d->max_col_deg <= 8 ? 8 : 16;
     d->nn = (cfg->new_n <= 0) ? std::min(n, 2 * m) : std::min(cfg->new_n, n);
     {   // worst-case edge count of a shortened graph: the nn heaviest columns
@@ -292,6 +304,7 @@ static void make_path_smem(PathSmem &S3, int nn, int m, int es) {
 
 static int setup_kernels(swd_decoder *d) {
     const int m = d->m, n = d->n, nn = d->nn, es = std::max(d->es_max, 1);
+    const bool osd_only = d->osd_only;
     const swd_config &c = d->cfg;
     // ---- GDG parameters
     GdgDev &P = d->P;
@@ -314,7 +327,14 @@ static int setup_kernels(swd_decoder *d) {
     // ---- blob layouts: global (worst case), shared-memory tier A (typical shots), tier B (worst case)
     const int lcap = std::min(255, d->max_row_deg);
     const int es_slots = es + m;      // every row may carry one pad slot
-    make_layout(d->L, nn, m, es_slots, lcap);
+    make_layout(d->L, nn, m, osd_only ? 8 : es_slots, lcap);
+    if (osd_only) {
+        int st;
+        if ((st = osd_setup(d->m, d->n, d->nn, d->rank, d->cfg.osd_method, d->cfg.osd_order, d->num_sm, &d->OS, &d->T5, &d->grid5))) {
+            set_err("osd kernel does not fit in shared memory"); return st;
+        }
+        return SWD_OK;
+    }
     // ---- K1
     d->T1 = std::min(256, std::max(64, r32up((n + 3) / 4)));
     if (const char *e = getenv("SWD_T1")) d->T1 = std::min(256, std::max(32, r32up(atoi(e))));
@@ -772,8 +792,20 @@ struct swd_bp4 {
     u8 *synd_x = nullptr, *synd_z = nullptr, *bp_dec = nullptr, *conv = nullptr, *dec = nullptr, *osd0 = nullptr, *tmp = nullptr;
     int *iters = nullptr;
     double *lpr = nullptr, *key_x = nullptr, *key_z = nullptr;
+    // camel_decode: four runs per shot
+    long long cap4 = 0;
+    u8 *c_synd_x = nullptr, *c_synd_z = nullptr, *c_bp_dec = nullptr, *c_conv4 = nullptr, *c_dec = nullptr, *c_conv = nullptr;
+    int *c_it4 = nullptr, *c_it = nullptr;
+    double *c_pm4 = nullptr, *c_pm = nullptr, *c_lpr = nullptr;
     cudaStream_t stream = nullptr;
 };
+
+static void bp4_free_camel(swd_bp4 *b) {
+    void *ptrs[] = {b->c_synd_x, b->c_synd_z, b->c_bp_dec, b->c_conv4, b->c_dec, b->c_conv, b->c_it4, b->c_it, b->c_pm4, b->c_pm, b->c_lpr};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    b->c_synd_x = b->c_synd_z = b->c_bp_dec = b->c_conv4 = b->c_dec = b->c_conv = nullptr; b->c_it4 = b->c_it = nullptr;
+    b->c_pm4 = b->c_pm = b->c_lpr = nullptr; b->cap4 = 0;
+}
 
 static void bp4_free_buffers(swd_bp4 *b) {
     void *ptrs[] = {b->synd_x, b->synd_z, b->bp_dec, b->conv, b->dec, b->osd0, b->tmp, b->iters, b->lpr, b->key_x, b->key_z};
@@ -786,6 +818,7 @@ extern "C" void swd_bp4_destroy(swd_bp4 *b) {
     if (!b) return;
     cudaSetDevice(b->device);
     bp4_free_buffers(b);
+    bp4_free_camel(b);
     if (b->llr) cudaFree(b->llr);
     if (b->dx) swd_destroy(b->dx);
     if (b->dz) swd_destroy(b->dz);
@@ -805,8 +838,8 @@ extern "C" int swd_bp4_create(int device, int mx, int mz, int n, const int32_t *
     cfg.kind = SWD_KIND_OSD_WINDOW; cfg.device = device; cfg.max_iter = 1; cfg.ms_scaling_factor = 1.0; cfg.new_n = n;
     cfg.post_max_iter = 0; cfg.osd_method = osd_method; cfg.osd_order = osd_order; cfg.max_iter_per_step = 6; cfg.max_step = 1;
     int st;
-    if ((st = swd_create(&cfg, mx, n, hx_colptr, hx_rowidx, prior_llr_x, &b->dx)) != SWD_OK) { swd_bp4_destroy(b); return st; }
-    if ((st = swd_create(&cfg, mz, n, hz_colptr, hz_rowidx, prior_llr_z, &b->dz)) != SWD_OK) { swd_bp4_destroy(b); return st; }
+    if ((st = create_impl(&cfg, mx, n, hx_colptr, hx_rowidx, prior_llr_x, &b->dx, true)) != SWD_OK) { swd_bp4_destroy(b); return st; }
+    if ((st = create_impl(&cfg, mz, n, hz_colptr, hz_rowidx, prior_llr_z, &b->dz, true)) != SWD_OK) { swd_bp4_destroy(b); return st; }
     b->num_sm = b->dx->num_sm;
     std::vector<double> l(3 * (size_t)n);
     for (int v = 0; v < n; v++) { l[v] = llr_x[v]; l[n + v] = llr_y[v]; l[2 * (size_t)n + v] = llr_z[v]; }
@@ -821,7 +854,8 @@ extern "C" int swd_bp4_create(int device, int mx, int mz, int n, const int32_t *
     b->S.total = o;
     if (o > 227 * 1024) { swd_bp4_destroy(b); set_err("bp4: the two message arrays do not fit in shared memory"); return SWD_ERR_UNSUPPORTED; }
     int occ = 0;
-    if ((st = occupancy(bp4_kernel, 256, b->S.total, &occ)) != SWD_OK || occ < 1) { swd_bp4_destroy(b); if (!st) { set_err("bp4_kernel does not fit"); st = SWD_ERR_UNSUPPORTED; } return st; }
+    if ((st = occupancy(bp4_kernel<true>, 256, b->S.total, &occ)) != SWD_OK || occ < 1 ||
+        (st = occupancy(bp4_kernel<false>, 256, b->S.total, &occ)) != SWD_OK || occ < 1) { swd_bp4_destroy(b); if (!st) { set_err("bp4_kernel does not fit"); st = SWD_ERR_UNSUPPORTED; } return st; }
     b->grid = b->num_sm * occ;
     if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) { swd_bp4_destroy(b); set_err("stream create failed"); return SWD_ERR_CUDA; }
     *out = b;
@@ -864,8 +898,8 @@ extern "C" int swd_bp4_decode_batch_host(swd_bp4 *b, const uint8_t *synd_x, cons
     cudaStream_t s = b->stream;
     CK(cudaMemcpyAsync(b->synd_x, synd_x, (size_t)B * b->mx, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(b->synd_z, synd_z, (size_t)B * b->mz, cudaMemcpyHostToDevice, s));
-    bp4_kernel<<<(int)std::min<long long>(B, b->grid), 256, b->S.total, s>>>(b->dx->g, b->dz->g, b->llr, b->llr + n, b->llr + 2 * n, b->synd_x, b->synd_z, B,
-                                                                             b->max_iter, b->alpha, b->bp_dec, b->conv, b->iters, b->lpr, b->key_x, b->key_z, b->S);
+    bp4_kernel<false><<<(int)std::min<long long>(B, b->grid), 256, b->S.total, s>>>(b->dx->g, b->dz->g, b->llr, b->llr + n, b->llr + 2 * n, b->synd_x, b->synd_z, B,
+                                                                                    b->max_iter, b->alpha, b->bp_dec, b->conv, b->iters, b->lpr, b->key_x, b->key_z, b->S, nullptr);
     CK(cudaGetLastError());
     int st;
     if ((st = bp4_osd_pass(b->dx, b->synd_x, b->key_x, b->conv, B, b->tmp, s))) return st;      // osd('x') -> z part
@@ -879,6 +913,41 @@ extern "C" int swd_bp4_decode_batch_host(swd_bp4 *b, const uint8_t *synd_x, cons
     if (osd0) CK(cudaMemcpyAsync(osd0, b->osd0, (size_t)B * 2 * n, cudaMemcpyDeviceToHost, s));
     if (lpr) CK(cudaMemcpyAsync(lpr, b->lpr, (size_t)B * n * 24, cudaMemcpyDeviceToHost, s));
     if (bp_iteration) CK(cudaMemcpyAsync(bp_iteration, b->iters, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SWD_OK;
+}
+
+// bp4_osd.camel_decode (src/bp4_osd.pyx:223-248) for a batch: four BP runs per shot with the last qubit pinned to I / X / Z / Y,
+// the converged run with the smallest path metric wins.  min_pm: 10000.0 when no run converged (then dec = 0, converge = 0).
+// lpr / bp_iteration: those of the last run (Y), as the reference's properties show after the call.
+extern "C" int swd_bp4_camel_decode_batch_host(swd_bp4 *b, const uint8_t *synd_x, const uint8_t *synd_z, int64_t B, uint8_t *dec, uint8_t *conv,
+                                               double *min_pm, double *lpr, int32_t *bp_iteration) {
+    if (!b || B < 0 || (B > 0 && (!synd_x || !synd_z || !dec || !conv))) { set_err("swd_bp4_camel_decode_batch_host: null argument"); return SWD_ERR_INVALID; }
+    if (B == 0) return SWD_OK;
+    CK(cudaSetDevice(b->device));
+    const size_t n = b->n;
+    if (B > b->cap4) {
+        bp4_free_camel(b);
+        CK(cudaMalloc(&b->c_synd_x, (size_t)B * b->mx)); CK(cudaMalloc(&b->c_synd_z, (size_t)B * b->mz));
+        CK(cudaMalloc(&b->c_bp_dec, (size_t)B * 8 * n)); CK(cudaMalloc(&b->c_conv4, (size_t)B * 4)); CK(cudaMalloc(&b->c_dec, (size_t)B * 2 * n));
+        CK(cudaMalloc(&b->c_conv, (size_t)B)); CK(cudaMalloc(&b->c_it4, (size_t)B * 16)); CK(cudaMalloc(&b->c_it, (size_t)B * 4));
+        CK(cudaMalloc(&b->c_pm4, (size_t)B * 32)); CK(cudaMalloc(&b->c_pm, (size_t)B * 8)); CK(cudaMalloc(&b->c_lpr, (size_t)B * n * 24));
+        b->cap4 = B;
+    }
+    cudaStream_t s = b->stream;
+    CK(cudaMemcpyAsync(b->c_synd_x, synd_x, (size_t)B * b->mx, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b->c_synd_z, synd_z, (size_t)B * b->mz, cudaMemcpyHostToDevice, s));
+    bp4_kernel<true><<<(int)std::min<long long>(4 * B, b->grid), 256, b->S.total, s>>>(b->dx->g, b->dz->g, b->llr, b->llr + n, b->llr + 2 * n, b->c_synd_x, b->c_synd_z, B,
+                                                                                       b->max_iter, b->alpha, b->c_bp_dec, b->c_conv4, b->c_it4, b->c_lpr, nullptr, nullptr, b->S, b->c_pm4);
+    CK(cudaGetLastError());
+    bp4_camel_finish_kernel<<<(unsigned)std::min<long long>((B + 7) / 8, 4096), 256, 0, s>>>(b->c_bp_dec, b->c_conv4, b->c_pm4, b->c_it4, B, (int)n,
+                                                                                             b->c_dec, b->c_conv, b->c_pm, b->c_it);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dec, b->c_dec, (size_t)B * 2 * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(conv, b->c_conv, (size_t)B, cudaMemcpyDeviceToHost, s));
+    if (min_pm) CK(cudaMemcpyAsync(min_pm, b->c_pm, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+    if (lpr) CK(cudaMemcpyAsync(lpr, b->c_lpr, (size_t)B * n * 24, cudaMemcpyDeviceToHost, s));
+    if (bp_iteration) CK(cudaMemcpyAsync(bp_iteration, b->c_it, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return SWD_OK;
 }

@@ -41,20 +41,41 @@ __device__ __forceinline__ void b4_row_update(double *msg, int p0, int p1, u32 p
     }
 }
 
+// CAMEL = true: bp4_osd.camel_decode (pyx:223-248) - an item is (shot, value), value = 0..3 = I / X / Z / Y pinned on the last
+// qubit (vn_set_value, pyx:389-423): the pinned qubit is skipped by the variable pass, its bit-to-check messages keep their
+// initial value, and its contribution to the checks is folded into the syndrome (seed of the check pass = current_cn;
+// H.dec == s  <=>  H_rest.dec_rest == s ^ H_fix.dec_fix).  Per item: converge flag, iteration count, hard decision and the
+// path metric cal_pm (pyx:250-259, ordered sum); the posteriors of the last run (value 3) go to lpr.
+template <bool CAMEL>
 __global__ void __launch_bounds__(256)
 bp4_kernel(GraphDev gx, GraphDev gz, const double *__restrict__ llrx, const double *__restrict__ llry, const double *__restrict__ llrz,
            const u8 *__restrict__ synd_x, const u8 *__restrict__ synd_z, long long B, int max_iter, double alpha,
            u8 *__restrict__ bp_dec /*[B][2n]*/, u8 *__restrict__ conv_out, int *__restrict__ iter_out, double *__restrict__ lpr /*[B][n][3]*/,
-           double *__restrict__ key_x /*[B][n]*/, double *__restrict__ key_z, Bp4Smem S) {
+           double *__restrict__ key_x /*[B][n]*/, double *__restrict__ key_z, Bp4Smem S, double *__restrict__ pm_out) {
     extern __shared__ __align__(16) unsigned char smem[];
     double *mx = (double *)(smem + S.off_mx), *mz = (double *)(smem + S.off_mz);
     u32 *ux = (u32 *)(smem + S.off_ux), *uz = (u32 *)(smem + S.off_uz);
     u8 *sx = smem + S.off_sx, *sz = smem + S.off_sz;
     const int T = blockDim.x, tid = threadIdx.x;
     const int n = gx.n, nmx = gx.m, nmz = gz.m;
-    for (long long shot = blockIdx.x; shot < B; shot += gridDim.x) {
+    const long long items = CAMEL ? 4 * B : B;
+    const int fix = CAMEL ? n - 1 : -1;
+    double fix_mx = 0.0, fix_mz = 0.0;
+    if (CAMEL) {
+        const double lx = llrx[fix], ly = llry[fix], lz = llrz[fix];
+        fix_mx = b4_log1pexp(-1. * lx) - b4_logaddexp(-1. * ly, -1. * lz);
+        fix_mz = b4_log1pexp(-1. * lz) - b4_logaddexp(-1. * ly, -1. * lz);
+    }
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long shot = CAMEL ? (item >> 2) : item;
+        const int value = CAMEL ? (int)(item & 3) : 0;
         for (int r = tid; r < nmx; r += T) sx[r] = synd_x[shot * nmx + r];
         for (int r = tid; r < nmz; r += T) sz[r] = synd_z[shot * nmz + r];
+        if (CAMEL) {
+            __syncthreads();
+            if (value >> 1) for (int e = gx.cp[fix] + tid; e < gx.cp[fix + 1]; e += T) sx[gx.cr[e]] ^= 1;     // z part toggles the Hx checks
+            if (value & 1) for (int e = gz.cp[fix] + tid; e < gz.cp[fix + 1]; e += T) sz[gz.cr[e]] ^= 1;      // x part toggles the Hz checks
+        }
         for (int v = tid; v < n; v += T) {                                     // bp_init, pyx:425-442
             const double lx = llrx[v], ly = llry[v], lz = llrz[v];
             const double msg_x = b4_log1pexp(-1. * lx) - b4_logaddexp(-1. * ly, -1. * lz);
@@ -65,7 +86,12 @@ bp4_kernel(GraphDev gx, GraphDev gz, const double *__restrict__ llrx, const doub
         __syncthreads();
         int conv = 0, it = 0;
         double *lp = lpr + (size_t)shot * n * 3;
-        u8 *bx = bp_dec + (size_t)shot * 2 * n, *bz = bx + n;
+        const bool write_lp = !CAMEL || value == 3;
+        u8 *bx = bp_dec + (size_t)item * 2 * n, *bz = bx + n;
+        if (CAMEL && tid == 0) {
+            bx[fix] = (u8)(value & 1); bz[fix] = (u8)(value >> 1);
+            if (write_lp) { lp[3 * fix] = 0.0; lp[3 * fix + 1] = 0.0; lp[3 * fix + 2] = 0.0; }
+        }
         for (int iter = 0; iter < max_iter; iter++) {
             it++;
             for (int r = tid; r < nmx + nmz; r += T) {                         // cn_update_all('x'), ('z')
@@ -74,6 +100,7 @@ bp4_kernel(GraphDev gx, GraphDev gz, const double *__restrict__ llrx, const doub
             }
             __syncthreads();
             for (int v = tid; v < n; v += T) {                                 // vn_update, pyx:533-591
+                if (CAMEL && v == fix) continue;
                 const int x0 = gx.cp[v], x1 = gx.cp[v + 1], z0 = gz.cp[v], z1 = gz.cp[v + 1];
                 double llrx_hx = 0.0, llrz_hz = 0.0;
                 for (int e = z0; e < z1; e++) llrx_hx += mz[gz.cpos[e]];
@@ -81,7 +108,7 @@ bp4_kernel(GraphDev gx, GraphDev gz, const double *__restrict__ llrx, const doub
                 const double llry_all = llrx_hx + llrz_hz + llry[v];
                 llrx_hx = llrx_hx + llrx[v];
                 llrz_hz = llrz_hz + llrz[v];
-                lp[3 * v] = llrx_hx; lp[3 * v + 1] = llry_all; lp[3 * v + 2] = llrz_hz;
+                if (write_lp) { lp[3 * v] = llrx_hx; lp[3 * v + 1] = llry_all; lp[3 * v + 2] = llrz_hz; }
                 int idx;
                 if (0 < llrx_hx && 0 < llry_all && 0 < llrz_hz) idx = 0;
                 else if (llrx_hx < llry_all && llrx_hx < llrz_hz) idx = 1;
@@ -104,13 +131,28 @@ bp4_kernel(GraphDev gx, GraphDev gz, const double *__restrict__ llrx, const doub
                     mz[p] = num_hz - b4_logaddexp(-1. * (llrx_hx - msg), -1. * (llry_all - msg));
                 }
             }
+            if (CAMEL) {                                                       // the pinned qubit keeps its initial messages
+                for (int e = gx.cp[fix] + tid; e < gx.cp[fix + 1]; e += T) mx[gx.cpos[e]] = fix_mx;
+                for (int e = gz.cp[fix] + tid; e < gz.cp[fix + 1]; e += T) mz[gz.cpos[e]] = fix_mz;
+            }
             __syncthreads();
             int mism = 0;
             for (int r = tid; r < nmx + nmz; r += T) mism |= (r < nmx) ? (ux[r] != (u32)sx[r]) : (uz[r - nmx] != (u32)sz[r - nmx]);
             if (!__syncthreads_or(mism)) { conv = 1; break; }
         }
-        if (tid == 0) { conv_out[shot] = (u8)conv; iter_out[shot] = it; }
-        if (!conv) {                                                           // OSD ranking keys, pyx:280,297
+        if (tid == 0) { conv_out[item] = (u8)conv; iter_out[item] = it; }
+        if (CAMEL) {
+            if (conv && tid == 0) {                                            // cal_pm, pyx:250-259
+                double pm = 0.0;
+                for (int v = 0; v < n; v++) {
+                    const int ex = bx[v], ez = bz[v];
+                    if (ex && ez) pm += llry[v];
+                    else if (ex) pm += llrx[v];
+                    else if (ez) pm += llrz[v];
+                }
+                pm_out[item] = pm;
+            }
+        } else if (!conv) {                                                           // OSD ranking keys, pyx:280,297
             for (int v = tid; v < n; v += T) {
                 const double lx = lp[3 * v], ly = lp[3 * v + 1], lz = lp[3 * v + 2];
                 key_x[(size_t)shot * n + v] = b4_log1pexp(-1. * lx) - b4_logaddexp(-1. * ly, -1. * lz);
@@ -118,6 +160,21 @@ bp4_kernel(GraphDev gx, GraphDev gz, const double *__restrict__ llrx, const doub
             }
         }
         __syncthreads();
+    }
+}
+
+// camel_decode (pyx:229-245): the converged run with the smallest path metric in the order I, X, Z, Y (strict <, start 10000);
+// zeros when no run converged (the reference returns the buffer of an earlier call)
+__global__ void bp4_camel_finish_kernel(const u8 *__restrict__ bp_dec /*[4B][2n]*/, const u8 *__restrict__ conv4, const double *__restrict__ pm4,
+                                        const int *__restrict__ it4, long long B, int n, u8 *__restrict__ dec, u8 *__restrict__ conv,
+                                        double *__restrict__ min_pm, int *__restrict__ iters) {
+    const int warps = (gridDim.x * blockDim.x) >> 5, lane = threadIdx.x & 31;
+    for (long long b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
+        double best = 10000.0; int arg = -1;
+        for (int v = 0; v < 4; v++) if (conv4[4 * b + v] && pm4[4 * b + v] < best) { best = pm4[4 * b + v]; arg = v; }
+        const u8 *src = bp_dec + (size_t)(4 * b + (arg < 0 ? 0 : arg)) * 2 * n;
+        for (int i = lane; i < 2 * n; i += 32) dec[(size_t)b * 2 * n + i] = (arg < 0) ? (u8)0 : src[i];
+        if (lane == 0) { conv[b] = (u8)(best < 9999.0); min_pm[b] = best; iters[b] = it4[4 * b + 3]; }
     }
 }
 

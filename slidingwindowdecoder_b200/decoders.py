@@ -296,8 +296,9 @@ class bp4_osd:
     (`channel_probs_x/y/z`, `max_iter=32`, `ms_scaling_factor=1.0`, `osd_method="osd_0"`, `osd_order=0`),
     `decode(synd_x, synd_z) -> np.int64[2, n]` (row 0: X part, row 1: Z part), `.converge`, `.bp_iteration`, `.min_pm`
     (0.0, as in the reference whose decode never updates it), `.bp_decoding_x/z`, `.osd0_decoding_x/z`,
-    `.osdw_decoding_x/z`, `.log_prob_ratios` [n, 3].  Added: `decode_batch(synd_x[B, mx], synd_z[B, mz])`.
-    `camel_decode` (pyx:223-248) is not provided."""
+    `.osdw_decoding_x/z`, `.log_prob_ratios` [n, 3], and `camel_decode(synd_x, synd_z)` (pyx:223-248: four BP runs with the last
+    qubit pinned to I / X / Z / Y, best converged path metric; sets `.converge`, `.min_pm`).
+    Added: `decode_batch(synd_x[B, mx], synd_z[B, mz])`, `camel_decode_batch(...)`."""
 
     def __init__(self, Hx, Hz, **kwargs):
         if not (isinstance(Hx, np.ndarray) or isinstance(Hx, spmatrix)):
@@ -377,6 +378,30 @@ class bp4_osd:
         self._last = {k: v[0] for k, v in out.items()}
         self.converge = int(self._last["converge"]); self.bp_iteration = int(self._last["bp_iteration"])
         return self._last["dec"].astype(np.int64)
+
+    def camel_decode_batch(self, synd_x, synd_z):
+        """-> dict(dec [B, 2, n] uint8, converge [B], min_pm [B], log_prob_ratios [B, n, 3] and bp_iteration [B] of the last run)"""
+        sx = np.ascontiguousarray(np.asarray(synd_x), dtype=np.uint8); sz = np.ascontiguousarray(np.asarray(synd_z), dtype=np.uint8)
+        if sx.ndim != 2 or sz.ndim != 2 or sx.shape[1] != self.mx or sz.shape[1] != self.mz or sx.shape[0] != sz.shape[0]:
+            raise ValueError(f"camel_decode_batch expects syndromes of shape [B, {self.mx}] and [B, {self.mz}]")
+        B, n = sx.shape[0], self.n
+        dec = np.empty((B, 2, n), dtype=np.uint8); conv = np.empty(B, dtype=np.uint8); pm = np.empty(B)
+        lpr = np.empty((B, n, 3)); it = np.empty(B, dtype=np.int32)
+        st = self._lib.swd_bp4_camel_decode_batch_host(self._handle, sx.ctypes.data, sz.ctypes.data, B, dec.ctypes.data, conv.ctypes.data,
+                                                       pm.ctypes.data_as(C.POINTER(C.c_double)), lpr.ctypes.data_as(C.POINTER(C.c_double)), it.ctypes.data)
+        _lib.check(st, "swd_bp4_camel_decode_batch_host")
+        return dict(dec=dec, converge=conv, min_pm=pm, log_prob_ratios=lpr, bp_iteration=it)
+
+    def camel_decode(self, input_vector_x, input_vector_z):
+        if input_vector_x.shape[0] != self.mx or input_vector_z.shape[0] != self.mz:
+            raise ValueError(f"The input to the bp4_osd.decode must be a syndrome (of length={self.mx}).")
+        out = self.camel_decode_batch(np.asarray(input_vector_x).reshape(1, -1), np.asarray(input_vector_z).reshape(1, -1))
+        last = {k: v[0] for k, v in out.items()}
+        # the reference keeps the winning run in osd0_decoding and leaves bp_decoding at the last (Y) run, which is not kept here
+        last["osd0"] = last["dec"]; last["bp_decoding"] = last["dec"]
+        self._last = last
+        self.converge = int(last["converge"]); self.bp_iteration = int(last["bp_iteration"]); self.min_pm = float(last["min_pm"])
+        return last["dec"].astype(np.int64)
 
     bp_decoding_x = property(lambda self: self._last["bp_decoding"][0].astype(np.int64))
     bp_decoding_z = property(lambda self: self._last["bp_decoding"][1].astype(np.int64))

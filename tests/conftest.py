@@ -40,6 +40,7 @@ GOLDEN_OSD = ["c1_osdw_osd_00", "c1_osdw_osd_cs10", "c1_osdw_osd_e6", "c2_w0_osd
 
 
 GOLDEN_BP4 = ["c1_bp4_osd_00", "c1_bp4_osd_cs8", "c1_bp4_osd_e5"]
+GOLDEN_CAMEL = ["c1_bp4_camel", "c1_bp4_camel_tied"]      # camel_decode; the same layout plus min_pm [B]
 
 
 def load_golden_bp4(name):

@@ -146,12 +146,47 @@ def bp4_section():
         print("wrote", name, "shots", shots, "converged", int(conv.sum()))
 
 
+def camel_section():
+    """bp4_osd.camel_decode (src/bp4_osd.pyx:223-248): (a) the [[72,12,6]] matrices as they are, (b) a CAMEL-shaped pair
+    Hx = (H1 | 1), Hz = (H2 | 1) (Misc.ipynb cell 6): an all-ones last column ties every check to the pinned qubit.
+    A fresh decoder per shot, so a shot on which none of the four runs converges returns the zero-initialised buffer."""
+    from src.bp4_osd import bp4_osd
+    from slidingwindowdecoder_b200.codes import bb_code
+    code, _, _ = bb_code(72)
+    for tag, tied in (("c1_bp4_camel", False), ("c1_bp4_camel_tied", True)):
+        Hx, Hz = np.asarray(code.hx).astype(np.int64), np.asarray(code.hz).astype(np.int64)
+        if tied:
+            Hx = np.hstack([Hx, np.ones((Hx.shape[0], 1), dtype=np.int64)]); Hz = np.hstack([Hz, np.ones((Hz.shape[0], 1), dtype=np.int64)])
+        n = Hx.shape[1]
+        rng = np.random.default_rng(505 + tied)
+        p = 0.08
+        px, py, pz = (p / 3 * (1 + 0.2 * rng.random(n)) for _ in range(3))
+        shots = 400
+        r = rng.random((shots, n))
+        isx, isy, isz = r < px, (r >= px) & (r < px + py), (r >= px + py) & (r < px + py + pz)
+        ex, ez = (isx | isy).astype(np.int64), (isy | isz).astype(np.int64)
+        sx, sz = (ez @ Hx.T % 2).astype(np.uint8), (ex @ Hz.T % 2).astype(np.uint8)
+        hx_shape, hx_p, hx_i = csc_of(Hx); hz_shape, hz_p, hz_i = csc_of(Hz)
+        kw = dict(max_iter=24, ms_scaling_factor=0.9, osd_method="osd_0", osd_order=0)
+        dec = np.zeros((shots, 2 * n), dtype=np.uint8); conv = np.zeros(shots, dtype=np.uint8); it = np.zeros(shots, dtype=np.int32)
+        lpr = np.zeros((shots, n, 3)); pm = np.zeros(shots)
+        for i in range(shots):
+            d = bp4_osd(Hx, Hz, channel_probs_x=px, channel_probs_y=py, channel_probs_z=pz, **kw)
+            dec[i] = d.camel_decode(sx[i], sz[i]).reshape(-1); conv[i] = int(d.converge); it[i] = d.bp_iteration
+            lpr[i] = d.log_prob_ratios; pm[i] = d.min_pm
+        np.savez_compressed(os.path.join(OUT, tag + ".npz"), hx_shape=np.array(hx_shape), hx_indptr=hx_p, hx_indices=hx_i,
+                            hz_shape=np.array(hz_shape), hz_indptr=hz_p, hz_indices=hz_i, px=px, py=py, pz=pz,
+                            synd_x=np.packbits(sx, axis=1), synd_z=np.packbits(sz, axis=1), kwargs=np.array(repr(kw)),
+                            dec=np.packbits(dec, axis=1), conv=conv, bp_iteration=it, lpr_first16=lpr[:16], min_pm=pm)
+        print("wrote", tag, "shots", shots, "converged", int(conv.sum()))
+
+
 def main():
     build_reference()
-    if len(sys.argv) > 1 and sys.argv[1] == "bp4":
+    if len(sys.argv) > 1 and sys.argv[1] in ("bp4", "camel"):
         devnull = os.open(os.devnull, os.O_WRONLY)
         os.dup2(devnull, 2)
-        bp4_section()
+        bp4_section() if sys.argv[1] == "bp4" else camel_section()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "c4":
         devnull = os.open(os.devnull, os.O_WRONLY)
@@ -245,6 +280,7 @@ def main():
     shyps_section(bpgdg_decoder, osd_window)
     c4_section(bpgdg_decoder, osd_window)
     bp4_section()
+    camel_section()
 
 
 if __name__ == "__main__":

@@ -601,3 +601,39 @@ def test_bp4_osd_matches_oracle_and_golden(name, oracle_mod):
     assert one.shape == (2, n) and np.array_equal(one.reshape(-1).astype(np.uint8), out["dec"][3].reshape(-1))
     assert dec.converge == int(g["conv"][3]) and dec.bp_iteration == int(g["bp_iteration"][3])
     assert dec.log_prob_ratios.shape == (n, 3) and dec.osdw_decoding_x.shape == (n,)
+
+
+@pytest.mark.parametrize("name", __import__("conftest").GOLDEN_CAMEL)
+def test_bp4_camel_decode_matches_golden(name, oracle_mod):
+    """bp4_osd.camel_decode on the GPU against the compiled reference's outputs (floating-point bar as for bp4_osd.decode:
+    exp / log1p come from libdevice): converge flags and iteration counts equal, corrections equal on >= 99.9 % of the shots,
+    path metrics and posteriors within 1e-6 relative.  The tied fixture has an all-ones last column (weight 36 per basis)."""
+    from conftest import load_golden_bp4
+    from slidingwindowdecoder_b200 import bp4_osd
+    g = load_golden_bp4(name)
+    dec = bp4_osd(g["hx"], g["hz"], channel_probs_x=g["px"], channel_probs_y=g["py"], channel_probs_z=g["pz"], **g["kwargs"])
+    out = dec.camel_decode_batch(g["synd_x"], g["synd_z"])
+    B, n = len(g["conv"]), g["hx"].shape[1]
+    assert np.array_equal(out["converge"], g["conv"])
+    assert np.array_equal(out["bp_iteration"], g["bp_iteration"])
+    same = (out["dec"].reshape(B, 2 * n) == g["dec"]).all(axis=1)
+    assert same.mean() >= 0.999, same.mean()
+    assert np.max(np.abs(out["min_pm"] - g["min_pm"]) / np.maximum(1.0, np.abs(g["min_pm"]))) < 1e-6
+    a, b = out["log_prob_ratios"][:16], g["lpr_first16"]
+    assert np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))) < 1e-6
+    hx, hz = np.asarray(g["hx"].todense()).astype(np.int64), np.asarray(g["hz"].todense()).astype(np.int64)
+    ex, ez = out["dec"][:, 0].astype(np.int64), out["dec"][:, 1].astype(np.int64)
+    ok = out["converge"] == 1
+    assert np.array_equal((ez[ok] @ hx.T) % 2, g["synd_x"][ok]) and np.array_equal((ex[ok] @ hz.T) % 2, g["synd_z"][ok])
+    assert not out["dec"][~ok].any()
+    one = dec.camel_decode(g["synd_x"][5], g["synd_z"][5])
+    assert one.shape == (2, n) and np.array_equal(one.reshape(-1).astype(np.uint8), out["dec"][5].reshape(-1))
+    assert dec.converge == int(g["conv"][5]) and abs(dec.min_pm - g["min_pm"][5]) < 1e-6 * max(1.0, abs(g["min_pm"][5]))
+    # decode() on the tied pair exercises the OSD on a graph with a weight-36 column
+    o2 = dec.decode_batch(g["synd_x"][:64], g["synd_z"][:64])
+    orc = oracle_mod.Bp4Oracle(g["hx"], g["hz"], g["px"], g["py"], g["pz"])
+    agree = 0
+    for i in range(64):
+        o = orc.decode(g["synd_x"][i], g["synd_z"][i], **g["kwargs"])
+        agree += int(np.array_equal(o["dec"].reshape(-1).astype(np.uint8), o2["dec"][i].reshape(-1)) and o["converge"] == int(o2["converge"][i]))
+    assert agree >= 63, agree

@@ -138,3 +138,22 @@ def test_bp4_osd_matches_reference(name, oracle_mod):
         assert o["converge"] == int(g["conv"][i]) and o["bp_iteration"] == int(g["bp_iteration"][i])
         if i < 16:
             assert np.array_equal(o["log_prob_ratios"], g["lpr_first16"][i])
+
+
+@pytest.mark.parametrize("name", __import__("conftest").GOLDEN_CAMEL)
+def test_bp4_camel_decode_matches_reference(name, oracle_mod):
+    """bp4_osd.camel_decode (pyx:223-248; four runs with the last qubit pinned, best converged path metric) - the C restatement
+    against the compiled reference, incl. a CAMEL-shaped pair whose last column touches every check: bit-identical
+    corrections, converge flags, path metrics, iteration counts and posteriors of the last run."""
+    from conftest import load_golden_bp4
+    g = load_golden_bp4(name)
+    orc = oracle_mod.Bp4Oracle(g["hx"], g["hz"], g["px"], g["py"], g["pz"])
+    kw = {k: g["kwargs"][k] for k in ("max_iter", "ms_scaling_factor")}
+    assert 0 < int(g["conv"].sum()) < len(g["conv"])
+    for i in range(len(g["conv"])):
+        o = orc.camel_decode(g["synd_x"][i], g["synd_z"][i], **kw)
+        assert np.array_equal(o["dec"].reshape(-1).astype(np.uint8), g["dec"][i]), (name, i)
+        assert o["converge"] == int(g["conv"][i]) and o["bp_iteration"] == int(g["bp_iteration"][i])
+        assert o["min_pm"] == g["min_pm"][i]
+        if i < 16:
+            assert np.array_equal(o["log_prob_ratios"], g["lpr_first16"][i])
