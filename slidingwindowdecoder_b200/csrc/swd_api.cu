@@ -379,6 +379,11 @@ static int setup_kernels(swd_decoder *d) {
     SortSmem &S2 = d->SS;
     int np2 = 64; while (np2 < n) np2 <<= 1;
     S2.np2 = np2;
+    S2.cap_sel = 0;
+    if (c.kind != SWD_KIND_OSD_WINDOW && np2 >= 2048 && !getenv("SWD_FULL_SORT")) {
+        int cap = 64; while (cap < nn + 64) cap <<= 1;
+        if (cap <= np2 / 4) S2.cap_sel = cap;
+    }
     d->T2 = std::min(1024, std::max(128, np2 / 8));
     if (const char *e = getenv("SWD_T2")) d->T2 = std::min(1024, std::max(64, r32up(atoi(e))));
     o = 0; S2.off_key = o; o += 8 * np2; S2.off_idx = o; o += 2 * np2; o = r16(o);

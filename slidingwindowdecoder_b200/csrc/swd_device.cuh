@@ -207,6 +207,162 @@ __device__ __forceinline__ void block_bitonic_sort(double *key, u16 *idx, int NP
     }
 }
 
+// The same argsort with E = NP2 / blockDim.x elements per thread held in registers (element i = tid * E + e): strides
+// below E are compare-exchanges between registers, strides below 32 E are warp shuffles, and only the strides that cross
+// warps go through shared memory (conflict-free transposed image, two barriers each): 6 block-wide exchange stages
+// instead of 66 barrier-separated passes for NP2 = 2048.  (key, idx) is a strict total order on the real entries, so any
+// correct network returns the order of std::stable_sort.  Loads the keys itself: src[0..n) (global), padded with
+// (+inf, 0xffff); leaves the sorted idx[] (and key[]) in shared memory in natural order.  Contains __syncthreads().
+__device__ __forceinline__ bool pair_less(double a, u32 ia, double b, u32 ib) { return (a < b) || (!(b < a) && ia < ib); }
+
+template <int E>
+__device__ __forceinline__ void block_bitonic_sort_regs(double *key, u16 *idx, int NP2, const double *__restrict__ src, int n) {
+    const int T = blockDim.x, tid = threadIdx.x;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double k_[E]; u32 i_[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const int i = tid * E + e;
+        k_[e] = (i < n) ? src[i] : inf;
+        i_[e] = (i < n) ? (u32)i : 0xffffu;
+    }
+    // runs up to length E: registers only
+#pragma unroll
+    for (int k = 2; k <= E; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                if ((e & j) == 0) {
+                    const bool asc = (((tid * E + e) & k) == 0);
+                    const bool gt = pair_less(k_[e | j], i_[e | j], k_[e], i_[e]);
+                    if (gt == asc) { const double tk = k_[e]; k_[e] = k_[e | j]; k_[e | j] = tk; const u32 ti = i_[e]; i_[e] = i_[e | j]; i_[e | j] = ti; }
+                }
+            }
+        }
+    }
+    for (int k = 2 * E; k <= NP2; k <<= 1) {
+        const bool asc = (((tid * E) & k) == 0);
+        for (int j = k >> 1; j >= E; j >>= 1) {
+            const int dj = j / E;                                  // distance in threads
+            const bool keep_min = (((tid & dj) == 0) == asc);
+            if (dj < 32) {
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    const double pk = __shfl_xor_sync(FULLMASK, k_[e], dj);
+                    const u32 pi = __shfl_xor_sync(FULLMASK, i_[e], dj);
+                    const bool pl = pair_less(pk, pi, k_[e], i_[e]);
+                    const bool sl = pair_less(k_[e], i_[e], pk, pi);
+                    if (keep_min ? pl : sl) { k_[e] = pk; i_[e] = pi; }
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; e++) { key[e * T + tid] = k_[e]; idx[e * T + tid] = (u16)i_[e]; }
+                __syncthreads();
+                const int pt = tid ^ dj;
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    const double pk = key[e * T + pt];
+                    const u32 pi = idx[e * T + pt];
+                    const bool pl = pair_less(pk, pi, k_[e], i_[e]);
+                    const bool sl = pair_less(k_[e], i_[e], pk, pi);
+                    if (keep_min ? pl : sl) { k_[e] = pk; i_[e] = pi; }
+                }
+                __syncthreads();
+            }
+        }
+#pragma unroll
+        for (int j = E >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                if ((e & j) == 0) {
+                    const bool gt = pair_less(k_[e | j], i_[e | j], k_[e], i_[e]);
+                    if (gt == asc) { const double tk = k_[e]; k_[e] = k_[e | j]; k_[e | j] = tk; const u32 ti = i_[e]; i_[e] = i_[e | j]; i_[e | j] = ti; }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; e++) { key[tid * E + e] = k_[e]; idx[tid * E + e] = (u16)i_[e]; }
+    __syncthreads();
+}
+
+// The GDG kinds keep only the nn columns with the smallest keys (BPGD::reset copies the first new_n sorted columns,
+// bpgd.cpp:199-209; the dropped ones are zeroed whatever their order), so a full argsort of n keys is not needed:
+// radix-select the nn-th smallest on the order-preserving integer image of the keys (11 + 11 leading bits, two shared-
+// memory histograms), compact the candidates (everything up to and including the boundary bucket, so ties stay
+// together) and sort those CAP << n pairs.  idx[0..nn) then equals the first nn entries of the full stable argsort.
+// Returns false (nothing written that matters) when the boundary bucket is too crowded - the caller sorts everything.
+// E * blockDim.x >= n; key needs >= 2049 u32 and >= CAP u64; misc[4..7] and wt (>= 33 u32) are scratch.
+__device__ __forceinline__ u64 ordered_key(double x) {
+    if (x == 0.0) x = 0.0;                                          // -0.0 and +0.0 compare equal
+    const u64 b = (u64)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+template <int E>
+__device__ __forceinline__ bool block_select_sort(double *key, u16 *idx, u32 *wt, int *misc, const double *__restrict__ src,
+                                                  int n, int nn, int CAP) {
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
+    u32 *hist = (u32 *)key; u64 *ckey = (u64 *)key;
+    u64 k_[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) { const int i = tid * E + e; k_[e] = (i < n) ? ordered_key(src[i]) : ~0ull; }
+    for (int b = tid; b <= 2048; b += T) hist[b] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < E; e++) if (tid * E + e < n) atomicAdd(&hist[(u32)(k_[e] >> 53)], 1u);
+    __syncthreads();
+    block_excl_scan(hist, 2049, wt);
+    for (int b = tid; b < 2048; b += T) if ((int)hist[b] < nn && (int)hist[b + 1] >= nn) { misc[4] = b; misc[5] = (int)hist[b]; misc[6] = (int)hist[b + 1]; }
+    __syncthreads();
+    const u32 b1 = (u32)misc[4]; const int below = misc[5]; int upto = misc[6];
+    u64 thr = b1; int sh = 53;
+    if (upto > CAP) {                                                // refine inside the boundary bucket
+        __syncthreads();
+        for (int b = tid; b <= 2048; b += T) hist[b] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < E; e++) if (tid * E + e < n && (u32)(k_[e] >> 53) == b1) atomicAdd(&hist[(u32)(k_[e] >> 42) & 0x7ffu], 1u);
+        __syncthreads();
+        block_excl_scan(hist, 2049, wt);
+        const int need = nn - below;
+        for (int b = tid; b < 2048; b += T) if ((int)hist[b] < need && (int)hist[b + 1] >= need) { misc[4] = b; misc[6] = below + (int)hist[b + 1]; }
+        __syncthreads();
+        thr = ((u64)b1 << 11) | (u32)misc[4]; sh = 42; upto = misc[6];
+        if (upto > CAP) return false;
+    }
+    __syncthreads();
+    if (tid == 0) misc[7] = 0;
+    for (int p = upto + tid; p < CAP; p += T) { ckey[p] = ~0ull; idx[p] = (u16)0xffff; }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const int i = tid * E + e;
+        const bool cand = (i < n) && ((k_[e] >> sh) <= thr);
+        const u32 bal = __ballot_sync(FULLMASK, cand);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&misc[7], __popc(bal));
+        base = __shfl_sync(FULLMASK, base, 0);
+        if (cand) { const int pos = base + __popc(bal & ((1u << lane) - 1)); ckey[pos] = k_[e]; idx[pos] = (u16)i; }
+    }
+    __syncthreads();
+    for (int k = 2; k <= CAP; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (CAP >> 1); t += T) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
+                const bool asc = ((lo & k) == 0);
+                const u64 a = ckey[lo], b = ckey[hi];
+                const u16 ia = idx[lo], ib = idx[hi];
+                const bool gt = (b < a) || (b == a && ib < ia);
+                if (gt == asc) { ckey[lo] = b; ckey[hi] = a; idx[lo] = ib; idx[hi] = ia; }
+            }
+            __syncthreads();
+        }
+    }
+    return true;
+}
+
 // ----------------------------------------------------------------------------------------------
 // branch-path context (all pointers into shared memory)
 // ----------------------------------------------------------------------------------------------

@@ -193,9 +193,10 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
 // ----------------------------------------------------------------------------------------------
 // K2: sort + reset
 // ----------------------------------------------------------------------------------------------
-struct SortSmem { int off_key, off_idx, off_posof, off_blob, off_u32a, off_u32b, off_u32c, off_wt, off_error, off_misc, off_bins, total; int np2; };
+struct SortSmem { int off_key, off_idx, off_posof, off_blob, off_u32a, off_u32b, off_u32c, off_wt, off_error, off_misc, off_bins, total; int np2;
+                  int cap_sel; };     // > 0: GDG kinds select + sort the cap_sel smallest keys instead of sorting all n
 
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(1024, 1)
 sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayout L, GdgDev P, SortSmem S,
                   u8 *__restrict__ dec_out, int capA) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -233,13 +234,23 @@ sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayo
     for (int slot = blockIdx.x; slot < count; slot += gridDim.x) {
         const int shot = ws.gdg_list[slot];
         const double inf = __longlong_as_double(0x7ff0000000000000LL);
-        for (int i = tid; i < NP2; i += T) {
-            key[i] = (i < n) ? ws.sum[(size_t)slot * n + i] : inf;
-            idx[i] = (i < n) ? (u16)i : (u16)0xffff;
+        bool partial = false;                                       // only idx[0..nn) is ordered, posof = 0xffff for the rest
+        if (S.cap_sel > 0 && NP2 == 8 * T)
+            partial = block_select_sort<8>(key, idx, wt, misc, ws.sum + (size_t)slot * n, n, nn, S.cap_sel);
+        if (partial) {
+            for (int cI = tid; cI < n; cI += T) posof[cI] = (u16)0xffff;
+            __syncthreads();
+        } else if (NP2 == 8 * T) {
+            block_bitonic_sort_regs<8>(key, idx, NP2, ws.sum + (size_t)slot * n, n);      // 8 keys per thread in registers
+        } else {
+            for (int i = tid; i < NP2; i += T) {
+                key[i] = (i < n) ? ws.sum[(size_t)slot * n + i] : inf;
+                idx[i] = (i < n) ? (u16)i : (u16)0xffff;
+            }
+            __syncthreads();
+            block_bitonic_sort(key, idx, NP2);
         }
-        __syncthreads();
-        block_bitonic_sort(key, idx, NP2);
-        for (int j = tid; j < n; j += T) posof[idx[j]] = (u16)j;
+        for (int j = tid; j < (partial ? nn : n); j += T) posof[idx[j]] = (u16)j;
         if (P.kind == SWD_KIND_OSD_WINDOW)          // decided-0 key of the dropped columns (osd_window.pyx:208-209)
             for (int j = nn + tid; j < n; j += T) ws.sum[(size_t)slot * n + idx[j]] = 1000.0;
         for (int j = tid; j < nn; j += T) {
@@ -324,7 +335,8 @@ sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayo
             for (int j = nn + tid; j <= failpos && j < n; j += T) dec_out[(size_t)shot * n + idx[j]] = 0;
             status = -2;
         } else {
-            for (int j = nn + tid; j < n; j += T) dec_out[(size_t)shot * n + idx[j]] = 0;   // pyx:250-251 / :270-271
+            if (partial) { for (int cI = tid; cI < n; cI += T) if (posof[cI] >= nn) dec_out[(size_t)shot * n + cI] = 0; }
+            else for (int j = nn + tid; j < n; j += T) dec_out[(size_t)shot * n + idx[j]] = 0;   // pyx:250-251 / :270-271
             Ctx c;
             c.m = m; c.nn = nn; c.es = es; c.msg = nullptr; c.prior = prior; c.voff = voff; c.vrow = vrow; c.vpos = vpos;
             c.coff = coff; c.crank = crank; c.cvn = cvn; c.vperm = vperm; c.cperm = cperm; c.synd = s_synd; c.vn_mask = vn_mask; c.error = s_error; c.cn_mask = cn_mask;
