@@ -468,7 +468,7 @@ static int setup_kernels(swd_decoder *d) {
 static int alloc_workspace(swd_decoder *d, long long want) {
     if (want <= d->cap) return SWD_OK;
     CK(cudaSetDevice(d->device));
-    size_t budget = (size_t)8 << 30;
+    size_t budget = (size_t)16 << 30;     // per decoder; 180 GB of HBM3e per GPU
     if (const char *e = getenv("SWD_WS_BYTES")) budget = (size_t)atoll(e);
     const int n = d->n;
     const bool osd = d->cfg.kind == SWD_KIND_OSD_WINDOW;
