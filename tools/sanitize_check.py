@@ -3,8 +3,8 @@ import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
-from conftest import load_golden
-from slidingwindowdecoder_b200 import bpgdg_decoder, bpgd_decoder, osd_window
+from conftest import load_golden, load_golden_bp4
+from slidingwindowdecoder_b200 import bpgdg_decoder, bpgd_decoder, osd_window, bp4_osd
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 48
 for name, cls in (("c2_w1_gdg_mt1", bpgdg_decoder), ("c2_w1_gdg_mt0", bpgdg_decoder), ("c1_bpgd", bpgd_decoder),
@@ -13,3 +13,17 @@ for name, cls in (("c2_w1_gdg_mt1", bpgdg_decoder), ("c2_w1_gdg_mt0", bpgdg_deco
     d = cls(g["mat"], channel_probs=g["priors"], **g["kwargs"])
     corr, conv = d.decode_batch(g["synd"][:n])
     print(name, "ok", bool(np.array_equal(corr, g["dec"][:n]) or name.endswith("mt1")), int(conv.sum()))
+
+# a [[144,12,12]] window (n = 1728): the radix-select / partial-sort path of sort_reset_kernel
+g = load_golden("c3_w5_gdg_mt1")
+d = bpgdg_decoder(g["mat"], channel_probs=g["priors"], **g["kwargs"])
+k = max(4, n // 6)
+corr, conv = d.decode_batch(g["synd"][:k])
+print("c3_w5_gdg_mt1", "ok", int((corr == g["dec"][:k]).all(axis=1).sum()), "of", k, int(conv.sum()))
+# bp4_osd decode + camel_decode on the pair with an all-ones last column
+g = load_golden_bp4("c1_bp4_camel_tied")
+d = bp4_osd(g["hx"], g["hz"], channel_probs_x=g["px"], channel_probs_y=g["py"], channel_probs_z=g["pz"], **g["kwargs"])
+out = d.camel_decode_batch(g["synd_x"][:n], g["synd_z"][:n])
+print("c1_bp4_camel_tied", "ok", bool(np.array_equal(out["converge"], g["conv"][:n])), int(out["converge"].sum()))
+out = d.decode_batch(g["synd_x"][:n], g["synd_z"][:n])
+print("c1_bp4 decode (tied)", "ok", int(out["converge"].sum()))
