@@ -18,6 +18,7 @@ import sys
 import threading
 import time
 
+_STDOUT = sys.stdout
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -418,7 +419,7 @@ def run_ours(args):
                     "gdg_fraction": round(ctr["gdg_shots"] / max(1, ctr["shots"]), 4)},
         "counters": ctr_timed,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -466,7 +467,7 @@ def run_reference(args):
                                                           "15 std::threads per decode, 48 shots" if as_shipped else "oracle/_ref not built"},
             "e2e": {"value": round(v, 2), "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "results": {"shots": n, "failed": fails}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_STDOUT, flush=True)
 
 
 def main():
@@ -481,6 +482,12 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: do not time the CPU baseline")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
+    # the contract is ONE JSON line on stdout: libraries that write to fd 1 themselves (NCCL prints its version banner
+    # there) are sent to stderr, the line itself goes to the saved descriptor
+    global _STDOUT
+    sys.stdout.flush()
+    _STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     select_workload(args.workload)
     if args.impl == "reference":
         run_reference(args)
