@@ -52,7 +52,7 @@ struct swd_decoder {
     bool osd_only = false;
     int device = 0, num_sm = 0;
     GraphDev g{};
-    void *d_graph[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *d_graph[11] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     SubLayout L{}, LsA{}, LsB{};
     PathSmem PS{}, PSB{};
     int es_capA = 0, grid3B = 0;
@@ -222,6 +222,31 @@ static int create_impl(const swd_config *cfg, int m, int n, const int32_t *colpt
         (st = upload(cr16, &d->d_graph[3])) || (st = upload(cpos16, &d->d_graph[4])) || (st = upload(llr, &d->d_graph[5])) ||
         (st = upload(vord, &d->d_graph[6])) || (st = upload(vrec, &d->d_graph[7])) || (st = upload(llr_s, &d->d_graph[8]))) {
         swd_destroy(d); return st;
+    }
+    d->g.c2b1 = nullptr; d->g.rowof = nullptr;
+    if (!osd_only && cfg->bp_method == SWD_BP_MIN_SUM && !getenv("SWD_NO_FIRST_PASS_TABLE")) {
+        // the check pass of iteration 1 for syndrome 0, with the kernel's own arithmetic (osd / bpgd pyx:62-96)
+        std::vector<double> t(std::max(nnz, 1)); std::vector<u16> ro(std::max(nnz, 1));
+        const double alpha = cfg->ms_scaling_factor;
+        for (int r = 0; r < m; r++) {
+            double m1 = SWD_BIG, m2 = SWD_BIG; int arg = -1; unsigned par = 0;
+            for (int p = rp[r]; p < rp[r + 1]; p++) {
+                const double b = llr[rc[p]];
+                double a = fabs(b); a = (a > SWD_CLIP) ? SWD_CLIP : a;
+                const bool lt = a < m1; const double hi = lt ? m1 : a;
+                m2 = (hi < m2) ? hi : m2; m1 = lt ? a : m1; arg = lt ? p : arg;
+                par ^= (unsigned)(b <= 0.0);
+            }
+            const double q1 = m1 * alpha, q2 = m2 * alpha;
+            for (int p = rp[r]; p < rp[r + 1]; p++) {
+                const double b = llr[rc[p]];
+                const double q = (p == arg) ? q2 : q1;
+                t[p] = ((par ^ (unsigned)(b <= 0.0)) & 1u) ? -q : q;
+                ro[p] = (u16)r;
+            }
+        }
+        if ((st = upload(t, &d->d_graph[9])) || (st = upload(ro, &d->d_graph[10]))) { swd_destroy(d); return st; }
+        d->g.c2b1 = (const double *)d->d_graph[9]; d->g.rowof = (const u16 *)d->d_graph[10];
     }
     d->g.m = m; d->g.n = n; d->g.nnz = nnz;
     d->g.rp = (const int *)d->d_graph[0]; d->g.rc = (const u16 *)d->d_graph[1]; d->g.cp = (const int *)d->d_graph[2];

@@ -68,6 +68,11 @@ struct GraphDev {               // static window graph (device pointers)
     const double *llr;          // [n]
     const u32 *vrec;            // [n]    per ownership slot: first CSC entry | degree << 16   (pre-BP kernel)
     const double *llr_s;        // [n]    llr in ownership-slot order
+    // first check pass of the full-window min-sum BP for an all-zero syndrome: in iteration 1 every bit-to-check message
+    // is its column's prior (pyx:55-60), so the check-to-bit magnitudes do not depend on the shot and a syndrome bit
+    // only flips the sign of its row.  nullptr: not available (product-sum, osd-only graphs).
+    const double *c2b1;         // [nnz]  CSR order
+    const u16 *rowof;           // [nnz]  CSR position -> row
 };
 
 struct GdgDev {                 // parameters of the decimation tree
@@ -433,6 +438,18 @@ __device__ __forceinline__ int peel_warp(Ctx &c, int lane) {
             if (!b) { cn += 32; continue; }
             r = cn + __ffs(b) - 1;
             if (c.cn_deg[r] == 0) {                 // bpgd.cpp:22-26
+                if (!HASMSG) {
+                    // reset-time peel (many emptied checks): retire every degree-0 candidate of this ballot window that comes
+                    // before its first degree-1 candidate at once - they only get their mask cleared, in any order
+                    const bool z = cand && (c.cn_deg[cn + lane] == 0);
+                    const u32 zb = __ballot_sync(FULLMASK, z), ob = b & ~zb;
+                    const u32 upto = ob ? ((1u << (__ffs(ob) - 1)) - 1u) : 0xffffffffu;
+                    __syncwarp();
+                    if (z && ((1u << lane) & upto)) c.cn_mask[cn + lane] = -1;
+                    __syncwarp();
+                    cn = ob ? cn + __ffs(ob) - 1 : cn + 32;
+                    continue;
+                }
                 __syncwarp();
                 if (lane == 0) c.cn_mask[r] = -1;
                 __syncwarp();

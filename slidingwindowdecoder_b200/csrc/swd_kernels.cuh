@@ -80,6 +80,14 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
 
     for (long long shot = blockIdx.x; shot < B; shot += gridDim.x) {
         for (int r = tid; r < m; r += T) s_synd[r] = synd[shot * m + r];
+        const bool table1 = !PS && g.c2b1 != nullptr;        // iteration 1's check pass comes from the static table
+        if (table1) {
+            __syncthreads();
+            for (int r = tid; r < m; r += T) upar[r] = 0;
+#pragma unroll 4
+            for (int p = tid; p < g.nnz; p += T) msg[p] = flip_sign(g.c2b1[p], (u32)s_synd[g.rowof[p]]);
+            for (int sl = tid; sl < n; sl += T) s_dec[sl] = 0;
+        } else
         for (int sl = tid; sl < n; sl += T) {                  // pyx:55-60
             const u32 vr = vrec[sl];
             const int e0 = (int)(vr & 0xffffu), d = (int)(vr >> 16);
@@ -92,7 +100,8 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
         int conv = 0, it = 0;
         for (; it < max_iter; it++) {
             // ---- check pass: min1/min2/argmin/parity with plain compares, sign applied by xor (all edges live)
-            if (PS) {
+            if (it == 0 && table1) {
+            } else if (PS) {
                 // product-sum (restated from the published ldpc BpOsdDecoder algorithm, parity unpinned): forward products
                 // in `fwd`, backward sweep writes c2b = s * log((1 + P) / (1 - P)), P saturated to +-(1 - 2^-52)
                 double *fwd = (double *)(smem + S.off_fwd);
@@ -304,6 +313,10 @@ sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayo
         block_excl_scan(uc, m + 1, wt);
         const int nslots = (int)uc[m];
         for (int q = tid; q <= m; q += T) coff[q] = (u16)uc[q];
+        // message slot of every kept edge: the row pass notes the slot under the edge's CSR position (in the `key` area,
+        // dead after the sort), the column pass picks it up through the static CSC -> CSR map
+        u16 *slot_of = (u16 *)key;
+        const bool via_table = (2 * g.nnz <= 8 * NP2);
         for (int r = tid; r < m; r += T) {
             const int q = crank[r];
             int p = (int)uc[q];
@@ -311,13 +324,21 @@ sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayo
                 const int j = posof[g.rc[qq]];
                 if (j < nn) {
                     cvn[p] = (u16)j;
-                    for (int e = voff[j]; e < voff[j + 1]; e++) if (vrow[e] == r) vpos[e] = (u16)p;
+                    if (via_table) slot_of[qq] = (u16)p;
+                    else for (int e = voff[j]; e < voff[j + 1]; e++) if (vrow[e] == r) vpos[e] = (u16)p;
                     p++;
                 }
             }
             if (p < (int)uc[q + 1]) cvn[p] = (u16)0xffff;      // pad slot
         }
         __syncthreads();
+        if (via_table) {
+            for (int j = tid; j < nn; j += T) {
+                const int cI = col[j], e0 = g.cp[cI], d = g.cp[cI + 1] - e0, o = (int)voff[j];
+                for (int k = 0; k < d; k++) vpos[o + k] = slot_of[g.cpos[e0 + k]];
+            }
+            __syncthreads();
+        }
 
         int status = 0;
         if (P.kind == SWD_KIND_OSD_WINDOW && bad) {
