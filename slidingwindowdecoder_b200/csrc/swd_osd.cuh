@@ -169,7 +169,7 @@ post_bp_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, in
 // ----------------------------------------------------------------------------------------------
 // OSD: one CTA per shot that needs it
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(1024, 1)
 osd_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayout L, GdgDev P, OsdSmem S, OsdWork ow,
            int method, int order_w, int rank, u8 *__restrict__ dec_out, double *__restrict__ pm_out, long long chunk_base) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -219,77 +219,96 @@ osd_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayout L, G
         if (tid == 0) { misc[0] = 0; }
         __syncthreads();
         // ---- greedy independent columns in scan order, Gauss-Jordan on T (mod2sparse_extra.cpp:113-376).
-        // The scan is inherently serial (a column has to be reduced by all earlier pivots), but it does not need the whole
-        // CTA: warp 0 scans columns against the last *applied* T plus up to 32 *pending* pivots kept in composed form
+        // A column has to be reduced by all earlier pivots, but only a column that yields a pivot changes the state, and deep
+        // in the scan (the last pivots of a full-rank window sit thousands of columns down the order) almost none does.
+        // So the scan takes a block of one column per warp: every warp gathers its column against the last *applied* T and
+        // resolves it against up to 32 *pending* pivots kept in composed form
         //   M = U_p ... U_1 = I + sum_j w_j e_{pr_j}^T,   appending U = I + a e_s^T:  w_j += a * w_j[s],  w_new = a,
-        // so that applying them to a column needs one gather of the bits x[pr_j] (all tests on the original x) instead of a
-        // dependent chain; the whole CTA then applies M to every column of T in one sweep.  Two barriers per 32 pivots
-        // instead of three per scanned column (ncu r1g, C4: barrier stalls were 19.8 cycles per issued instruction).
-        // The pivots, their order and the final T are exactly those of the column-at-a-time elimination.
-        int found = 0, pos = 0;
+        // (one gather of the bits x[pr_j], all tests on the original x).  The first column of the block with a free row
+        // becomes the next pivot (its warp appends it), the columns before it are dependent and done, the columns after it
+        // take the one new elementary step in registers and the block goes round again; a block without a free row costs one
+        // barrier for all its columns.  The whole CTA folds the pending pivots into T every 32 pivots.  Pivots, their order
+        // and the final T are exactly those of the column-at-a-time elimination (ncu r1h, C4: 76 % of the samples were the
+        // other 18 warps waiting for the one scanning warp).
+        int found = 0, pos = 0, pcount = 0, rnd = 0;
+        const int nw = T >> 5;
         for (;;) {
-            if (wid == 0) {
-                int pcount = 0, myprow = 0;
-                while (pos < n && found < rank && pcount < 32) {
-                    // lane l preloads column pos + l of the scan order: index, first entry, degree and its first 8 rows,
-                    // so that the per-column chain below is shuffles and shared-memory reads only
-                    const int ccol = (pos + lane < n) ? (int)idx[pos + lane] : -1;
-                    int ce0 = 0, cd = 0;
-                    if (ccol >= 0) { ce0 = g.cp[ccol]; cd = g.cp[ccol + 1] - ce0; }
-                    u32 rpk[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                    for (int e = 0; e < 8; e++) if (e < cd) rpk[e >> 1] |= (u32)g.cr[ce0 + e] << (16 * (e & 1));
-                    for (int l = 0; l < 32 && pos < n && found < rank && pcount < 32; l++, pos++) {
-                        const int cidx = __shfl_sync(FULLMASK, ccol, l), d = __shfl_sync(FULLMASK, cd, l), e0 = __shfl_sync(FULLMASK, ce0, l);
-                        u64 x = 0;
-#pragma unroll
-                        for (int e = 0; e < 8; e++) {
-                            const u32 pk = __shfl_sync(FULLMASK, rpk[e >> 1], l);
-                            if (e < d && lane < W64) x ^= tcol[(int)((pk >> (16 * (e & 1))) & 0xffffu) * W64 + lane];
-                        }
-                        if (lane < W64) for (int e = 8; e < d; e++) x ^= tcol[(int)g.cr[e0 + e] * W64 + lane];
-                        // pending pivots: lane j tests bit pr_j of the (original) x
-                        const u64 xw = __shfl_sync(FULLMASK, x, myprow >> 6);
-                        u32 hm = __ballot_sync(FULLMASK, (lane < pcount) && ((xw >> (myprow & 63)) & 1ull));
-                        while (hm) { const int j = __ffs(hm) - 1; hm &= hm - 1; if (lane < W64) x ^= pend[j * W64 + lane]; }
-                        const u64 free_bits = (lane < W64) ? (x & ~pivmask[lane]) : 0ull;
-                        const u32 bsel = __ballot_sync(FULLMASK, free_bits != 0);
-                        if (bsel) {
-                            const int fl = __ffs(bsel) - 1;
-                            const u64 fb = __shfl_sync(FULLMASK, free_bits, fl);
-                            const int pr = fl * 64 + (__ffsll((long long)fb) - 1);
-                            u64 av = x; if (lane == fl) av &= ~(1ull << (pr & 63));
-                            u32 tm = __ballot_sync(FULLMASK, (lane < pcount) && ((pend[lane * W64 + (pr >> 6)] >> (pr & 63)) & 1ull));
-                            __syncwarp();
-                            while (tm) { const int j = __ffs(tm) - 1; tm &= tm - 1; if (lane < W64) pend[j * W64 + lane] ^= av; }
-                            if (lane < W64) pend[pcount * W64 + lane] = av;
-                            if (lane == pcount) myprow = pr;
-                            if (lane == fl) pivmask[lane] |= 1ull << (pr & 63);
-                            if (lane == 0) { colinfo[cidx] = (u16)pr; prow[pcount] = pr; }
-                            pcount++; found++;
-                            __syncwarp();
+            const int ci = pos + wid;
+            bool valid = (ci < n);
+            int cidx = 0; u64 x = 0;
+            if (valid) {
+                cidx = idx[ci];
+                const int e0 = g.cp[cidx], d = g.cp[cidx + 1] - e0;
+                if (lane < W64) for (int e = 0; e < d; e++) x ^= tcol[(int)g.cr[e0 + e] * W64 + lane];
+                const int myprow = (lane < pcount) ? prow[lane] : 0;
+                const u64 xw = __shfl_sync(FULLMASK, x, myprow >> 6);
+                u32 hm = __ballot_sync(FULLMASK, (lane < pcount) && ((xw >> (myprow & 63)) & 1ull));
+                while (hm) { const int jj = __ffs(hm) - 1; hm &= hm - 1; if (lane < W64) x ^= pend[jj * W64 + lane]; }
+            }
+            int cur = 0;
+            bool stop = false;
+            for (;;) {
+                int *flags = red_i + 32 * (rnd & 1); rnd++;
+                const u64 free_bits = (valid && lane < W64) ? (x & ~pivmask[lane]) : 0ull;
+                const u32 bsel = __ballot_sync(FULLMASK, free_bits != 0);
+                if (lane == 0) flags[wid] = bsel ? 1 : 0;
+                __syncthreads();
+                const u32 fm = __ballot_sync(FULLMASK, lane < nw && lane >= cur && flags[lane] != 0);
+                if (!fm) break;                                  // the rest of the block depends on the pivots so far
+                const int first = __ffs(fm) - 1;
+                if (wid == first) {
+                    const int fl = __ffs(bsel) - 1;
+                    const u64 fb = __shfl_sync(FULLMASK, free_bits, fl);
+                    const int pr = fl * 64 + (__ffsll((long long)fb) - 1);
+                    u64 av = x; if (lane == fl) av &= ~(1ull << (pr & 63));
+                    u32 tm = __ballot_sync(FULLMASK, (lane < pcount) && ((pend[lane * W64 + (pr >> 6)] >> (pr & 63)) & 1ull));
+                    __syncwarp();
+                    while (tm) { const int jj = __ffs(tm) - 1; tm &= tm - 1; if (lane < W64) pend[jj * W64 + lane] ^= av; }
+                    if (lane < W64) pend[pcount * W64 + lane] = av;
+                    if (lane == fl) pivmask[lane] |= 1ull << (pr & 63);
+                    if (lane == 0) { colinfo[cidx] = (u16)pr; prow[pcount] = pr; }
+                }
+                if (wid <= first) valid = false;
+                pcount++; found++;
+                __syncthreads();
+                if (valid) {                                     // later columns of the block: the one new elementary step
+                    const int pr = prow[pcount - 1];
+                    const u64 xw = __shfl_sync(FULLMASK, x, pr >> 6);
+                    if (((xw >> (pr & 63)) & 1ull) && lane < W64) x ^= pend[(pcount - 1) * W64 + lane];
+                }
+                cur = first + 1;
+                if (found >= rank) { stop = true; break; }
+                if (pcount == 32) {
+                    __syncthreads();
+                    for (int r = tid; r <= m; r += T) {
+                        u64 *tc = tcol + r * W64;
+                        u32 hits = 0;
+                        for (int jj = 0; jj < 32; jj++) { const int pr = prow[jj]; hits |= (u32)((tc[pr >> 6] >> (pr & 63)) & 1ull) << jj; }
+                        while (hits) {
+                            const int jj = __ffs(hits) - 1; hits &= hits - 1;
+                            for (int w = 0; w < W64; w++) tc[w] ^= pend[jj * W64 + w];
                         }
                     }
-                }
-                if (lane == 0) { misc[0] = pcount; misc[1] = pos; misc[3] = found; }
-            }
-            __syncthreads();
-            const int pcount = misc[0];
-            pos = misc[1]; found = misc[3];
-            if (pcount > 0) {
-                for (int r = tid; r <= m; r += T) {
-                    u64 *tc = tcol + r * W64;
-                    u32 hits = 0;
-                    for (int j = 0; j < pcount; j++) { const int pr = prow[j]; hits |= (u32)((tc[pr >> 6] >> (pr & 63)) & 1ull) << j; }
-                    while (hits) {
-                        const int j = __ffs(hits) - 1; hits &= hits - 1;
-                        for (int w = 0; w < W64; w++) tc[w] ^= pend[j * W64 + w];
-                    }
+                    pcount = 0;
+                    __syncthreads();
                 }
             }
-            __syncthreads();
-            if (pos >= n || found >= rank) break;
+            pos += nw;
+            if (stop || pos >= n) break;
         }
+        __syncthreads();
+        if (pcount > 0) {
+            for (int r = tid; r <= m; r += T) {
+                u64 *tc = tcol + r * W64;
+                u32 hits = 0;
+                for (int jj = 0; jj < pcount; jj++) { const int pr = prow[jj]; hits |= (u32)((tc[pr >> 6] >> (pr & 63)) & 1ull) << jj; }
+                while (hits) {
+                    const int jj = __ffs(hits) - 1; hits &= hits - 1;
+                    for (int w = 0; w < W64; w++) tc[w] ^= pend[jj * W64 + w];
+                }
+            }
+        }
+        __syncthreads();
         // ---- the non-pivot columns that may be flipped: first k of order[0..nn) \ pivots (osd_window.pyx:243-258)
         if (wid == 0) {
             int cnt = 0;
