@@ -36,6 +36,7 @@ static path_fn_t pick_path_kernel(int dmax, int T) {
 #define SWD_MINB 7
 #endif
         if (T <= 128) return path_kernel<4, 6, 128, SWD_MINB>;
+        if (T <= 320) return path_kernel<4, 6, 320, 2>;          // e.g. 576 x 4896 windows (new_n = 1152): two CTAs per SM
         if (T <= 512) return path_kernel<4, 6, 512, 1>;
         return path_kernel<4, 6, 1024, 1>;
     }

@@ -515,6 +515,7 @@ typedef void (*post_fn_t)(Workspace, SubLayout, SubLayout, PathSmem, GdgDev, int
 static inline post_fn_t pick_post_kernel(int dmax, int T) {
     if (dmax == 6) {
         if (T <= 128) return post_bp_kernel<4, 6, 128, 5>;
+        if (T <= 320) return post_bp_kernel<4, 6, 320, 2>;
         if (T <= 512) return post_bp_kernel<4, 6, 512, 1>;
         return post_bp_kernel<4, 6, 1024, 1>;
     }
