@@ -406,7 +406,7 @@ static int setup_kernels(swd_decoder *d) {
     int np2 = 64; while (np2 < n) np2 <<= 1;
     S2.np2 = np2;
     S2.cap_sel = 0;
-    if (c.kind != SWD_KIND_OSD_WINDOW && np2 >= 2048 && !getenv("SWD_FULL_SORT")) {
+    if (np2 >= 2048 && !getenv("SWD_FULL_SORT")) {
         int cap = 64; while (cap < nn + 64) cap <<= 1;
         if (cap <= np2 / 4) S2.cap_sel = cap;
     }

@@ -203,7 +203,7 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
 // K2: sort + reset
 // ----------------------------------------------------------------------------------------------
 struct SortSmem { int off_key, off_idx, off_posof, off_blob, off_u32a, off_u32b, off_u32c, off_wt, off_error, off_misc, off_bins, total; int np2;
-                  int cap_sel; };     // > 0: GDG kinds select + sort the cap_sel smallest keys instead of sorting all n
+                  int cap_sel; };     // > 0: select + sort the cap_sel smallest keys instead of sorting all n
 
 __global__ void __launch_bounds__(1024, 1)
 sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayout L, GdgDev P, SortSmem S,
@@ -260,8 +260,6 @@ sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayo
             block_bitonic_sort(key, idx, NP2);
         }
         for (int j = tid; j < (partial ? nn : n); j += T) posof[idx[j]] = (u16)j;
-        if (P.kind == SWD_KIND_OSD_WINDOW)          // decided-0 key of the dropped columns (osd_window.pyx:208-209)
-            for (int j = nn + tid; j < n; j += T) ws.sum[(size_t)slot * n + idx[j]] = 1000.0;
         for (int j = tid; j < nn; j += T) {
             const int c = idx[j];
             col[j] = (u16)c; prior[j] = g.llr[c];
@@ -340,6 +338,18 @@ sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayo
             __syncthreads();
         }
 
+        if (P.kind == SWD_KIND_OSD_WINDOW) {
+            if (bad && partial) {
+                // the failure position below needs the order of the dropped columns as well (rare): sort everything after all
+                block_bitonic_sort_regs<8>(key, idx, NP2, ws.sum + (size_t)slot * n, n);
+                for (int j = tid; j < n; j += T) posof[idx[j]] = (u16)j;
+                partial = false;
+                __syncthreads();
+            }
+            // decided-0 key of the dropped columns (osd_window.pyx:208-209)
+            if (partial) { for (int cI = tid; cI < n; cI += T) if (posof[cI] >= nn) ws.sum[(size_t)slot * n + cI] = 1000.0; }
+            else for (int j = nn + tid; j < n; j += T) ws.sum[(size_t)slot * n + idx[j]] = 1000.0;
+        }
         int status = 0;
         if (P.kind == SWD_KIND_OSD_WINDOW && bad) {
             // osd_window.pyx:178-181: decimating the dropped columns in sorted order hits a check whose

@@ -665,3 +665,28 @@ def test_sort_select_with_many_equal_keys(kind, oracle_mod):
         assert 0 < int(conv.sum())
         assert np.array_equal(conv, np.asarray(o_conv).astype(np.uint8))
         assert np.array_equal(corr, np.asarray(o_dec).astype(np.uint8))
+
+
+def test_osd_window_reset_failure_on_large_window(oracle_mod):
+    """osd_window on a [[144,12,12]] window takes the radix-select path of sort_reset_kernel, which orders only the kept
+    columns; when decimating the dropped columns hits a check whose every column is dropped while its syndrome bit is 1
+    (osd_window.pyx:178-181) the failure position needs the order of the dropped columns too and the kernel sorts
+    everything after all.  Forced here: the columns of one check get a 1e-12 prior, its syndrome bit is set and a small
+    scaling factor keeps their posteriors large.  Bit-exact vs the oracle (corrections, flags, BP decisions)."""
+    from slidingwindowdecoder_b200 import osd_window
+    g = load_golden("c3_w5_osdw_cs10")
+    H = np.asarray(g["mat"].todense()) if hasattr(g["mat"], "todense") else np.asarray(g["mat"])
+    pri = np.array(g["priors"], dtype=np.float64).copy()
+    r0 = 17
+    pri[H[r0] != 0] = 1e-12
+    synd = np.array(g["synd"][:48]).copy()
+    synd[::2, r0] = 1
+    kw = dict(g["kwargs"]); kw["ms_scaling_factor"] = 0.1
+    orc = oracle_mod.Oracle(g["mat"], pri)
+    o_dec, o_conv, o_pm, _ = orc.osd_window_batch(synd, **kw)
+    dec = osd_window(g["mat"], channel_probs=pri, **kw)
+    corr, conv, pm = dec.decode_batch(synd, return_pm=True)
+    assert np.array_equal(conv, np.asarray(o_conv).astype(np.uint8))
+    assert np.array_equal(corr, np.asarray(o_dec).astype(np.uint8))
+    per = [orc.osd_window(x, **kw) for x in synd]
+    assert np.array_equal(dec.last_outputs()["bp_decoding"], np.array([r["bp_decoding"] for r in per]).astype(np.uint8))
