@@ -203,9 +203,12 @@ osd_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayout L, G
         const int shot = ws.gdg_list[slot];
         osd_shots++;
         // ---- order the columns (osd_window.pyx:205-215)
-        for (int i = tid; i < NP2; i += T) {
-            key[i] = (i < n) ? ws.sum[(size_t)slot * n + i] : inf;
-            idx[i] = (i < n) ? (u16)i : (u16)0xffff;
+        const bool regsort = (NP2 == 8 * T);                     // osd_setup sizes the CTA for this whenever it can
+        if (!regsort) {
+            for (int i = tid; i < NP2; i += T) {
+                key[i] = (i < n) ? ws.sum[(size_t)slot * n + i] : inf;
+                idx[i] = (i < n) ? (u16)i : (u16)0xffff;
+            }
         }
         for (int i = tid; i < (m + 1) * W64; i += T) tcol[i] = 0;
         for (int i = tid; i < n; i += T) colinfo[i] = 0xffff;
@@ -215,7 +218,8 @@ osd_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayout L, G
             tcol[r * W64 + (r >> 6)] = 1ull << (r & 63);
             if (synd[(size_t)shot * m + r]) atomicOr(&tcol[m * W64 + (r >> 6)], 1ull << (r & 63));
         }
-        block_bitonic_sort(key, idx, NP2);
+        if (regsort) block_bitonic_sort_regs<8>(key, idx, NP2, ws.sum + (size_t)slot * n, n);
+        else block_bitonic_sort(key, idx, NP2);
         if (tid == 0) { misc[0] = 0; }
         __syncthreads();
         // ---- greedy independent columns in scan order, Gauss-Jordan on T (mod2sparse_extra.cpp:113-376).
@@ -503,6 +507,7 @@ static inline int osd_setup(int m, int n, int nn, int rank, int method, int orde
     if (S->W64 > 32) return -2;                          // one word of a T column per lane of the scanning warp
     if (S->total > 227 * 1024) return -2;
     int t = ((m + 1 + 31) / 32) * 32; if (t < 128) t = 128; if (t > 1024) t = 1024;
+    if (np2 / 8 >= t && np2 / 8 <= 1024) t = np2 / 8;     // 8 sort keys per thread in registers; more warps for the block scan
     *T5 = t;
     if (cudaFuncSetAttribute(osd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -3;
     int occ = 0;
