@@ -184,6 +184,14 @@ int  swd_bp4_decode_batch_host(swd_bp4 *b, const uint8_t *synd_x, const uint8_t 
  * log_prob_ratios [B*n*3] and bp_iteration [B] of the last run, as the reference's properties hold after the call. */
 int  swd_bp4_camel_decode_batch_host(swd_bp4 *b, const uint8_t *synd_x, const uint8_t *synd_z, int64_t B, uint8_t *dec,
                                      uint8_t *converge, double *min_pm, double *log_prob_ratios, int32_t *bp_iteration);
+/* The same two calls with device pointers (e.g. torch tensors) on the caller's stream, without host synchronisation; the
+ * optional outputs may be NULL.  Results pass through the decoder's own buffers: calls on one swd_bp4 must be stream-ordered. */
+int  swd_bp4_decode_batch_device(swd_bp4 *b, const uint8_t *d_synd_x, const uint8_t *d_synd_z, int64_t B, uint8_t *d_dec,
+                                 uint8_t *d_converge, uint8_t *d_bp_dec, uint8_t *d_osd0, double *d_log_prob_ratios,
+                                 int32_t *d_bp_iteration, void *stream);
+int  swd_bp4_camel_decode_batch_device(swd_bp4 *b, const uint8_t *d_synd_x, const uint8_t *d_synd_z, int64_t B, uint8_t *d_dec,
+                                       uint8_t *d_converge, double *d_min_pm, double *d_log_prob_ratios, int32_t *d_bp_iteration,
+                                       void *stream);
 
 const char *swd_strerror(int status);
 const char *swd_last_error(void);

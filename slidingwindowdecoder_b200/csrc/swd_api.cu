@@ -912,11 +912,7 @@ static int bp4_osd_pass(swd_decoder *d, const u8 *d_synd, const double *d_keys, 
     return SWD_OK;
 }
 
-extern "C" int swd_bp4_decode_batch_host(swd_bp4 *b, const uint8_t *synd_x, const uint8_t *synd_z, int64_t B, uint8_t *dec, uint8_t *conv,
-                                         uint8_t *bp_dec, uint8_t *osd0, double *lpr, int32_t *bp_iteration) {
-    if (!b || B < 0 || (B > 0 && (!synd_x || !synd_z || !dec || !conv))) { set_err("swd_bp4_decode_batch_host: null argument"); return SWD_ERR_INVALID; }
-    if (B == 0) return SWD_OK;
-    CK(cudaSetDevice(b->device));
+static int bp4_reserve(swd_bp4 *b, int64_t B) {
     const size_t n = b->n;
     if (B > b->cap) {
         bp4_free_buffers(b);
@@ -926,18 +922,36 @@ extern "C" int swd_bp4_decode_batch_host(swd_bp4 *b, const uint8_t *synd_x, cons
         CK(cudaMalloc(&b->lpr, (size_t)B * n * 24)); CK(cudaMalloc(&b->key_x, (size_t)B * n * 8)); CK(cudaMalloc(&b->key_z, (size_t)B * n * 8));
         b->cap = B;
     }
-    cudaStream_t s = b->stream;
-    CK(cudaMemcpyAsync(b->synd_x, synd_x, (size_t)B * b->mx, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(b->synd_z, synd_z, (size_t)B * b->mz, cudaMemcpyHostToDevice, s));
-    bp4_kernel<false><<<(int)std::min<long long>(B, b->grid), 256, b->S.total, s>>>(b->dx->g, b->dz->g, b->llr, b->llr + n, b->llr + 2 * n, b->synd_x, b->synd_z, B,
+    return SWD_OK;
+}
+
+// BP4 + OSD per basis on device-resident syndromes; results are left in the decoder's own buffers (dec, conv, bp_dec, osd0, lpr, iters)
+static int bp4_run(swd_bp4 *b, const u8 *d_sx, const u8 *d_sz, int64_t B, cudaStream_t s) {
+    const size_t n = b->n;
+    bp4_kernel<false><<<(int)std::min<long long>(B, b->grid), 256, b->S.total, s>>>(b->dx->g, b->dz->g, b->llr, b->llr + n, b->llr + 2 * n, d_sx, d_sz, B,
                                                                                     b->max_iter, b->alpha, b->bp_dec, b->conv, b->iters, b->lpr, b->key_x, b->key_z, b->S, nullptr);
     CK(cudaGetLastError());
     int st;
-    if ((st = bp4_osd_pass(b->dx, b->synd_x, b->key_x, b->conv, B, b->tmp, s))) return st;      // osd('x') -> z part
-    if ((st = bp4_osd_pass(b->dz, b->synd_z, b->key_z, b->conv, B, b->tmp, s))) return st;      // osd('z') -> x part
+    if ((st = bp4_osd_pass(b->dx, d_sx, b->key_x, b->conv, B, b->tmp, s))) return st;      // osd('x') -> z part
+    if ((st = bp4_osd_pass(b->dz, d_sz, b->key_z, b->conv, B, b->tmp, s))) return st;      // osd('z') -> x part
     bp4_finish_kernel<<<(unsigned)std::min<long long>((B * 2 * (long long)n + 255) / 256, 8192), 256, 0, s>>>(
         b->bp_dec, b->conv, b->dx->ow.osdw, b->dx->ow.osd0, b->dz->ow.osdw, b->dz->ow.osd0, B, (int)n, b->dec, b->osd0);
     CK(cudaGetLastError());
+    return SWD_OK;
+}
+
+extern "C" int swd_bp4_decode_batch_host(swd_bp4 *b, const uint8_t *synd_x, const uint8_t *synd_z, int64_t B, uint8_t *dec, uint8_t *conv,
+                                         uint8_t *bp_dec, uint8_t *osd0, double *lpr, int32_t *bp_iteration) {
+    if (!b || B < 0 || (B > 0 && (!synd_x || !synd_z || !dec || !conv))) { set_err("swd_bp4_decode_batch_host: null argument"); return SWD_ERR_INVALID; }
+    if (B == 0) return SWD_OK;
+    CK(cudaSetDevice(b->device));
+    const size_t n = b->n;
+    int st;
+    if ((st = bp4_reserve(b, B))) return st;
+    cudaStream_t s = b->stream;
+    CK(cudaMemcpyAsync(b->synd_x, synd_x, (size_t)B * b->mx, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b->synd_z, synd_z, (size_t)B * b->mz, cudaMemcpyHostToDevice, s));
+    if ((st = bp4_run(b, b->synd_x, b->synd_z, B, s))) return st;
     CK(cudaMemcpyAsync(dec, b->dec, (size_t)B * 2 * n, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(conv, b->conv, (size_t)B, cudaMemcpyDeviceToHost, s));
     if (bp_dec) CK(cudaMemcpyAsync(bp_dec, b->bp_dec, (size_t)B * 2 * n, cudaMemcpyDeviceToHost, s));
@@ -948,14 +962,31 @@ extern "C" int swd_bp4_decode_batch_host(swd_bp4 *b, const uint8_t *synd_x, cons
     return SWD_OK;
 }
 
+// the same with device pointers (e.g. torch tensors) on the caller's stream, no host synchronisation
+extern "C" int swd_bp4_decode_batch_device(swd_bp4 *b, const uint8_t *d_synd_x, const uint8_t *d_synd_z, int64_t B, uint8_t *d_dec,
+                                           uint8_t *d_conv, uint8_t *d_bp_dec, uint8_t *d_osd0, double *d_lpr, int32_t *d_bp_iteration,
+                                           void *stream) {
+    if (!b || B < 0 || (B > 0 && (!d_synd_x || !d_synd_z || !d_dec || !d_conv))) { set_err("swd_bp4_decode_batch_device: null argument"); return SWD_ERR_INVALID; }
+    if (B == 0) return SWD_OK;
+    CK(cudaSetDevice(b->device));
+    const size_t n = b->n;
+    int st;
+    if ((st = bp4_reserve(b, B))) return st;
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((st = bp4_run(b, d_synd_x, d_synd_z, B, s))) return st;
+    CK(cudaMemcpyAsync(d_dec, b->dec, (size_t)B * 2 * n, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(d_conv, b->conv, (size_t)B, cudaMemcpyDeviceToDevice, s));
+    if (d_bp_dec) CK(cudaMemcpyAsync(d_bp_dec, b->bp_dec, (size_t)B * 2 * n, cudaMemcpyDeviceToDevice, s));
+    if (d_osd0) CK(cudaMemcpyAsync(d_osd0, b->osd0, (size_t)B * 2 * n, cudaMemcpyDeviceToDevice, s));
+    if (d_lpr) CK(cudaMemcpyAsync(d_lpr, b->lpr, (size_t)B * n * 24, cudaMemcpyDeviceToDevice, s));
+    if (d_bp_iteration) CK(cudaMemcpyAsync(d_bp_iteration, b->iters, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
+    return SWD_OK;
+}
+
 // bp4_osd.camel_decode (src/bp4_osd.pyx:223-248) for a batch: four BP runs per shot with the last qubit pinned to I / X / Z / Y,
 // the converged run with the smallest path metric wins.  min_pm: 10000.0 when no run converged (then dec = 0, converge = 0).
 // lpr / bp_iteration: those of the last run (Y), as the reference's properties show after the call.
-extern "C" int swd_bp4_camel_decode_batch_host(swd_bp4 *b, const uint8_t *synd_x, const uint8_t *synd_z, int64_t B, uint8_t *dec, uint8_t *conv,
-                                               double *min_pm, double *lpr, int32_t *bp_iteration) {
-    if (!b || B < 0 || (B > 0 && (!synd_x || !synd_z || !dec || !conv))) { set_err("swd_bp4_camel_decode_batch_host: null argument"); return SWD_ERR_INVALID; }
-    if (B == 0) return SWD_OK;
-    CK(cudaSetDevice(b->device));
+static int bp4_camel_reserve(swd_bp4 *b, int64_t B) {
     const size_t n = b->n;
     if (B > b->cap4) {
         bp4_free_camel(b);
@@ -965,20 +996,55 @@ extern "C" int swd_bp4_camel_decode_batch_host(swd_bp4 *b, const uint8_t *synd_x
         CK(cudaMalloc(&b->c_pm4, (size_t)B * 32)); CK(cudaMalloc(&b->c_pm, (size_t)B * 8)); CK(cudaMalloc(&b->c_lpr, (size_t)B * n * 24));
         b->cap4 = B;
     }
-    cudaStream_t s = b->stream;
-    CK(cudaMemcpyAsync(b->c_synd_x, synd_x, (size_t)B * b->mx, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(b->c_synd_z, synd_z, (size_t)B * b->mz, cudaMemcpyHostToDevice, s));
-    bp4_kernel<true><<<(int)std::min<long long>(4 * B, b->grid), 256, b->S.total, s>>>(b->dx->g, b->dz->g, b->llr, b->llr + n, b->llr + 2 * n, b->c_synd_x, b->c_synd_z, B,
+    return SWD_OK;
+}
+
+static int bp4_camel_run(swd_bp4 *b, const u8 *d_sx, const u8 *d_sz, int64_t B, cudaStream_t s) {
+    const size_t n = b->n;
+    bp4_kernel<true><<<(int)std::min<long long>(4 * B, b->grid), 256, b->S.total, s>>>(b->dx->g, b->dz->g, b->llr, b->llr + n, b->llr + 2 * n, d_sx, d_sz, B,
                                                                                        b->max_iter, b->alpha, b->c_bp_dec, b->c_conv4, b->c_it4, b->c_lpr, nullptr, nullptr, b->S, b->c_pm4);
     CK(cudaGetLastError());
     bp4_camel_finish_kernel<<<(unsigned)std::min<long long>((B + 7) / 8, 4096), 256, 0, s>>>(b->c_bp_dec, b->c_conv4, b->c_pm4, b->c_it4, B, (int)n,
                                                                                              b->c_dec, b->c_conv, b->c_pm, b->c_it);
     CK(cudaGetLastError());
+    return SWD_OK;
+}
+
+extern "C" int swd_bp4_camel_decode_batch_host(swd_bp4 *b, const uint8_t *synd_x, const uint8_t *synd_z, int64_t B, uint8_t *dec, uint8_t *conv,
+                                               double *min_pm, double *lpr, int32_t *bp_iteration) {
+    if (!b || B < 0 || (B > 0 && (!synd_x || !synd_z || !dec || !conv))) { set_err("swd_bp4_camel_decode_batch_host: null argument"); return SWD_ERR_INVALID; }
+    if (B == 0) return SWD_OK;
+    CK(cudaSetDevice(b->device));
+    const size_t n = b->n;
+    int st;
+    if ((st = bp4_camel_reserve(b, B))) return st;
+    cudaStream_t s = b->stream;
+    CK(cudaMemcpyAsync(b->c_synd_x, synd_x, (size_t)B * b->mx, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b->c_synd_z, synd_z, (size_t)B * b->mz, cudaMemcpyHostToDevice, s));
+    if ((st = bp4_camel_run(b, b->c_synd_x, b->c_synd_z, B, s))) return st;
     CK(cudaMemcpyAsync(dec, b->c_dec, (size_t)B * 2 * n, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(conv, b->c_conv, (size_t)B, cudaMemcpyDeviceToHost, s));
     if (min_pm) CK(cudaMemcpyAsync(min_pm, b->c_pm, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
     if (lpr) CK(cudaMemcpyAsync(lpr, b->c_lpr, (size_t)B * n * 24, cudaMemcpyDeviceToHost, s));
     if (bp_iteration) CK(cudaMemcpyAsync(bp_iteration, b->c_it, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    return SWD_OK;
+}
+
+extern "C" int swd_bp4_camel_decode_batch_device(swd_bp4 *b, const uint8_t *d_synd_x, const uint8_t *d_synd_z, int64_t B, uint8_t *d_dec,
+                                                 uint8_t *d_conv, double *d_min_pm, double *d_lpr, int32_t *d_bp_iteration, void *stream) {
+    if (!b || B < 0 || (B > 0 && (!d_synd_x || !d_synd_z || !d_dec || !d_conv))) { set_err("swd_bp4_camel_decode_batch_device: null argument"); return SWD_ERR_INVALID; }
+    if (B == 0) return SWD_OK;
+    CK(cudaSetDevice(b->device));
+    const size_t n = b->n;
+    int st;
+    if ((st = bp4_camel_reserve(b, B))) return st;
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((st = bp4_camel_run(b, d_synd_x, d_synd_z, B, s))) return st;
+    CK(cudaMemcpyAsync(d_dec, b->c_dec, (size_t)B * 2 * n, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(d_conv, b->c_conv, (size_t)B, cudaMemcpyDeviceToDevice, s));
+    if (d_min_pm) CK(cudaMemcpyAsync(d_min_pm, b->c_pm, (size_t)B * 8, cudaMemcpyDeviceToDevice, s));
+    if (d_lpr) CK(cudaMemcpyAsync(d_lpr, b->c_lpr, (size_t)B * n * 24, cudaMemcpyDeviceToDevice, s));
+    if (d_bp_iteration) CK(cudaMemcpyAsync(d_bp_iteration, b->c_it, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
     return SWD_OK;
 }

@@ -360,6 +360,8 @@ class bp4_osd:
     def decode_batch(self, synd_x, synd_z):
         """-> dict(dec [B, 2, n] uint8, converge [B], bp_decoding [B, 2, n], osd0 [B, 2, n], log_prob_ratios [B, n, 3],
         bp_iteration [B])"""
+        if _is_torch_cuda(synd_x) and _is_torch_cuda(synd_z):
+            return self._batch_torch(synd_x, synd_z, camel=False)
         sx = np.ascontiguousarray(np.asarray(synd_x), dtype=np.uint8); sz = np.ascontiguousarray(np.asarray(synd_z), dtype=np.uint8)
         if sx.ndim != 2 or sz.ndim != 2 or sx.shape[1] != self.mx or sz.shape[1] != self.mz or sx.shape[0] != sz.shape[0]:
             raise ValueError(f"decode_batch expects syndromes of shape [B, {self.mx}] and [B, {self.mz}]")
@@ -379,8 +381,36 @@ class bp4_osd:
         self.converge = int(self._last["converge"]); self.bp_iteration = int(self._last["bp_iteration"])
         return self._last["dec"].astype(np.int64)
 
+    def _batch_torch(self, synd_x, synd_z, camel):
+        """torch CUDA uint8 tensors in -> dict of torch CUDA tensors out, asynchronous on the current stream (device-pointer
+        entry points of the C-ABI; calls on one decoder must be stream-ordered)."""
+        import torch
+        sx = synd_x.to(torch.uint8).contiguous(); sz = synd_z.to(torch.uint8).contiguous()
+        if sx.dim() != 2 or sz.dim() != 2 or sx.shape[1] != self.mx or sz.shape[1] != self.mz or sx.shape[0] != sz.shape[0]:
+            raise ValueError(f"expected syndromes of shape [B, {self.mx}] and [B, {self.mz}]")
+        B, n, dev = sx.shape[0], self.n, sx.device
+        dec = torch.empty((B, 2, n), dtype=torch.uint8, device=dev); conv = torch.empty(B, dtype=torch.uint8, device=dev)
+        lpr = torch.empty((B, n, 3), dtype=torch.float64, device=dev); it = torch.empty(B, dtype=torch.int32, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        if camel:
+            pm = torch.empty(B, dtype=torch.float64, device=dev)
+            st = self._lib.swd_bp4_camel_decode_batch_device(self._handle, sx.data_ptr(), sz.data_ptr(), B, dec.data_ptr(), conv.data_ptr(),
+                                                             pm.data_ptr(), lpr.data_ptr(), it.data_ptr(), stream)
+            _lib.check(st, "swd_bp4_camel_decode_batch_device")
+            out = dict(dec=dec, converge=conv, min_pm=pm, log_prob_ratios=lpr, bp_iteration=it)
+        else:
+            bp = torch.empty_like(dec); o0 = torch.empty_like(dec)
+            st = self._lib.swd_bp4_decode_batch_device(self._handle, sx.data_ptr(), sz.data_ptr(), B, dec.data_ptr(), conv.data_ptr(),
+                                                       bp.data_ptr(), o0.data_ptr(), lpr.data_ptr(), it.data_ptr(), stream)
+            _lib.check(st, "swd_bp4_decode_batch_device")
+            out = dict(dec=dec, converge=conv, bp_decoding=bp, osd0=o0, log_prob_ratios=lpr, bp_iteration=it)
+        self._keepalive = (sx, sz)
+        return out
+
     def camel_decode_batch(self, synd_x, synd_z):
         """-> dict(dec [B, 2, n] uint8, converge [B], min_pm [B], log_prob_ratios [B, n, 3] and bp_iteration [B] of the last run)"""
+        if _is_torch_cuda(synd_x) and _is_torch_cuda(synd_z):
+            return self._batch_torch(synd_x, synd_z, camel=True)
         sx = np.ascontiguousarray(np.asarray(synd_x), dtype=np.uint8); sz = np.ascontiguousarray(np.asarray(synd_z), dtype=np.uint8)
         if sx.ndim != 2 or sz.ndim != 2 or sx.shape[1] != self.mx or sz.shape[1] != self.mz or sx.shape[0] != sz.shape[0]:
             raise ValueError(f"camel_decode_batch expects syndromes of shape [B, {self.mx}] and [B, {self.mz}]")

@@ -690,3 +690,22 @@ def test_osd_window_reset_failure_on_large_window(oracle_mod):
     assert np.array_equal(corr, np.asarray(o_dec).astype(np.uint8))
     per = [orc.osd_window(x, **kw) for x in synd]
     assert np.array_equal(dec.last_outputs()["bp_decoding"], np.array([r["bp_decoding"] for r in per]).astype(np.uint8))
+
+
+def test_bp4_device_pointer_entry_points_match_host_calls():
+    """swd_bp4_decode_batch_device / swd_bp4_camel_decode_batch_device (torch CUDA tensors in and out, caller's stream) return
+    exactly what the host-buffer calls return."""
+    import torch
+    from conftest import load_golden_bp4
+    from slidingwindowdecoder_b200 import bp4_osd
+    g = load_golden_bp4("c1_bp4_camel_tied")
+    kw = dict(g["kwargs"], osd_method="osd_cs", osd_order=6)
+    dec = bp4_osd(g["hx"], g["hz"], channel_probs_x=g["px"], channel_probs_y=g["py"], channel_probs_z=g["pz"], **kw)
+    sx, sz = g["synd_x"], g["synd_z"]
+    tx, tz = torch.from_numpy(sx).cuda(), torch.from_numpy(sz).cuda()
+    for host, devc in ((dec.decode_batch(sx, sz), dec.decode_batch(tx, tz)), (dec.camel_decode_batch(sx, sz), dec.camel_decode_batch(tx, tz))):
+        torch.cuda.synchronize()
+        assert set(host) == set(devc)
+        for k in host:
+            assert torch.is_tensor(devc[k]) and devc[k].is_cuda
+            assert np.array_equal(host[k], devc[k].cpu().numpy()), k
