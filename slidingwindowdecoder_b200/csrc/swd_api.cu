@@ -33,7 +33,7 @@ typedef void (*path_fn_t)(Workspace, SubLayout, SubLayout, PathSmem, GdgDev, int
 static path_fn_t pick_path_kernel(int dmax, int T) {
     if (dmax == 6) {
 #ifndef SWD_MINB
-#define SWD_MINB 7
+#define SWD_MINB (SWD_DIET ? 8 : 7)
 #endif
         if (T <= 128) return path_kernel<4, 6, 128, SWD_MINB>;
         if (T <= 320) return path_kernel<4, 6, 320, 2>;          // e.g. 576 x 4896 windows (new_n = 1152): two CTAs per SM
@@ -289,6 +289,9 @@ static int occupancy(K kernel, int threads, size_t smem, int *out) {
 
 // with_col = false: shared-memory image of the blob; `col` (needed only for the final scatter) stays in HBM
 static void make_layout(SubLayout &L, int nn, int m, int es, int lcap, bool with_col = true) {
+    // with_col = false: the shared-memory image.  With SWD_DIET it is a prefix of the global blob's fixed part (what the
+    // min-sum iteration reads) plus vrow / vpos; the reset snapshot, col and cvn are read from the global blob.
+    const bool image = !with_col;
     L.nn = nn; L.m = m; L.es_max = es; L.lcap = lcap;
     int o = 16;
     L.off_prior = o; o += 8 * nn; o = r16(o);
@@ -296,16 +299,18 @@ static void make_layout(SubLayout &L, int nn, int m, int es, int lcap, bool with
     L.off_coff = o; o += 2 * (m + 1); o = r16(o);
     L.off_crank = o; o += 2 * m; o = r16(o);
     L.off_synd = o; o += m; o = r16(o);
+    L.off_vperm = o; o += 2 * nn; o = r16(o);
+    L.off_cperm = o; o += 2 * m; o = r16(o);
+    const int prefix = o;
     L.off_vnmask = o; o += nn; o = r16(o);
     L.off_cnmask = o; o += m; o = r16(o);
     L.off_cndeg = o; o += m; o = r16(o);
-    L.off_vperm = o; o += 2 * nn; o = r16(o);
-    L.off_cperm = o; o += 2 * m; o = r16(o);
+    if (image && SWD_DIET) o = prefix;
     L.off_col = o; if (with_col) { o += 2 * nn; o = r16(o); }
     L.fixed_bytes = o;
     L.off_vrow = o; o += r16(2 * es);
     L.off_vpos = o; o += r16(2 * es);
-    L.off_cvn = o; o += r16(2 * es);
+    L.off_cvn = o; if (!(image && SWD_DIET)) o += r16(2 * es);
     L.blob_bytes = o;
 }
 
@@ -319,9 +324,9 @@ static void make_path_smem(PathSmem &S3, int nn, int m, int es) {
     S3.off_cndeg = o; o += m; o = r16(o);
     S3.off_flip = o; o += m; o = r16(o);
     S3.off_upar = o; o += 4 * m; o = r16(o);
-    S3.off_bvn = o; o += nn; o = r16(o);
-    S3.off_bcn = o; o += m; o = r16(o);
-    S3.off_bdeg = o; o += m; o = r16(o);
+    S3.off_bvn = o; if (!SWD_DIET) { o += nn; o = r16(o); }
+    S3.off_bcn = o; if (!SWD_DIET) { o += m; o = r16(o); }
+    S3.off_bdeg = o; if (!SWD_DIET) { o += m; o = r16(o); }
     S3.off_red = o; o += 64 * 8 + 64 * 4; o = r16(o);
     S3.off_misc = o; o += 64;
     S3.off_bar = o; o += 16;
@@ -350,6 +355,7 @@ static int setup_kernels(swd_decoder *d) {
     P.rec_stride = r16((int)sizeof(RecHeader) + 4 * ((nn + 31) / 32));
     P.side_stride = r16((int)sizeof(SideHeader) + nn + 2 * m);
     P.shared_T = 0; P.n_nodes = 0; P.node_stride = 16;
+    P.bak_stride = SWD_DIET ? r16(nn) + 2 * r16(m) : 16;
     // ---- blob layouts: global (worst case), shared-memory tier A (typical shots), tier B (worst case)
     const int lcap = std::min(255, d->max_row_deg);
     const int es_slots = es + m;      // every row may carry one pad slot
@@ -499,7 +505,8 @@ static int alloc_workspace(swd_decoder *d, long long want) {
     const int n = d->n;
     const bool osd = d->cfg.kind == SWD_KIND_OSD_WINDOW;
     size_t per = (size_t)n * 8 + d->L.blob_bytes + (size_t)d->P.n_rec * d->P.rec_stride + (size_t)d->P.n_side * d->P.side_stride + 4 + 64 +
-                 (size_t)d->P.n_nodes * d->P.node_stride;
+                 (size_t)d->P.n_nodes * d->P.node_stride + (size_t)std::max(1, std::max(d->P.n_tree + 1, d->P.n_side)) * SWD_WL_MAX * sizeof(u64) +
+                 (size_t)std::max(1, d->P.n_tree) * d->P.bak_stride;
     if (osd) per += (size_t)n * 32 + osd_bytes_per_shot(d->m, n);
     long long cap = std::max<long long>(1, std::min<long long>(want, (long long)(budget / per)));
     if (cap <= d->cap) return SWD_OK;
@@ -516,6 +523,9 @@ static int alloc_workspace(swd_decoder *d, long long want) {
     size_t o_side = o; o += a256((size_t)cap * std::max(1, d->P.n_side) * d->P.side_stride);
     size_t o_node = o; o += a256((size_t)cap * std::max(1, d->P.n_nodes) * d->P.node_stride);
     size_t o_osd = o; if (osd) o += a256((size_t)cap * osd_bytes_per_shot(d->m, n));
+    const long long wl_stride = cap * std::max(1, std::max(d->P.n_tree + 1, d->P.n_side));
+    size_t o_bak = o; o += a256((size_t)cap * std::max(1, d->P.n_tree) * d->P.bak_stride);
+    size_t o_wl = o; o += a256((size_t)wl_stride * SWD_WL_MAX * sizeof(u64));
     cudaError_t e = cudaMalloc(&d->ws_block, o);
     if (e != cudaSuccess) { set_err("workspace cudaMalloc failed"); return SWD_ERR_NOMEM; }
     CK(cudaMemset(d->ws_block, 0, o_list));
@@ -523,6 +533,7 @@ static int alloc_workspace(swd_decoder *d, long long want) {
     d->ws.counters = (int *)(b + o_cnt); d->ws.stats = (u64 *)(b + o_stats); d->ws.gdg_list = (int *)(b + o_list);
     d->ws.sum = (double *)(b + o_sum); d->ws.hist = osd ? (double *)(b + o_hist) : nullptr;
     d->ws.blob = b + o_blob; d->ws.rec = b + o_rec; d->ws.side = b + o_side; d->ws.node = b + o_node;
+    d->ws.wl = (u64 *)(b + o_wl); d->ws.wl_stride = wl_stride; d->ws.bak = b + o_bak;
     if (osd) osd_bind(&d->ow, b + o_osd, cap, d->m, n);
     if (!d->hscratch) CK(cudaMalloc(&d->hscratch, (size_t)d->grid1 * 4 * n * sizeof(double)));
     d->cap = cap;

@@ -20,6 +20,9 @@ typedef unsigned long long u64;
 #define SWD_MAX_PM  10000.0     /* bpgd.cpp:11 */
 #define FULLMASK    0xffffffffu
 #define SWD_CPT     4           /* checks owned per thread in path kernels: m <= SWD_CPT * blockDim */
+#ifndef SWD_DIET
+#define SWD_DIET    1           /* 1: cvn, the reset snapshot and the tree backup stay in HBM (L2), not in shared memory */
+#endif
 
 // ----------------------------------------------------------------------------------------------
 // layouts (byte offsets), computed once on the host
@@ -86,6 +89,7 @@ struct GdgDev {                 // parameters of the decimation tree
     // shared-prefix tree: the first shared_T decimation steps are identical for all branch paths with the same
     // prefix of favour/flip decisions, so they are computed once per prefix ("nodes") instead of once per path
     int shared_T, n_nodes, node_stride;
+    int bak_stride;             // bytes per tree-path backup (vn_mask, cn_mask, cn_deg)
     int node_off_err, node_off_cn, node_off_deg, node_off_flip, node_off_msg, node_off_hist;
 };
 
@@ -99,7 +103,27 @@ struct Workspace {              // per-batch device buffers
     u8 *side;                   // [cap][n_side][side_stride]
     u8 *node;                   // [cap][n_nodes][node_stride] shared-prefix snapshots (masks, messages, history)
     u64 *stats;                 // device counters: [0] pre edge-iters [1] path edge-iters [2] paths [3] bp calls [4] osd shots
+    // work lists of the branch-path launches: list `l` holds counters[SWD_WL_CNT + l] packed items at wl + l * wl_stride.
+    // A launch only draws tickets for work that exists (a node that died or converged lists no children), and the item
+    // itself carries what the set-up needs first (slot, branch path, message-slot count), so the shot's graph can be
+    // requested from HBM right after the item is read.
+    u64 *wl;
+    long long wl_stride;
+    u8 *bak;                    // [cap][n_tree][bak_stride] tree paths' backup state (bpgd.cpp:476-484), SWD_DIET only
 };
+#define SWD_WL_CNT   32          /* counters[32 ..]: list lengths */
+#define SWD_WL_MAX   20
+// item: bits 0..27 slot, 28..43 message slots (es), 44 bad_rows, 48..63 branch path
+__device__ __forceinline__ u64 wl_pack(int slot, int es, int bad, int path) {
+    return (u64)(u32)slot | ((u64)(u32)es << 28) | ((u64)(bad ? 1u : 0u) << 44) | ((u64)(u32)path << 48);
+}
+__device__ __forceinline__ void wl_push(const Workspace &ws, int list, u64 item) {
+    const int pos = atomicAdd(&ws.counters[SWD_WL_CNT + list], 1);
+    ws.wl[(size_t)list * ws.wl_stride + pos] = item;
+}
+// list ids (tier t = 0 typical shots / 1 oversized shortened graphs): node level l: 2 l + t; with T = shared_T:
+// main path 2 T + t, other paths from depth T: 2 T + 2 + t, side branches 2 T + 4 + t.  Kinds without the shared-prefix
+// tree use list t for their first (phase 0) launch.
 
 // ----------------------------------------------------------------------------------------------
 // small helpers
@@ -515,19 +539,30 @@ __device__ __forceinline__ double flip_sign(double x, u32 flip) {
 }
 
 // one message slot of the first check-update loop: running (min1, min2, argmin), sign and dead masks.
-// Plain compares instead of fmin/fmax: no operand can be NaN once dead slots are mapped to 1e308.
+// Dead slots (decided VN, pad) hold a quiet NaN: every ordered compare is false for them, so they are neither clipped nor
+// do they enter min1 / min2.  The masks are shifted in most-significant-first (one funnel shift each): after S slots,
+// slot k sits at bit S - 1 - k.  neg: the sign bit (an exact +0.0, which also counts as "<= 0", bpgd.cpp:124, is caught by
+// the caller: it makes min1 zero).  dead: exponent field all ones <=> (|hi| + 0x00100000) carries into bit 31.
 __device__ __forceinline__ void check_slot(const double b, const int k, double &m1, double &m2, int &arg, u32 &neg, u32 &dead) {
-    const bool isdead = (b != b);                                // decided VN or pad slot
-    const bool isneg = (b <= 0.0);                               // false for NaN
-    double a = fabs(b);
-    a = (a > SWD_CLIP) ? SWD_CLIP : a;
-    a = isdead ? SWD_BIG : a;
+    const u32 hi = (u32)__double2hiint(b);
+    const u32 ahi = hi & 0x7fffffffu;
+    double a = __hiloint2double((int)ahi, __double2loint(b));
+    a = (a > SWD_CLIP) ? SWD_CLIP : a;                           // bpgd.cpp:119-121
     const bool lt = a < m1;
-    const double hi = lt ? m1 : a;                               // max(m1, a)
-    m2 = (hi < m2) ? hi : m2;
+    const double h = lt ? m1 : a;                                // max(m1, a); NaN stays NaN
+    m2 = (h < m2) ? h : m2;
     m1 = lt ? a : m1;
     arg = lt ? k : arg;
-    neg |= (u32)isneg << k; dead |= (u32)isdead << k;
+    neg = __funnelshift_l(hi, neg, 1);
+    dead = __funnelshift_l(ahi + 0x00100000u, dead, 1);
+}
+
+// rare: a message of the row is an exact zero - rebuild the sign mask with the reference's "<= 0" test
+__device__ __noinline__ u32 check_neg_mask_exact(const double *row, int len) {
+    u32 neg = 0;
+#pragma unroll 1
+    for (int k = 0; k < len; k++) neg = (neg << 1) | (u32)(row[k] <= 0.0);       // false for NaN
+    return neg;
 }
 
 // rows longer than 32 slots (heavy checks of non-BB codes): out of line, so that the hot loop stays small
@@ -558,21 +593,30 @@ __device__ __forceinline__ void check_update(Ctx &c, int p0, int len, int cm, do
     if (len > 32) { check_update_long(row, len, cm, fpos, fneg); return; }
     double m1 = SWD_BIG, m2 = SWD_BIG; int arg = -1;
     u32 neg = 0, dead = 0;
+    // rows have an odd number of slots (pad): the first one alone, then two per trip
+    check_slot(row[0], 0, m1, m2, arg, neg, dead);
 #pragma unroll 1
-    for (int k = 0; k < len; k += 2) {
-        const double b0 = row[k];
-        const double b1 = (k + 1 < len) ? row[k + 1] : dnan();
+    for (int k = 1; k < len; k += 2) {
+        const double b0 = row[k], b1 = row[k + 1];
         check_slot(b0, k, m1, m2, arg, neg, dead);
         check_slot(b1, k + 1, m1, m2, arg, neg, dead);
     }
+    if (m1 == 0.0) neg = check_neg_mask_exact(row, len);
     const u32 par = (u32)cm ^ (__popc(neg) & 1u);
     const double q1 = m1 * fpos, q2 = m2 * fpos;                 // c2b magnitude * alpha (sign applied below)
-    u32 live = ~dead & ((len >= 32) ? 0xffffffffu : ((1u << len) - 1u));
+    // second sweep: every live slot gets +-q1 (sign = row parity ^ own sign), then the argmin slot is patched with +-q2.
+    // Masks re-aligned so that slot k sits at bit 31 - k; the row parity is folded into the sign mask.
+    const int sh = 32 - len;                                     // 1 <= len <= 31 (odd)
+    u32 negA = (neg << sh) ^ (0u - par), deadA = dead << sh;
+    const int q1lo = __double2loint(q1), q1hi = __double2hiint(q1);
+    if (!(deadA & 0x80000000u)) row[0] = __hiloint2double(q1hi ^ (int)(negA & 0x80000000u), q1lo);
 #pragma unroll 1
-    while (live) {                                               // live slots only
-        const int k = __ffs(live) - 1; live &= live - 1;
-        row[k] = flip_sign((k == arg) ? q2 : q1, par ^ ((neg >> k) & 1u));
+    for (int k = 1; k < len; k += 2) {
+        if (!(deadA & 0x40000000u)) row[k] = __hiloint2double(q1hi ^ (int)((negA << 1) & 0x80000000u), q1lo);
+        if (!(deadA & 0x20000000u)) row[k + 1] = __hiloint2double(q1hi ^ (int)((negA << 2) & 0x80000000u), q1lo);
+        negA <<= 2; deadA <<= 2;
     }
+    if (arg >= 0) row[arg] = flip_sign(q2, par ^ ((neg >> (len - 1 - arg)) & 1u));
 }
 
 // one variable-node update (bpgd.cpp:151-182) for a VN of degree d <= DM: returns the posterior, writes the hard
@@ -636,9 +680,18 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
         na = run;
         __syncthreads();
     }
-    for (int it = 0; it <= num_iter; it++) {
+    // work counters: the active sets do not change inside a call, so count them once (not per iteration)
+    u32 my_vn = 0, my_edges = 0, my_cn = 0;
+#pragma unroll
+    for (int i = 0; i < VPT; i++) {
+        const int sl = own_slot(i, tid, T);
+        if (sl < c.nn) { const int j = c.vperm[sl]; if (c.vn_mask[j] < 0) { my_vn++; my_edges += (u32)(c.voff[j + 1] - c.voff[j]); } }
+    }
+    for (int i = 0; i * T < na; i++) my_cn += (own_slot(i, tid, T) < na);
+    int it = 0, conv = 0;
+    for (;; it++) {
         // ---- check pass (+ convergence test of the previous iteration)
-        int mism = (it > 0) ? c.bad_rows : 0;
+        int mism = 0;
         const bool last = (it == num_iter);
 #pragma unroll 1
         for (int i = 0; i * T < na; i++) {
@@ -654,11 +707,11 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
             }
             c.upar[r] = 0;
             if (last) continue;
-            cn_iters++;
             { const int p0 = c.coff[q]; check_update(c, p0, c.coff[q + 1] - p0, cm, fpos, fneg); }
         }
         if (it > 0) {
-            if (!__syncthreads_or(mism)) { if (iters_done) *iters_done = it; return 1; }
+            // a check that lost all its columns at reset while its syndrome bit is 1 (bad_rows) can never be satisfied
+            if (!__syncthreads_or(mism) && !c.bad_rows) { conv = 1; break; }
         } else __syncthreads();
         if (last) break;
         // ---- variable pass: ordered prefix / suffix sums (bpgd.cpp:151-182); predicated straight-line code per slot.
@@ -674,13 +727,16 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
                 const double t = vn_update<DMAX>(c, j, e0, d, dw);     // dw: warp-uniform loop bound (VNs are owned in degree order)
                 h[i][ring] = t;      // dynamic ring index: the history lives in (L1/L2-backed) local memory, written once per
                                      // iteration and read once per call by select_vn - it does not occupy 32 registers
-                edge_iters += d; vn_iters++;
             }
         }
         __syncthreads();
     }
-    if (iters_done) *iters_done = num_iter > 0 ? num_iter : 0;
-    return 0;
+    // `it` variable passes were executed; check updates: one per variable pass, plus one more when the call converged
+    // before the last iteration (the messages of that extra pass are never used)
+    const u32 vp = (u32)it, cp = (u32)(conv ? (it < num_iter ? it + 1 : it) : it);
+    edge_iters += (u64)my_edges * vp; vn_iters += my_vn * vp; cn_iters += my_cn * cp;
+    if (iters_done) *iters_done = conv ? it : (num_iter > 0 ? num_iter : 0);
+    return conv;
 }
 
 // BPGD::select_vn (bpgd.cpp:288-351), whole CTA.  Returns favor (0/1) or -1; guess = -1 if no
@@ -729,7 +785,23 @@ __device__ __forceinline__ int select_vn(Ctx &c, const double (&h)[VPT][4], int 
     }
     any_dec = __syncthreads_or(any_dec);
     if (any_dec) {
-        // per check: how many of its undecided VNs were decimated, with which parity, last scan index
+        // per check: how many of its undecided VNs were decimated and with which parity.  The decimated VNs (few) add
+        // (1 | value << 8) to their checks' parity words - `upar` is zero for every active check between two min-sum
+        // calls (the check pass clears it, bp_run) and is cleared again by the next call's first check pass - so no
+        // thread scans whole rows here (and `cvn` is only touched on the contradiction path below).
+#pragma unroll
+        for (int i = 0; i < VPT; i++) {
+            const int sl = own_slot(i, tid, T);
+            if (sl < c.nn) {
+                const int j = c.vperm[sl];
+                const int a = c.dec[j];
+                if (a >= 0) {
+#pragma unroll 1
+                    for (int e = c.voff[j]; e < c.voff[j + 1]; e++) atomicAdd(&c.upar[c.vrow[e]], 1u | ((u32)a << 8));
+                }
+            }
+        }
+        __syncthreads();
         int ndg[SWD_CPT], nmk[SWD_CPT];                      // SWD_CPT checks per thread (m <= SWD_CPT*T)
 #pragma unroll
         for (int i = 0; i < SWD_CPT; i++) {
@@ -739,18 +811,20 @@ __device__ __forceinline__ int select_vn(Ctx &c, const double (&h)[VPT][4], int 
             const int r = c.cperm[q];
             const int cm = c.cn_mask[r];
             if (cm < 0) continue;
-            int cnt = 0, par = 0, last = -1;
-            const int p0 = c.coff[q], p1 = c.coff[q + 1];
-#pragma unroll 1
-            for (int p = p0; p < p1; p++) {
-                const int j = c.cvn[p];
-                if (j == 0xffff) continue;
-                const int a = c.dec[j];
-                if (a >= 0) { cnt++; par ^= a; last = max(last, j); }
-            }
+            const u32 w = c.upar[r];
+            const int cnt = (int)(w & 0xffu), par = (int)((w >> 8) & 1u);        // row weight <= 255
             if (cnt) {
                 const int nd = (int)c.cn_deg[r] - cnt, nm = cm ^ par;
-                if (nd == 0 && nm != 0) atomicMin(&c.misc[0], last);
+                if (nd == 0 && nm != 0) {                    // contradiction (rare): last decimated VN of the row in scan order
+                    int last = -1;
+                    const int p0 = c.coff[q], p1 = c.coff[q + 1];
+#pragma unroll 1
+                    for (int p = p0; p < p1; p++) {
+                        const int j = c.cvn[p];
+                        if (j != 0xffff && c.dec[j] >= 0) last = max(last, j);
+                    }
+                    atomicMin(&c.misc[0], last);
+                }
                 ndg[i] = nd; nmk[i] = (nd == 0) ? -1 : nm;
             }
         }

@@ -383,7 +383,11 @@ sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayo
                 for (int j = tid; j < nn; j += T) if (vn_mask[j] >= 0) dec_out[(size_t)shot * n + col[j]] = (u8)vn_mask[j];
             }
         }
-        if (tid == 0) { hdr->es = nslots; hdr->status = status; hdr->bad_rows = bad; hdr->shot = shot; if (nslots > capA) atomicAdd(&ws.counters[8], 1); }
+        if (tid == 0) {
+            hdr->es = nslots; hdr->status = status; hdr->bad_rows = bad; hdr->shot = shot;
+            if (nslots > capA) atomicAdd(&ws.counters[8], 1);
+            if (status == 0) wl_push(ws, nslots > capA ? 1 : 0, wl_pack(slot, nslots, bad, 0));
+        }
         __syncthreads();
         // publish the blob (16-byte vectors): fixed part + the three es-sized arrays
         {
@@ -454,7 +458,7 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
     c.prior = pinned_smem<const double>(blob + L.off_prior);
     c.voff = pinned_smem<const u16>(blob + L.off_voff); c.coff = pinned_smem<const u16>(blob + L.off_coff);
     c.crank = (const u16 *)(blob + L.off_crank);
-    c.vrow = pinned_smem<const u16>(blob + L.off_vrow); c.vpos = pinned_smem<const u16>(blob + L.off_vpos); c.cvn = (const u16 *)(blob + L.off_cvn);
+    c.vrow = pinned_smem<const u16>(blob + L.off_vrow); c.vpos = pinned_smem<const u16>(blob + L.off_vpos); c.cvn = (const u16 *)(blob + L.off_cvn);   // SWD_DIET: re-pointed per item
     c.vperm = pinned_smem<const u16>(blob + L.off_vperm); c.cperm = pinned_smem<const u16>(blob + L.off_cperm);
     c.synd = blob + L.off_synd;
     c.msg = pinned_smem<double>(st + S.off_msg);
@@ -462,20 +466,32 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
     c.cn_mask = pinned_smem<i8>(st + S.off_cnmask); c.cn_deg = st + S.off_cndeg; c.flip = pinned_smem<u8>(st + S.off_flip);
     c.upar = pinned_smem<u32>(st + S.off_upar);
     c.red_d = (double *)(st + S.off_red); c.red_i = (int *)(c.red_d + 64); c.misc = (int *)(st + S.off_misc);
+#if !SWD_DIET
     i8 *bvn = (i8 *)(st + S.off_bvn); i8 *bcn = (i8 *)(st + S.off_bcn); u8 *bdeg = st + S.off_bdeg;
+#endif
     u64 *bar = (u64 *)(st + S.off_bar);
+#if !SWD_DIET
     const i8 *snap_vn = (const i8 *)(blob + L.off_vnmask), *snap_cn = (const i8 *)(blob + L.off_cnmask);
     const u8 *snap_deg = blob + L.off_cndeg;
+#endif
 
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     u32 mphase = 0;
-    const int count = (tier == 1 && ws.counters[8] == 0) ? 0 : ws.counters[0];
     const int node_level = (phase >= 2) ? phase - 2 : -1;          // >= 0: shared-prefix node of that depth
-    const int npaths = (node_level >= 0) ? (1 << node_level)
-                     : (phase == 0) ? ((P.kind == SWD_KIND_BPGDG && P.multi_thread) ? 1 + P.n_tree : 1) : P.n_side;
+    const int sT = P.shared_T;
+    const int npaths = (phase == 0 && sT == 0 && P.kind == SWD_KIND_BPGDG && P.multi_thread) ? 1 + P.n_tree : 1;
+    // input lists of this launch (see swd_device.cuh): l1 is drawn `npaths` times (path-major), then l2
+    int l1, l2 = -1;
+    if (node_level >= 0) l1 = 2 * node_level + tier;
+    else if (phase == 0) { if (sT > 0) { l1 = 2 * sT + tier; l2 = 2 * sT + 2 + tier; } else l1 = tier; }
+    else l1 = 2 * sT + 4 + tier;
+    // list lengths live in shared memory (misc[8..10]): they are only needed once per item
+    if (tid == 0) {
+        const int n1 = ws.counters[SWD_WL_CNT + l1], n2 = (l2 >= 0) ? ws.counters[SWD_WL_CNT + l2] : 0;
+        c.misc[8] = n1; c.misc[9] = npaths * n1; c.misc[10] = npaths * n1 + n2;
+    }
     const int ticket = (node_level >= 0) ? 16 + 2 * node_level + tier : 1 + phase + 3 * tier;
-    const long long total = (long long)npaths * count;
     u64 edge_iters = 0, bp_calls = 0, paths_run = 0;
     u32 vn_iters = 0, cn_iters = 0;
 
@@ -483,47 +499,53 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
         __syncthreads();
         if (tid == 0) c.misc[2] = atomicAdd(&ws.counters[ticket], 1);
         __syncthreads();
-        const long long item = c.misc[2];
-        if (item >= total) break;
-        const int path = (int)(item / count), slot = (int)(item % count);
+        const int tk = c.misc[2];
+        if (tk >= c.misc[10]) break;
+        const int n1 = c.misc[8], total1 = c.misc[9];
+        const u64 item = (tk < total1) ? ws.wl[(size_t)l1 * ws.wl_stride + (npaths > 1 ? tk % n1 : tk)]
+                                       : ws.wl[(size_t)l2 * ws.wl_stride + (tk - total1)];
+        const int slot = (int)(item & 0xfffffffu), es = (int)((item >> 28) & 0xffffu);
+        const int path = (npaths > 1) ? tk / n1 : (int)(item >> 48);
         const unsigned char *gblob = ws.blob + (size_t)slot * LG.blob_bytes;
-        const BlobHeader gh = *(const BlobHeader *)gblob;
-        if (gh.status != 0) continue;
-        if ((gh.es > capA) != (tier == 1)) continue;          // tier A: typical shots; tier B: oversized shortened graphs
-        const SideHeader *sh = nullptr;
-        if (phase == 1) {
-            sh = (const SideHeader *)(ws.side + ((size_t)slot * P.n_side + path) * P.side_stride);
-            if (!sh->valid) continue;
-        }
         // parent node of the shared-prefix tree (if this item continues from one)
         const unsigned char *pnode = nullptr;
-        NodeHeader ph = {0, -1, 0, 0};
-        if (P.shared_T > 0 && (node_level > 0 || phase == 0)) {
-            const int plevel = (node_level > 0) ? node_level - 1 : P.shared_T - 1;
+        if (sT > 0 && (node_level > 0 || phase == 0)) {
+            const int plevel = (node_level > 0) ? node_level - 1 : sT - 1;
             pnode = ws.node + ((size_t)slot * P.n_nodes + ((1 << plevel) - 1) + (path >> 1)) * P.node_stride;
-            ph = *(const NodeHeader *)pnode;
-            if (!ph.alive) continue;                              // that prefix already converged or died
         }
         // ---- stage the shot's shortened graph into shared memory with TMA bulk copies
         if (tid == 0) {
             fence_proxy_async();
-            const u32 vb = (u32)((gh.es * 2 + 15) & ~15);
-            const u32 mb = pnode ? (u32)((gh.es * 8 + 15) & ~15) : 0u;
-            mbar_expect_tx(bar, (u32)L.fixed_bytes + 3 * vb + mb);
+            const u32 vb = (u32)((es * 2 + 15) & ~15);
+            const u32 mb = pnode ? (u32)((es * 8 + 15) & ~15) : 0u;
+            mbar_expect_tx(bar, (u32)L.fixed_bytes + (SWD_DIET ? 2 : 3) * vb + mb);
             bulk_g2s(blob, gblob, (u32)L.fixed_bytes, bar);
             if (vb) {
                 bulk_g2s(blob + L.off_vrow, gblob + LG.off_vrow, vb, bar);
                 bulk_g2s(blob + L.off_vpos, gblob + LG.off_vpos, vb, bar);
+#if !SWD_DIET
                 bulk_g2s(blob + L.off_cvn, gblob + LG.off_cvn, vb, bar);
+#endif
             }
             if (mb) bulk_g2s(c.msg, pnode + P.node_off_msg, mb, bar);       // messages of the parent node
         }
-        mbar_wait(bar, mphase);
-        mphase ^= 1;
-        c.es = gh.es; c.bad_rows = gh.bad_rows;
+#if SWD_DIET
+        c.cvn = (const u16 *)(gblob + LG.off_cvn);
+        const i8 *snap_vn = (const i8 *)(gblob + LG.off_vnmask), *snap_cn = (const i8 *)(gblob + LG.off_cnmask);
+        const u8 *snap_deg = gblob + LG.off_cndeg;
+#define SWD_BAK_PTRS i8 *bvn = (i8 *)(ws.bak + ((size_t)slot * max(1, P.n_tree) + (size_t)max(0, path - 1)) * P.bak_stride); \
+                     i8 *bcn = bvn + ((c.nn + 15) & ~15); u8 *bdeg = (u8 *)(bcn + ((c.m + 15) & ~15));
+#else
+#define SWD_BAK_PTRS
+#endif
+        // ---- meanwhile: headers and the start state that comes from HBM (parent node / side snapshot)
+        const SideHeader *sh = nullptr;
+        SideHeader shv = {0, -1, 0, 0};
+        if (phase == 1) { sh = (const SideHeader *)(ws.side + ((size_t)slot * P.n_side + path) * P.side_stride); shv = *sh; }
+        NodeHeader ph = {0, -1, 0, 0};
+        if (pnode) ph = *(const NodeHeader *)pnode;
+        c.es = es; c.bad_rows = (int)((item >> 44) & 1u);
         c.C = 30; c.D = 3;
-
-        // ---- load the start state
         double h[VPT][4];
         if (pnode) {
             const i8 *nvn = (const i8 *)(pnode + sizeof(NodeHeader)), *ner = (const i8 *)(pnode + P.node_off_err);
@@ -538,20 +560,33 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
             for (int i = 0; i < VPT; i++)
 #pragma unroll
                 for (int q = 0; q < 4; q++) h[i][q] = nh[(size_t)(i * 4 + q) * T + tid];
-            __syncthreads();
-        } else {
-        if (phase != 1) {
-#pragma unroll 1
-            for (int j = tid; j < c.nn; j += T) { const i8 v = snap_vn[j]; c.vn_mask[j] = v; c.error[j] = v < 0 ? 0 : v; }
-#pragma unroll 1
-            for (int r = tid; r < c.m; r += T) { c.cn_mask[r] = snap_cn[r]; c.cn_deg[r] = snap_deg[r]; c.flip[r] = 0; }
-        } else {
+        } else if (phase == 1) {
             const i8 *svn = (const i8 *)(sh + 1); const i8 *scn = svn + c.nn; const u8 *sdg = (const u8 *)(scn + c.m);
 #pragma unroll 1
             for (int j = tid; j < c.nn; j += T) { const i8 v = svn[j]; c.vn_mask[j] = v; c.error[j] = v; }   // bpgd.cpp:541
 #pragma unroll 1
             for (int r = tid; r < c.m; r += T) { c.cn_mask[r] = scn[r]; c.cn_deg[r] = sdg[r]; c.flip[r] = 0; }
         }
+#if SWD_DIET
+        else {      // the post-reset state, from the global blob
+#pragma unroll 1
+            for (int j = tid; j < c.nn; j += T) { const i8 v = snap_vn[j]; c.vn_mask[j] = v; c.error[j] = v < 0 ? 0 : v; }
+#pragma unroll 1
+            for (int r = tid; r < c.m; r += T) { c.cn_mask[r] = snap_cn[r]; c.cn_deg[r] = snap_deg[r]; c.flip[r] = 0; }
+        }
+#endif
+        mbar_wait(bar, mphase);
+        mphase ^= 1;
+        if (pnode) __syncthreads();
+        else {
+#if !SWD_DIET
+        if (phase != 1) {
+#pragma unroll 1
+            for (int j = tid; j < c.nn; j += T) { const i8 v = snap_vn[j]; c.vn_mask[j] = v; c.error[j] = v < 0 ? 0 : v; }
+#pragma unroll 1
+            for (int r = tid; r < c.m; r += T) { c.cn_mask[r] = snap_cn[r]; c.cn_deg[r] = snap_deg[r]; c.flip[r] = 0; }
+        }
+#endif
         __syncthreads();
         init_msgs<VPT>(c);
 #pragma unroll
@@ -582,7 +617,7 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
         }
         else if (phase == 1) {                                  // side branch j (bpgd.cpp:527-570)
             role = R_SIDE; limit = P.side_step; rec = recbase + (size_t)(1 + P.n_tree + path) * P.rec_stride;
-            c.A = 0; c.A_sum = -10; depth = sh->depth; pend_vn = sh->vn; pend_val = sh->value;
+            c.A = 0; c.A_sum = -10; depth = shv.depth; pend_vn = shv.vn; pend_val = shv.value;
         } else if (path == 0) { role = R_MAIN; mainlike = true; limit = P.max_step; c.A = -3; c.A_sum = -16; }   // bpgd.cpp:623-683
         else {                                                  // tree branch id (bpgd.cpp:435-525)
             role = R_TREE; limit = P.tree_step + P.T + 1; rec = recbase + (size_t)path * P.rec_stride;
@@ -673,12 +708,16 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
                         for (int j = tid; j < c.nn; j += T) svn[j] = c.vn_mask[j];
 #pragma unroll 1
                         for (int r = tid; r < c.m; r += T) { scn[r] = c.cn_mask[r]; sdg[r] = c.cn_deg[r]; }
-                        if (tid == 0) { SideHeader *q = (SideHeader *)sp; q->vn = guess; q->value = 1 - favor; q->depth = depth + 1; q->valid = 1; }
+                        if (tid == 0) {
+                            SideHeader *q = (SideHeader *)sp; q->vn = guess; q->value = 1 - favor; q->depth = depth + 1; q->valid = 1;
+                            wl_push(ws, 2 * sT + 4 + tier, wl_pack(slot, c.es, c.bad_rows, depth - P.T));
+                        }
                     }
                     if (role == R_TREE && stage == 0) {
                         if (depth < P.T) {                                                        // :464-470
                             if ((path >> (P.T - 1 - depth)) & 1) { on_side = 1; c.A = 0; c.A_sum = -10; favor = 1 - favor; }
                         } else if (depth == P.T) {                                                // :476-484
+                            SWD_BAK_PTRS
 #pragma unroll 1
                             for (int j = tid; j < c.nn; j += T) bvn[j] = c.vn_mask[j];
 #pragma unroll 1
@@ -718,6 +757,7 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
             }
             if (role == R_TREE && stage == 0 && saved) {                                          // :490-503
                 __syncthreads();
+                SWD_BAK_PTRS
 #pragma unroll 1
                 for (int j = tid; j < c.nn; j += T) { const i8 v = bvn[j]; c.vn_mask[j] = v; c.error[j] = v; }
 #pragma unroll 1
@@ -746,7 +786,15 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
             for (int i = 0; i < VPT; i++)
 #pragma unroll
                 for (int q = 0; q < 4; q++) nh[(size_t)(i * 4 + q) * T + tid] = h[i][q];
-            if (tid == 0) { NodeHeader *hd = (NodeHeader *)nd; hd->guess = node_guess; hd->favor = node_favor; hd->alive = 1; }
+            if (tid == 0) {
+                NodeHeader *hd = (NodeHeader *)nd; hd->guess = node_guess; hd->favor = node_favor; hd->alive = 1;
+                // the two continuations of this prefix: next node level, or (after the last level) the branch paths - the
+                // main path has its own list, drawn first (it is the longest item of the launch)
+                const bool lastlv = (node_level + 1 >= sT);
+                const int lnext = lastlv ? 2 * sT + 2 + tier : 2 * (node_level + 1) + tier;
+                wl_push(ws, (lastlv && path == 0) ? 2 * sT + tier : lnext, wl_pack(slot, c.es, c.bad_rows, 2 * path));
+                wl_push(ws, lnext, wl_pack(slot, c.es, c.bad_rows, 2 * path + 1));
+            }
         } else if (role != R_ST && (conv || mainlike || role == R_GD)) record_result(c, rec, conv);
     }
     // ---- work counters

@@ -74,8 +74,10 @@ post_bp_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, in
     c.upar = (u32 *)(st + S.off_upar);
     c.red_d = (double *)(st + S.off_red); c.red_i = (int *)(c.red_d + 64); c.misc = (int *)(st + S.off_misc);
     u64 *bar = (u64 *)(st + S.off_bar);
+#if !SWD_DIET
     const i8 *snap_vn = (const i8 *)(blob + L.off_vnmask), *snap_cn = (const i8 *)(blob + L.off_cnmask);
     const u8 *snap_deg = blob + L.off_cndeg;
+#endif
     c.A = 0; c.A_sum = 0; c.C = 0; c.D = 0;
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
@@ -96,14 +98,21 @@ post_bp_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, in
         if (tid == 0) {
             fence_proxy_async();
             const u32 vb = (u32)((gh.es * 2 + 15) & ~15);
-            mbar_expect_tx(bar, (u32)L.fixed_bytes + 3 * vb);
+            mbar_expect_tx(bar, (u32)L.fixed_bytes + (SWD_DIET ? 2 : 3) * vb);
             bulk_g2s(blob, gblob, (u32)L.fixed_bytes, bar);
             if (vb) {
                 bulk_g2s(blob + L.off_vrow, gblob + LG.off_vrow, vb, bar);
                 bulk_g2s(blob + L.off_vpos, gblob + LG.off_vpos, vb, bar);
+#if !SWD_DIET
                 bulk_g2s(blob + L.off_cvn, gblob + LG.off_cvn, vb, bar);
+#endif
             }
         }
+#if SWD_DIET
+        c.cvn = (const u16 *)(gblob + LG.off_cvn);
+        const i8 *snap_vn = (const i8 *)(gblob + LG.off_vnmask), *snap_cn = (const i8 *)(gblob + LG.off_cnmask);
+        const u8 *snap_deg = gblob + LG.off_cndeg;
+#endif
         mbar_wait(bar, mphase);
         mphase ^= 1;
         c.es = gh.es; c.bad_rows = gh.bad_rows;
