@@ -11,6 +11,7 @@
 
 #include "../../include/swd_b200.h"
 #include "swd_kernels.cuh"
+#include "swd_stream.cuh"
 #include "swd_osd.cuh"
 #include "swd_window.cuh"
 #include "swd_bp4.cuh"
@@ -58,6 +59,8 @@ struct swd_decoder {
     PathSmem PS{}, PSB{};
     int es_capA = 0, grid3B = 0;
     PreSmem PRE{};
+    // graphs whose messages exceed one SM's shared memory: HBM-streamed full-window BP (swd_stream.cuh)
+    bool stream_mode = false; int Ts = 256; size_t stream_smem = 0; StreamWs sw{}; void *sw_block = nullptr; long long sw_G = 0;
     SortSmem SS{};
     OsdSmem OS{};
     GdgDev P{};
@@ -265,6 +268,7 @@ extern "C" void swd_destroy(swd_decoder *d) {
     for (auto &p : d->d_graph) if (p) cudaFree(p);
     if (d->ws_block) cudaFree(d->ws_block);
     if (d->hscratch) cudaFree(d->hscratch);
+    if (d->sw_block) cudaFree(d->sw_block);
     if (d->d_synd) cudaFree(d->d_synd);
     if (d->d_corr) cudaFree(d->d_corr);
     if (d->d_conv) cudaFree(d->d_conv);
@@ -380,7 +384,15 @@ static int setup_kernels(swd_decoder *d) {
     const bool ps = (c.bp_method == SWD_BP_PRODUCT_SUM);
     if (ps) { o = r16(o); S1.off_fwd = o; o += 8 * std::max(d->nnz, 1); }
     S1.total = o; S1.off_vrec = o; S1.off_cpos = o;
-    if (S1.total > 227 * 1024) { set_err("window graph does not fit in shared memory (nnz too large)"); return SWD_ERR_UNSUPPORTED; }
+    if (S1.total > 227 * 1024 || getenv("SWD_FORCE_STREAM")) {
+        // messages streamed from HBM, one thread per shot (swd_stream.cuh); syndrome + parity bit words per thread in shared memory
+        if (ps) { set_err("product-sum BP: window graph does not fit in shared memory (nnz too large)"); return SWD_ERR_UNSUPPORTED; }
+        const int MW = (m + 31) / 32;
+        int ts = 256; while (ts > 32 && (size_t)8 * MW * ts > 200 * 1024) ts -= 32;
+        if ((size_t)8 * MW * ts > 200 * 1024) { set_err("window graph has too many checks for the streamed BP kernel"); return SWD_ERR_UNSUPPORTED; }
+        d->stream_mode = true; d->Ts = ts; d->stream_smem = (size_t)8 * MW * ts;
+        S1.total = 0;
+    }
     // staged static graph info (per-slot records + CSC->CSR map) if it still fits next to the messages
     bool staged = false;
     {
@@ -390,6 +402,7 @@ static int setup_kernels(swd_decoder *d) {
         if (q <= 227 * 1024 && occ_staged >= occ_unstaged && !getenv("SWD_PRE_UNSTAGED")) { staged = true; S1.off_vrec = ov; S1.off_cpos = oc; S1.total = q; }
     }
     int occ = 0, st;
+    if (!d->stream_mode) {
 #define SWD_PRE_PICK(D, MT, MB) (ps ? (staged ? pre_bp_kernel<D, MT, MB, true, true> : pre_bp_kernel<D, MT, MB, true, false>) \
                                     : (staged ? pre_bp_kernel<D, MT, MB, false, true> : pre_bp_kernel<D, MT, MB, false, false>))
     if (ps) d->pre_fn = d->max_col_deg <= 8 ? SWD_PRE_PICK(8, 256, 2) : SWD_PRE_PICK(16, 256, 2);
@@ -407,6 +420,7 @@ static int setup_kernels(swd_decoder *d) {
 #undef SWD_PRE_PICK
     if (occ < 1) { set_err("pre_bp_kernel does not fit"); return SWD_ERR_UNSUPPORTED; }
     d->grid1 = d->num_sm * occ;
+    } else d->grid1 = d->num_sm;
     // ---- K2
     SortSmem &S2 = d->SS;
     int np2 = 64; while (np2 < n) np2 <<= 1;
@@ -418,17 +432,35 @@ static int setup_kernels(swd_decoder *d) {
     }
     d->T2 = std::min(1024, std::max(128, np2 / 8));
     if (const char *e = getenv("SWD_T2")) d->T2 = std::min(1024, std::max(64, r32up(atoi(e))));
-    o = 0; S2.off_key = o; o += 8 * np2; S2.off_idx = o; o += 2 * np2; o = r16(o);
-    S2.off_posof = o; o += 2 * n; o = r16(o);
-    S2.off_blob = o; o += d->L.blob_bytes;
-    S2.off_u32a = o; o += 4 * (nn + 1); o = r16(o);
-    S2.off_u32b = o; o += 4 * (m + 1); o = r16(o);
-    S2.off_u32c = o; o += 4 * (m + 1); o = r16(o);
-    S2.off_wt = o; o += 4 * 64;
-    S2.off_error = o; o += nn; o = r16(o);
-    S2.off_misc = o; o += 64;
-    S2.off_bins = o; o += 4 * (17 + 256); o = r16(o);
-    S2.total = o;
+    // n beyond the register sort (8 keys x 1024 threads): radix-select from global memory only, no full-sort fall-back, so
+    // key / idx hold cap_sel entries instead of np2 (the un-windowed [[144,12,12]] DEM has n = 8784)
+    S2.big = (np2 > 8192 || getenv("SWD_FORCE_BIG_SORT")) ? 1 : 0;
+    int idx_entries = np2;
+    S2.key_bytes = 8 * np2;
+    if (S2.big) {
+        int cap = 64; while (cap < nn + 64) cap <<= 1;
+        S2.cap_sel = cap; idx_entries = cap;
+        S2.key_bytes = r16(std::max(8 * cap, 4 * 2052));
+    }
+    auto sort_layout = [&](int key_bytes) {
+        int o = 0; S2.off_key = o; o += key_bytes; S2.off_idx = o; o += 2 * idx_entries; o = r16(o);
+        S2.off_posof = o; o += 2 * n; o = r16(o);
+        S2.off_blob = o; o += d->L.blob_bytes;
+        S2.off_u32a = o; o += 4 * (nn + 1); o = r16(o);
+        S2.off_u32b = o; o += 4 * (m + 1); o = r16(o);
+        S2.off_u32c = o; o += 4 * (m + 1); o = r16(o);
+        S2.off_wt = o; o += 4 * 64;
+        S2.off_error = o; o += nn; o = r16(o);
+        S2.off_misc = o; o += 64;
+        S2.off_bins = o; o += 4 * (17 + 256); o = r16(o);
+        S2.total = o;
+    };
+    sort_layout(S2.key_bytes);
+    if (S2.big && 2 * d->nnz > S2.key_bytes) {       // room for the CSR-position -> message-slot table (else: per-edge search)
+        const int kb = r16(2 * d->nnz);
+        sort_layout(kb);
+        if (S2.total <= 227 * 1024) S2.key_bytes = kb; else sort_layout(S2.key_bytes);
+    }
     if (S2.total > 227 * 1024) { set_err("sort/reset kernel does not fit in shared memory"); return SWD_ERR_UNSUPPORTED; }
     if ((st = occupancy(sort_reset_kernel, d->T2, S2.total, &occ))) return st;
     if (occ < 1) { set_err("sort_reset_kernel does not fit"); return SWD_ERR_UNSUPPORTED; }
@@ -535,7 +567,10 @@ static int alloc_workspace(swd_decoder *d, long long want) {
     d->ws.blob = b + o_blob; d->ws.rec = b + o_rec; d->ws.side = b + o_side; d->ws.node = b + o_node;
     d->ws.wl = (u64 *)(b + o_wl); d->ws.wl_stride = wl_stride; d->ws.bak = b + o_bak;
     if (osd) osd_bind(&d->ow, b + o_osd, cap, d->m, n);
-    if (!d->hscratch) CK(cudaMalloc(&d->hscratch, (size_t)d->grid1 * 4 * n * sizeof(double)));
+    if (osd && d->OS.big && !d->ow.big_scratch) {
+        if (cudaMalloc(&d->ow.big_scratch, (size_t)d->grid5 * d->OS.big_stride) != cudaSuccess) { set_err("OSD scratch cudaMalloc failed"); return SWD_ERR_NOMEM; }
+    }
+    if (!d->hscratch && !d->stream_mode) CK(cudaMalloc(&d->hscratch, (size_t)d->grid1 * 4 * n * sizeof(double)));
     d->cap = cap;
     return SWD_OK;
 }
@@ -549,6 +584,47 @@ static int pull_stats(swd_decoder *d, cudaStream_t s) {
     return SWD_OK;
 }
 
+// HBM-streamed full-window BP (graphs beyond one SM's shared memory): tiles of G = grid * Ts shots, one thread per shot
+static int stream_pre_bp(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_corr, u8 *d_conv, int full_hist, int *iter_out,
+                         double *lpr_out, cudaStream_t s) {
+    const int Ts = d->Ts, n = d->n;
+    size_t budget = (size_t)24 << 30;
+    if (const char *e = getenv("SWD_STREAM_BYTES")) budget = (size_t)atoll(e);
+    const size_t per_shot = (size_t)8 * (d->nnz + 4 * (size_t)n) + 4 * (size_t)((n + 31) / 32) + 8;
+    long long Gmax = (long long)d->num_sm * Ts;                                   // one CTA per SM
+    Gmax = std::max<long long>(Ts, std::min<long long>(Gmax, (long long)(budget / per_shot) / Ts * Ts));
+    const long long want = std::min<long long>(Gmax, (B + Ts - 1) / Ts * Ts);
+    if (want > d->sw_G) {
+        CK(cudaStreamSynchronize(s));
+        if (d->sw_block) { cudaFree(d->sw_block); d->sw_block = nullptr; d->sw_G = 0; }
+        auto a256 = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        size_t o = 0;
+        const size_t o_msg = o; o += a256((size_t)8 * d->nnz * want);
+        const size_t o_hs = o; o += a256((size_t)32 * n * want);
+        const size_t o_dec = o; o += a256((size_t)4 * ((n + 31) / 32) * want);
+        const size_t o_it = o; o += a256((size_t)4 * want);
+        const size_t o_cv = o; o += a256((size_t)want);
+        if (cudaMalloc(&d->sw_block, o) != cudaSuccess) { set_err("streamed-BP message buffer cudaMalloc failed"); return SWD_ERR_NOMEM; }
+        unsigned char *b = (unsigned char *)d->sw_block;
+        d->sw.msg = (double *)(b + o_msg); d->sw.hs = (double *)(b + o_hs); d->sw.decw = (u32 *)(b + o_dec);
+        d->sw.itdone = (int *)(b + o_it); d->sw.conv = b + o_cv;
+        d->sw_G = want;
+    }
+    typedef void (*sfn_t)(GraphDev, const u8 *, long long, long long, int, double, StreamWs, int, u64 *);
+    sfn_t fn = d->max_col_deg <= 6 ? pre_bp_stream_kernel<6> : (d->max_col_deg <= 8 ? pre_bp_stream_kernel<8> : pre_bp_stream_kernel<16>);
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    for (long long t0 = 0; t0 < B; t0 += d->sw_G) {
+        const long long nb = std::min<long long>(d->sw_G, B - t0);
+        StreamWs sw = d->sw; sw.G = (nb + Ts - 1) / Ts * Ts;
+        fn<<<(unsigned)(sw.G / Ts), Ts, d->stream_smem, s>>>(d->g, d_synd, B, t0, d->cfg.max_iter, d->cfg.ms_scaling_factor, sw, full_hist, d->ws.stats);
+        pre_bp_stream_finish_kernel<<<(unsigned)std::min<long long>((nb + 7) / 8, 8 * (long long)d->num_sm), 256, 0, s>>>(d->g, B, t0, sw, d_corr, d_conv, d->ws,
+                                                                                                              iter_out, lpr_out);
+        d->ctr.kernel_launches += 2;
+    }
+    CK(cudaGetLastError());
+    return SWD_OK;
+}
+
 // one chunk (B <= cap), everything asynchronous on `s`
 static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_corr, u8 *d_conv, double *d_pm, cudaStream_t s,
                         long long chunk_base) {
@@ -558,12 +634,16 @@ static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_cor
     const int full_hist = (c.kind == SWD_KIND_OSD_WINDOW) ? 1 : 0;
     int *iter_out = (c.kind == SWD_KIND_OSD_WINDOW) ? d->ow.bp_iter + chunk_base : nullptr;
     double *lpr_out = (c.kind == SWD_KIND_OSD_WINDOW) ? d->ow.lpr + (size_t)chunk_base * d->n * 4 : nullptr;
-    {
+    if (d->stream_mode) {
+        KTimer kt(d, s, SWD_K_PRE_BP);
+        int st = stream_pre_bp(d, d_synd, B, d_corr, d_conv, full_hist, iter_out, lpr_out, s);
+        if (st) return st;
+    } else {
     KTimer kt(d, s, SWD_K_PRE_BP);
     d->pre_fn<<<g1, d->T1, d->PRE.total, s>>>(d->g, d_synd, B, c.max_iter, c.ms_scaling_factor, d_corr, d_conv, d->ws,
                                               d->hscratch, full_hist, d->PRE, iter_out, lpr_out);
-    }
     d->ctr.kernel_launches++;
+    }
     if (d_pm) {
         const double fillv = (c.kind == SWD_KIND_OSD_WINDOW) ? 0.0 : SWD_MAX_PM;
         fill_pm_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(d_pm, B, fillv);

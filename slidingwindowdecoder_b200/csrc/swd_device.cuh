@@ -392,6 +392,98 @@ __device__ __forceinline__ bool block_select_sort(double *key, u16 *idx, u32 *wt
     return true;
 }
 
+// The same selection for any n (keys re-read from global memory at every level instead of held in registers) and without a
+// fall-back: the radix descent continues over all 64 key bits (11 bits per level, 9 at the last), and if the boundary
+// bucket is still too crowded then all its keys are EQUAL - the stable order takes those with the smallest indices, which
+// an index-ordered block scan ranks.  Always leaves idx[0..nn) = the first nn entries of the full stable argsort.
+// key needs >= max(2049 u32, CAP u64); idx >= CAP u16; misc[4..7], wt scratch.
+__device__ __forceinline__ void block_select_sort_big(double *key, u16 *idx, u32 *wt, int *misc, const double *__restrict__ src,
+                                                      int n, int nn, int CAP) {
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
+    u32 *hist = (u32 *)key; u64 *ckey = (u64 *)key;
+    u64 prefix = 0;            // bits above `sh + bits` of the boundary key
+    int below = 0, upto = 0, sh = 53, bits = 11;
+    bool equal_tail = false;   // boundary bucket = keys exactly equal to `prefix` (all 64 bits fixed)
+    for (int level = 0;; level++) {
+        const u32 mask = (1u << bits) - 1u;
+        __syncthreads();
+        for (int b = tid; b <= 2048; b += T) hist[b] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += T) {
+            const u64 k = ordered_key(src[i]);
+            if (level == 0 || (k >> (sh + bits)) == prefix) atomicAdd(&hist[(u32)(k >> sh) & mask], 1u);
+        }
+        __syncthreads();
+        block_excl_scan(hist, 2049, wt);
+        const int need = nn - below;
+        for (int b = tid; b < 2048; b += T) if ((int)hist[b] < need && (int)hist[b + 1] >= need) { misc[4] = b; misc[5] = (int)hist[b]; misc[6] = (int)hist[b + 1]; }
+        __syncthreads();
+        const u32 bsel = (u32)misc[4];
+        upto = below + misc[6]; below += misc[5];
+        prefix = (prefix << bits) | bsel;
+        if (upto <= CAP) break;
+        if (sh == 0) { equal_tail = true; break; }
+        if (sh >= 11) { sh -= 11; bits = 11; } else { bits = sh; sh = 0; }       // 53, 42, 31, 20, 9, then the last 9 bits
+    }
+    // prefix = the boundary key's bits from `sh` up; candidates: (k >> sh) < prefix, plus the boundary bucket itself
+    // (all of it, or - equal keys - its nn - below smallest indices)
+    __syncthreads();
+    const int take = nn - below;       // entries wanted from the boundary bucket (equal_tail only)
+    int rank_eq = 0;
+    if (equal_tail) {
+        u32 *cnt = hist;               // [T + 1] <= 2049: the histogram is dead
+        const int per = (n + T - 1) / T;
+        int c = 0;
+        for (int e = 0; e < per; e++) { const int i = tid * per + e; if (i < n && ordered_key(src[i]) == prefix) c++; }
+        cnt[tid] = (u32)c;
+        if (tid == 0) cnt[T] = 0;
+        __syncthreads();
+        block_excl_scan(cnt, T + 1, wt);
+        rank_eq = (int)cnt[tid];
+        upto = below + take;
+        __syncthreads();
+    }
+    if (tid == 0) misc[7] = 0;
+    for (int p = upto + tid; p < CAP; p += T) { ckey[p] = ~0ull; idx[p] = (u16)0xffff; }
+    __syncthreads();
+    if (!equal_tail) {
+        for (int base = 0; base < n; base += T) {
+            const int i = base + tid;
+            u64 k = 0; bool cand = false;
+            if (i < n) { k = ordered_key(src[i]); cand = (k >> sh) <= prefix; }
+            const u32 bal = __ballot_sync(FULLMASK, cand);
+            int pb = 0;
+            if (lane == 0 && bal) pb = atomicAdd(&misc[7], __popc(bal));
+            pb = __shfl_sync(FULLMASK, pb, 0);
+            if (cand) { const int pos = pb + __popc(bal & ((1u << lane) - 1)); ckey[pos] = k; idx[pos] = (u16)i; }
+        }
+    } else {
+        const int per = (n + T - 1) / T;
+        for (int e = 0; e < per; e++) {
+            const int i = tid * per + e;
+            if (i >= n) break;
+            const u64 k = ordered_key(src[i]);
+            bool cand = k < prefix;
+            if (k == prefix) { cand = rank_eq < take; rank_eq++; }
+            if (cand) { const int pos = atomicAdd(&misc[7], 1); ckey[pos] = k; idx[pos] = (u16)i; }
+        }
+    }
+    __syncthreads();
+    for (int k = 2; k <= CAP; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (CAP >> 1); t += T) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
+                const bool asc = ((lo & k) == 0);
+                const u64 a = ckey[lo], b = ckey[hi];
+                const u16 ia = idx[lo], ib = idx[hi];
+                const bool gt = (b < a) || (b == a && ib < ia);
+                if (gt == asc) { ckey[lo] = b; ckey[hi] = a; idx[lo] = ib; idx[hi] = ia; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------------------------
 // branch-path context (all pointers into shared memory)
 // ----------------------------------------------------------------------------------------------

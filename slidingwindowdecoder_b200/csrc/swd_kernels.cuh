@@ -203,7 +203,9 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
 // K2: sort + reset
 // ----------------------------------------------------------------------------------------------
 struct SortSmem { int off_key, off_idx, off_posof, off_blob, off_u32a, off_u32b, off_u32c, off_wt, off_error, off_misc, off_bins, total; int np2;
-                  int cap_sel; };     // > 0: select + sort the cap_sel smallest keys instead of sorting all n
+                  int cap_sel;        // > 0: select + sort the cap_sel smallest keys instead of sorting all n
+                  int big;            // n beyond the register sort: block_select_sort_big only (key / idx hold cap_sel entries)
+                  int key_bytes; };
 
 __global__ void __launch_bounds__(1024, 1)
 sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayout L, GdgDev P, SortSmem S,
@@ -244,7 +246,8 @@ sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayo
         const int shot = ws.gdg_list[slot];
         const double inf = __longlong_as_double(0x7ff0000000000000LL);
         bool partial = false;                                       // only idx[0..nn) is ordered, posof = 0xffff for the rest
-        if (S.cap_sel > 0 && NP2 == 8 * T)
+        if (S.big) { block_select_sort_big(key, idx, wt, misc, ws.sum + (size_t)slot * n, n, nn, S.cap_sel); partial = true; }
+        else if (S.cap_sel > 0 && NP2 == 8 * T)
             partial = block_select_sort<8>(key, idx, wt, misc, ws.sum + (size_t)slot * n, n, nn, S.cap_sel);
         if (partial) {
             for (int cI = tid; cI < n; cI += T) posof[cI] = (u16)0xffff;
@@ -314,7 +317,7 @@ sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayo
         // message slot of every kept edge: the row pass notes the slot under the edge's CSR position (in the `key` area,
         // dead after the sort), the column pass picks it up through the static CSC -> CSR map
         u16 *slot_of = (u16 *)key;
-        const bool via_table = (2 * g.nnz <= 8 * NP2);
+        const bool via_table = (2 * g.nnz <= S.key_bytes);
         for (int r = tid; r < m; r += T) {
             const int q = crank[r];
             int p = (int)uc[q];
@@ -338,34 +341,49 @@ sort_reset_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayo
             __syncthreads();
         }
 
-        if (P.kind == SWD_KIND_OSD_WINDOW) {
-            if (bad && partial) {
-                // the failure position below needs the order of the dropped columns as well (rare): sort everything after all
-                block_bitonic_sort_regs<8>(key, idx, NP2, ws.sum + (size_t)slot * n, n);
-                for (int j = tid; j < n; j += T) posof[idx[j]] = (u16)j;
-                partial = false;
-                __syncthreads();
+        int status = 0;
+        if (P.kind == SWD_KIND_OSD_WINDOW && bad) {
+            // osd_window.pyx:178-181: decimating the dropped columns in sorted order hits a check whose every VN is dropped
+            // while its syndrome bit is 1; the failure is at the last column of that check in the scan order, and the
+            // dropped columns up to there have been set to 0.  The scan order is the stable (key, index) order, so no
+            // ranks are needed: M_r = the largest (key, index) pair of bad row r, F = the smallest M_r, and a dropped
+            // column was reached iff its pair is <= F.  (Before the dropped columns' keys are overwritten below.)
+            const double *ksrc = ws.sum + (size_t)slot * n;
+            u64 *fkey = (u64 *)wt;
+            if (tid == 0) { *fkey = ~0ull; misc[0] = 0x7fffffff; }
+            __syncthreads();
+            u64 mk = 0; int mi = -1;
+            for (int r = tid; r < m; r += T) {          // at most one bad row per thread matters: keep the smallest M_r
+                if (ub[r] == 0 && s_synd[r]) {
+                    u64 rk = 0; int ri = -1;
+                    for (int q = g.rp[r]; q < g.rp[r + 1]; q++) {
+                        const int cI = g.rc[q]; const u64 kk = ordered_key(ksrc[cI]);
+                        if (ri < 0 || kk > rk || (kk == rk && cI > ri)) { rk = kk; ri = cI; }
+                    }
+                    if (ri >= 0 && (mi < 0 || rk < mk || (rk == mk && ri < mi))) { mk = rk; mi = ri; }
+                }
             }
+            if (mi >= 0) atomicMin(fkey, mk);
+            __syncthreads();
+            const u64 fk = *fkey;
+            if (mi >= 0 && mk == fk) atomicMin(&misc[0], mi);
+            __syncthreads();
+            const int fi = misc[0];
+            for (int cI = tid; cI < n; cI += T) {
+                if (posof[cI] >= nn) {
+                    const u64 kk = ordered_key(ksrc[cI]);
+                    if (kk < fk || (kk == fk && cI <= fi)) dec_out[(size_t)shot * n + cI] = 0;
+                }
+            }
+            status = -2;
+            __syncthreads();
+        }
+        if (P.kind == SWD_KIND_OSD_WINDOW) {
             // decided-0 key of the dropped columns (osd_window.pyx:208-209)
             if (partial) { for (int cI = tid; cI < n; cI += T) if (posof[cI] >= nn) ws.sum[(size_t)slot * n + cI] = 1000.0; }
             else for (int j = nn + tid; j < n; j += T) ws.sum[(size_t)slot * n + idx[j]] = 1000.0;
         }
-        int status = 0;
-        if (P.kind == SWD_KIND_OSD_WINDOW && bad) {
-            // osd_window.pyx:178-181: decimating the dropped columns in sorted order hits a check whose
-            // every VN is dropped while its syndrome bit is 1; failure at the last of them in scan order.
-            for (int r = tid; r < m; r += T) {
-                if (ub[r] == 0 && s_synd[r]) {
-                    int last = -1;
-                    for (int q = g.rp[r]; q < g.rp[r + 1]; q++) last = max(last, (int)posof[g.rc[q]]);
-                    atomicMin(&misc[0], last);
-                }
-            }
-            __syncthreads();
-            const int failpos = misc[0];
-            for (int j = nn + tid; j <= failpos && j < n; j += T) dec_out[(size_t)shot * n + idx[j]] = 0;
-            status = -2;
-        } else {
+        if (status == 0) {
             if (partial) { for (int cI = tid; cI < n; cI += T) if (posof[cI] >= nn) dec_out[(size_t)shot * n + cI] = 0; }
             else for (int j = nn + tid; j < n; j += T) dec_out[(size_t)shot * n + idx[j]] = 0;   // pyx:250-251 / :270-271
             Ctx c;

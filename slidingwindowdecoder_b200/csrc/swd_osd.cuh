@@ -8,6 +8,7 @@
 // extra column, so OSD-0 is read off directly; every higher-order candidate is y0 ^ v_t1 ^ v_t2 ...
 // and its path metric is an ordered fp64 sum (ascending column index, as the reference).
 #pragma once
+#include <stdlib.h>
 #include "swd_kernels.cuh"
 
 #define SWD_OSD_0  0
@@ -18,6 +19,8 @@ struct OsdSmem {
     int np2, W64, k;
     int off_key, off_idx, off_tcol, off_vt, off_colinfo, off_ent, off_vbuf, off_piv, off_scan, off_wt, off_red, off_misc, off_ybest, off_pend, off_prow;
     int total;
+    int big;                    // T does not fit next to the sort keys: key aliases tcol, vt / scan live in a per-CTA HBM scratch
+    long long big_stride;       // bytes of that scratch per CTA
 };
 
 struct OsdWork {
@@ -28,6 +31,7 @@ struct OsdWork {
     long long out_cap = 0;
     // per-chunk scratch (inside the workspace block)
     u8 *need_osd = nullptr;         // [cap] 1 if slot must run OSD
+    u8 *big_scratch = nullptr;      // [grid5][big_stride] (OsdSmem::big)
 };
 
 static inline size_t osd_bytes_per_shot(int m, int n) { return 2; }   // need_osd[cap] + in_list[cap]
@@ -46,6 +50,7 @@ static inline int osd_reserve_outputs(OsdWork *ow, long long B, int n) {
     return 0;
 }
 static inline void osd_free_outputs(OsdWork *ow) {
+    if (ow->big_scratch) { cudaFree(ow->big_scratch); ow->big_scratch = nullptr; }
     if (ow->bp_dec) { cudaFree(ow->bp_dec); cudaFree(ow->osd0); cudaFree(ow->osdw); cudaFree(ow->lpr); cudaFree(ow->bp_iter); ow->bp_dec = nullptr; }
 }
 
@@ -185,11 +190,11 @@ osd_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayout L, G
     double *key = (double *)(smem + S.off_key);
     u16 *idx = (u16 *)(smem + S.off_idx);               // after the sort: scan order of the columns
     u64 *tcol = (u64 *)(smem + S.off_tcol);             // [(m+1)][W64]; column m carries T*syndrome
-    u64 *vt = (u64 *)(smem + S.off_vt);                 // [k][W64] reduced non-pivot columns
+    u64 *vt = S.big ? (u64 *)(ow.big_scratch + (size_t)blockIdx.x * S.big_stride) : (u64 *)(smem + S.off_vt);   // [k][W64] reduced non-pivot columns
     u16 *colinfo = (u16 *)(smem + S.off_colinfo);       // per column: 0xffff none | pivot row | 0x8000 + T index
     u32 *ent = (u32 *)(smem + S.off_ent);               // [nn'] (col << 16 | info), ascending col
     u64 *pivmask = (u64 *)(smem + S.off_piv);           // [W64]
-    u32 *scan = (u32 *)(smem + S.off_scan);             // [n+1]
+    u32 *scan = S.big ? (u32 *)(ow.big_scratch + (size_t)blockIdx.x * S.big_stride + (size_t)S.off_scan) : (u32 *)(smem + S.off_scan);   // [n+1]
     u32 *wt = (u32 *)(smem + S.off_wt);
     double *red_d = (double *)(smem + S.off_red); int *red_i = (int *)(red_d + 64);
     int *misc = (int *)(smem + S.off_misc);
@@ -219,16 +224,25 @@ osd_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayout L, G
                 idx[i] = (i < n) ? (u16)i : (u16)0xffff;
             }
         }
-        for (int i = tid; i < (m + 1) * W64; i += T) tcol[i] = 0;
-        for (int i = tid; i < n; i += T) colinfo[i] = 0xffff;
-        for (int i = tid; i < W64; i += T) pivmask[i] = 0;
-        __syncthreads();
-        for (int r = tid; r < m; r += T) {
-            tcol[r * W64 + (r >> 6)] = 1ull << (r & 63);
-            if (synd[(size_t)shot * m + r]) atomicOr(&tcol[m * W64 + (r >> 6)], 1ull << (r & 63));
+        // big: the sort keys alias T, so T is set up after the sort
+        for (int pass = 0; pass < 2; pass++) {
+            if ((pass == 0) == (S.big == 0)) {
+                if (S.big) __syncthreads();
+                for (int i = tid; i < (m + 1) * W64; i += T) tcol[i] = 0;
+                for (int i = tid; i < n; i += T) colinfo[i] = 0xffff;
+                for (int i = tid; i < W64; i += T) pivmask[i] = 0;
+                __syncthreads();
+                for (int r = tid; r < m; r += T) {
+                    tcol[r * W64 + (r >> 6)] = 1ull << (r & 63);
+                    if (synd[(size_t)shot * m + r]) atomicOr(&tcol[m * W64 + (r >> 6)], 1ull << (r & 63));
+                }
+            }
+            if (pass == 0) {
+                if (S.big) __syncthreads();
+                if (regsort) block_bitonic_sort_regs<8>(key, idx, NP2, ws.sum + (size_t)slot * n, n);
+                else block_bitonic_sort(key, idx, NP2);
+            }
         }
-        if (regsort) block_bitonic_sort_regs<8>(key, idx, NP2, ws.sum + (size_t)slot * n, n);
-        else block_bitonic_sort(key, idx, NP2);
         if (tid == 0) { misc[0] = 0; }
         __syncthreads();
         // ---- greedy independent columns in scan order, Gauss-Jordan on T (mod2sparse_extra.cpp:113-376).
@@ -513,8 +527,32 @@ static inline int osd_setup(int m, int n, int nn, int rank, int method, int orde
     S->off_pend = o; o += 8 * 32 * S->W64; o = osd_r16(o);
     S->off_prow = o; o += 4 * 32; o = osd_r16(o);
     S->total = o;
+    S->big = 0; S->big_stride = 0;
     if (S->W64 > 32) return -2;                          // one word of a T column per lane of the scanning warp
-    if (S->total > 227 * 1024) return -2;
+    if (S->total > 227 * 1024 || getenv("SWD_FORCE_BIG_OSD")) {
+        // large window: key[] (dead after the sort) aliases T, the reduced flippable columns and the scan array go to HBM
+        S->big = 1;
+        const int ta = 8 * (m + 1) * S->W64, ka = 8 * np2;
+        o = 0;
+        S->off_key = 0; S->off_tcol = 0; o = osd_r16(ta > ka ? ta : ka);
+        S->off_idx = o; o += 2 * np2; o = osd_r16(o);
+        S->off_colinfo = o; o += 2 * n; o = osd_r16(o);
+        S->off_ent = o; o += 4 * (nn + rank + 1); o = osd_r16(o);
+        S->off_vbuf = o; o += 8 * S->W64; o = osd_r16(o);
+        S->off_piv = o; o += 8 * S->W64; o = osd_r16(o);
+        S->off_wt = o; o += 4 * 64;
+        S->off_red = o; o += 64 * 8 + 64 * 4; o = osd_r16(o);
+        S->off_misc = o; o += 64;
+        S->off_ybest = o; o += 8 * S->W64; o = osd_r16(o);
+        S->off_pend = o; o += 8 * 32 * S->W64; o = osd_r16(o);
+        S->off_prow = o; o += 4 * 32; o = osd_r16(o);
+        S->total = o;
+        long long q = (long long)8 * (S->k > 0 ? S->k : 1) * S->W64; q = (q + 255) & ~255ll;
+        S->off_vt = 0; S->off_scan = (int)q;               // offsets inside the per-CTA HBM scratch
+        q += (long long)4 * (n + 1); q = (q + 255) & ~255ll;
+        S->big_stride = q;
+        if (S->total > 227 * 1024) return -2;
+    }
     int t = ((m + 1 + 31) / 32) * 32; if (t < 128) t = 128; if (t > 1024) t = 1024;
     if (np2 / 8 >= t && np2 / 8 <= 1024) t = np2 / 8;     // 8 sort keys per thread in registers; more warps for the block scan
     *T5 = t;

@@ -34,9 +34,13 @@ def load_golden(name):
 GOLDEN_GDG = ["c1_gdg_sim_mt1", "c1_gdg_default_mt1", "c1_gdg_sim_mt0", "c1_gdg_default_mt0",
               "c2_w0_gdg_mt1", "c2_w1_gdg_mt1", "c2_w4_gdg_mt1", "c2_w0_gdg_mt0", "c2_w1_gdg_mt0", "c2_w4_gdg_mt0",
               "c3_w0_gdg_mt1", "c3_w5_gdg_mt1", "c3_w10_gdg_mt1",
-              "c5_w0_gdg_mt0", "c5_w4_gdg_mt0", "c5_w0_gdg_mt1", "c5_w4_gdg_mt1", "c4_w7_gdg_mt1"]
+              "c5_w0_gdg_mt0", "c5_w4_gdg_mt0", "c5_w0_gdg_mt1", "c5_w4_gdg_mt1", "c4_w7_gdg_mt1",
+              "c3_w5_gdg_mt0",            # headline window, single-thread schedule
+              "g144_gdg_mt1"]             # un-windowed [[144,12,12]] DEM (936 x 8784): HBM-streamed BP on the GPU
 GOLDEN_OSD = ["c1_osdw_osd_00", "c1_osdw_osd_cs10", "c1_osdw_osd_e6", "c2_w0_osdw_cs10", "c2_w1_osdw_cs10",
-              "c2_w4_osdw_cs10", "c3_w5_osdw_cs10", "c5_w0_osdw_cs10", "c5_w4_osdw_cs10", "c4_w7_osdw_cs10"]
+              "c2_w4_osdw_cs10", "c3_w5_osdw_cs10", "c5_w0_osdw_cs10", "c5_w4_osdw_cs10", "c4_w7_osdw_cs10",
+              "g144_osdw_cs10"]           # IBM.ipynb:122-123 (pre 16, post 1000, osd_cs 10) on the un-windowed [[144,12,12]] DEM
+GOLDEN_BPGD = ["c1_bpgd", "c3_w5_bpgd"]
 
 
 GOLDEN_BP4 = ["c1_bp4_osd_00", "c1_bp4_osd_cs8", "c1_bp4_osd_e5"]

@@ -56,7 +56,7 @@ def run_gdg(cls, mat, priors, synd, kwargs):
     return np.packbits(out, axis=1), conv
 
 
-def run_osd(cls, mat, priors, synd, kwargs):
+def run_osd(cls, mat, priors, synd, kwargs, nlpr=8):
     dec = cls(mat, channel_probs=priors, **kwargs)
     n = mat.shape[1]
     out = np.zeros((len(synd), n), dtype=np.uint8); bp = np.zeros_like(out); o0 = np.zeros_like(out)
@@ -69,7 +69,7 @@ def run_osd(cls, mat, priors, synd, kwargs):
             o0[i] = dec.osd0_decoding
         lpr[i] = dec.log_prob_ratios
     return dict(dec=np.packbits(out, axis=1), conv=conv, min_pm=pm, bp_iteration=it, bp_decoding=np.packbits(bp, axis=1),
-                osd0=np.packbits(o0, axis=1), lpr_first8=lpr[:8])
+                osd0=np.packbits(o0, axis=1), lpr_first8=lpr[:nlpr])
 
 
 def shyps_section(bpgdg_decoder, osd_window):
@@ -113,6 +113,45 @@ def c4_section(bpgdg_decoder, osd_window):
     kw = dict(max_iter=8, multi_thread=True)
     d, c = run_gdg(bpgdg_decoder, w.mat, w.prior, s[:80], kw)
     save("c4_w7_gdg_mt1", w.mat, w.prior, s[:80], kw, dec=d, conv=c)
+
+
+def global144_section(bpgdg_decoder, osd_window, bpgd_decoder):
+    """The un-windowed [[144,12,12]] DEM of IBM.ipynb cell 2 (936 x 8784, 30672 edges, p = 0.004, 12 rounds): its messages
+    exceed one SM's shared memory, so the product decodes it with the HBM-streamed BP kernel.
+    osd_window with the notebook's kwargs (IBM.ipynb:122-123: pre 16, post 1000, osd_cs 10) and multi-thread GDG."""
+    from slidingwindowdecoder_b200.codes import bb_code
+    from slidingwindowdecoder_b200.dem import bb_memory_circuit, detector_error_model, dem_to_check_matrices
+    from slidingwindowdecoder_b200.sliding_window import sample_dem
+    code, A, B = bb_code(144)
+    chk, obs, pri = dem_to_check_matrices(detector_error_model(bb_memory_circuit(code, A, B, 0.004, 12, z_basis=True)))
+    det, ob, _ = sample_dem(chk, obs, pri, 64, np.random.default_rng(936))
+    s = det[np.nonzero(det.any(axis=1))[0][:40]]
+    kw = dict(pre_max_iter=16, post_max_iter=1000, ms_scaling_factor=1.0, osd_method="osd_cs", osd_order=10)
+    save("g144_osdw_cs10", chk, pri, s, kw, **run_osd(osd_window, chk, pri, s, kw, nlpr=2))
+    kw = dict(max_iter=16, multi_thread=True)
+    d, c = run_gdg(bpgdg_decoder, chk, pri, s[:24], kw)
+    save("g144_gdg_mt1", chk, pri, s[:24], kw, dec=d, conv=c)
+
+
+def c3_extra_section(bpgdg_decoder, bpgd_decoder):
+    """More of the headline configuration's middle window (216 x 1728): single-thread GDG schedule and BPGD."""
+    from slidingwindowdecoder_b200.codes import bb_code
+    from slidingwindowdecoder_b200.dem import bb_memory_circuit, detector_error_model, dem_to_check_matrices
+    from slidingwindowdecoder_b200.windows import build_windows
+    from slidingwindowdecoder_b200.sliding_window import sample_dem
+    code, A, B = bb_code(144)
+    chk, obs, pri = dem_to_check_matrices(detector_error_model(bb_memory_circuit(code, A, B, 0.003, 12, z_basis=True)))
+    plan = build_windows(chk, obs, pri, code.N, W=3, F=1, method=1)
+    det, ob, _ = sample_dem(plan.chk, plan.obs, plan.priors, 1500, np.random.default_rng(144))
+    w = plan.windows[5]
+    s = det[:, w.row0:w.row1]
+    s = s[np.nonzero(s.any(axis=1))[0][:400]]
+    kw = dict(max_iter=8, multi_thread=False)
+    d, c = run_gdg(bpgdg_decoder, w.mat, w.prior, s, kw)
+    save("c3_w5_gdg_mt0", w.mat, w.prior, s, kw, dec=d, conv=c)
+    kw = dict(max_iter=8, ms_scaling_factor=1.0, max_iter_per_step=6, max_step=25, gd_factor=1.0)
+    d, c = run_gdg(bpgd_decoder, w.mat, w.prior, s, kw)
+    save("c3_w5_bpgd", w.mat, w.prior, s, kw, dec=d, conv=c)
 
 
 def bp4_section():
@@ -194,6 +233,13 @@ def main():
         from src.bp_guessing_decoder import bpgdg_decoder
         from src.osd_window import osd_window
         c4_section(bpgdg_decoder, osd_window)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] in ("g144", "c3x"):
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 2)
+        from src.bp_guessing_decoder import bpgdg_decoder, bpgd_decoder
+        from src.osd_window import osd_window
+        global144_section(bpgdg_decoder, osd_window, bpgd_decoder) if sys.argv[1] == "g144" else c3_extra_section(bpgdg_decoder, bpgd_decoder)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "shyps":
         devnull = os.open(os.devnull, os.O_WRONLY)
@@ -279,6 +325,8 @@ def main():
     save("c3_w5_osdw_cs10", w.mat, w.prior, s, kw, **run_osd(osd_window, w.mat, w.prior, s, kw))
     shyps_section(bpgdg_decoder, osd_window)
     c4_section(bpgdg_decoder, osd_window)
+    c3_extra_section(bpgdg_decoder, bpgd_decoder)
+    global144_section(bpgdg_decoder, osd_window, bpgd_decoder)
     bp4_section()
     camel_section()
 

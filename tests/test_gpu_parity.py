@@ -41,9 +41,10 @@ def test_gdg_single_thread_matches_golden(name, oracle_mod):
     assert len(bad) == 0, f"shots {bad[:10]}"
 
 
-def test_bpgd_matches_oracle_and_golden(oracle_mod):
+@pytest.mark.parametrize("name", __import__("conftest").GOLDEN_BPGD)
+def test_bpgd_matches_oracle_and_golden(name, oracle_mod):
     from slidingwindowdecoder_b200 import bpgd_decoder
-    g = load_golden("c1_bpgd")
+    g = load_golden(name)
     dec = bpgd_decoder(g["mat"], channel_probs=g["priors"], **g["kwargs"])
     corr, conv = dec.decode_batch(g["synd"])
     assert np.array_equal(conv, g["conv"])
@@ -161,7 +162,7 @@ def test_osd_window_bit_exact(name, oracle_mod):
     assert ran_osd.any()
     assert np.array_equal(out["osd0_decoding"][ran_osd], g["osd0"][ran_osd])
     assert dec.counters()["osd_shots"] == int(ran_osd.sum())
-    for i in range(min(8, len(corr))):
+    for i in range(min(len(g["lpr_first8"]), len(corr))):
         if g["bp_iteration"][i] >= 4:
             assert np.array_equal(out["log_prob_ratios"][i], g["lpr_first8"][i]), i
 
@@ -639,13 +640,18 @@ def test_bp4_camel_decode_matches_golden(name, oracle_mod):
     assert agree >= 63, agree
 
 
+@pytest.mark.parametrize("big", [False, True])
 @pytest.mark.parametrize("kind", ["gdg_mt", "bpgd"])
-def test_sort_select_with_many_equal_keys(kind, oracle_mod):
+def test_sort_select_with_many_equal_keys(kind, big, oracle_mod, monkeypatch):
     """sort_reset_kernel on a [[144,12,12]] window (n = 1728, new_n = 432): the GDG kinds radix-select the new_n smallest
     keys and sort only those; with uniform priors many columns have exactly equal posterior sums, so boundary buckets get
     crowded (ties must stay together, the crowded case falls back to the full stable argsort) - the result has to equal
-    the reference's std::stable_sort order either way: corrections bit-exact vs the oracle."""
+    the reference's std::stable_sort order either way: corrections bit-exact vs the oracle.
+    big: the selection used for n > 8192 (keys re-read from HBM, radix descent over all 64 key bits, equal keys ranked by
+    index - no full-sort fall-back), forced on this window."""
     from slidingwindowdecoder_b200 import bpgdg_decoder, bpgd_decoder
+    if big:
+        monkeypatch.setenv("SWD_FORCE_BIG_SORT", "1")
     g = load_golden("c3_w5_gdg_mt1")
     n = g["mat"].shape[1]
     rng = np.random.default_rng(77)
@@ -667,13 +673,16 @@ def test_sort_select_with_many_equal_keys(kind, oracle_mod):
         assert np.array_equal(corr, np.asarray(o_dec).astype(np.uint8))
 
 
-def test_osd_window_reset_failure_on_large_window(oracle_mod):
+@pytest.mark.parametrize("big", [False, True])
+def test_osd_window_reset_failure_on_large_window(big, oracle_mod, monkeypatch):
     """osd_window on a [[144,12,12]] window takes the radix-select path of sort_reset_kernel, which orders only the kept
     columns; when decimating the dropped columns hits a check whose every column is dropped while its syndrome bit is 1
     (osd_window.pyx:178-181) the failure position needs the order of the dropped columns too and the kernel sorts
     everything after all.  Forced here: the columns of one check get a 1e-12 prior, its syndrome bit is set and a small
     scaling factor keeps their posteriors large.  Bit-exact vs the oracle (corrections, flags, BP decisions)."""
     from slidingwindowdecoder_b200 import osd_window
+    if big:
+        monkeypatch.setenv("SWD_FORCE_BIG_SORT", "1")
     g = load_golden("c3_w5_osdw_cs10")
     H = np.asarray(g["mat"].todense()) if hasattr(g["mat"], "todense") else np.asarray(g["mat"])
     pri = np.array(g["priors"], dtype=np.float64).copy()
@@ -690,6 +699,52 @@ def test_osd_window_reset_failure_on_large_window(oracle_mod):
     assert np.array_equal(corr, np.asarray(o_dec).astype(np.uint8))
     per = [orc.osd_window(x, **kw) for x in synd]
     assert np.array_equal(dec.last_outputs()["bp_decoding"], np.array([r["bp_decoding"] for r in per]).astype(np.uint8))
+
+
+@pytest.mark.parametrize("force", ["SWD_FORCE_STREAM", "SWD_FORCE_BIG_OSD"])
+@pytest.mark.parametrize("name", ["c3_w5_gdg_mt1", "c3_w5_osdw_cs10", "c5_w4_osdw_cs10"])
+def test_streamed_bp_equals_shared_memory_bp(name, force, monkeypatch):
+    """The HBM-streamed full-window BP (swd_stream.cuh: one thread per shot, shot-interleaved messages; what graphs beyond
+    one SM's shared memory run) forced on windows that also fit the shared-memory kernel: corrections, flags, path metrics,
+    BP decisions, iteration counts and the posterior history must be bit-identical, and equal to the reference's goldens.
+    SWD_FORCE_BIG_OSD: the same for osd_kernel's large-window layout (sort keys alias T, reduced columns / scan array in HBM)."""
+    from slidingwindowdecoder_b200 import bpgdg_decoder, osd_window
+    g = load_golden(name)
+    cls = osd_window if "osdw" in name else bpgdg_decoder
+    a = cls(g["mat"], channel_probs=g["priors"], **g["kwargs"])
+    ra = a.decode_batch(g["synd"], return_pm=True)
+    oa = a.last_outputs() if cls is osd_window else None
+    if force == "SWD_FORCE_BIG_OSD" and "osdw" not in name:
+        pytest.skip("OSD layout only")
+    monkeypatch.setenv(force, "1")
+    b = cls(g["mat"], channel_probs=g["priors"], **g["kwargs"])
+    rb = b.decode_batch(g["synd"], return_pm=True)
+    for x, y in zip(ra, rb):
+        assert np.array_equal(x, y)
+    assert np.array_equal(rb[1], g["conv"])
+    if oa is not None:
+        ob = b.last_outputs()
+        for k in oa:
+            assert np.array_equal(oa[k], ob[k]), k
+        assert np.array_equal(rb[0], g["dec"])
+    assert b.counters()["pre_bp_edge_iters"] == a.counters()["pre_bp_edge_iters"]
+
+
+def test_unwindowed_144_limits_lifted():
+    """the un-windowed [[144,12,12]] DEM (936 x 8784, 30672 edges; IBM.ipynb:122-123) used to be rejected with
+    SWD_ERR_UNSUPPORTED because its messages exceed one SM's shared memory.  It now constructs for all three kinds and a
+    decode of trivial / weight-1 syndromes returns consistent corrections."""
+    from slidingwindowdecoder_b200 import bpgdg_decoder, bpgd_decoder, osd_window
+    g = load_golden("g144_osdw_cs10")
+    H = g["mat"].tocsc()
+    synd = np.zeros((3, H.shape[0]), dtype=np.uint8)
+    synd[1] = np.asarray(H[:, 100].todense()).ravel() % 2
+    synd[2] = np.asarray((H[:, 7] + H[:, 4000]).todense()).ravel() % 2
+    for dec in (osd_window(H, channel_probs=g["priors"], **g["kwargs"]), bpgdg_decoder(H, channel_probs=g["priors"], max_iter=16, multi_thread=True),
+                bpgd_decoder(H, channel_probs=g["priors"], max_iter=16)):
+        corr, conv = dec.decode_batch(synd)
+        assert conv.all()
+        assert not ((corr.astype(np.int64) @ H.T.toarray() + synd) % 2).any()
 
 
 def test_bp4_device_pointer_entry_points_match_host_calls():

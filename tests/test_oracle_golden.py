@@ -38,8 +38,9 @@ def test_gdg_matches_reference(name, oracle_mod):
     check_only_ties(g, orc, dec, conv, pm, bad, name)
 
 
-def test_bpgd_matches_reference(oracle_mod):
-    g = load_golden("c1_bpgd")
+@pytest.mark.parametrize("name", __import__("conftest").GOLDEN_BPGD)
+def test_bpgd_matches_reference(name, oracle_mod):
+    g = load_golden(name)
     orc = oracle_mod.Oracle(g["mat"], g["priors"])
     for i, s in enumerate(g["synd"]):
         dec, conv, pm, _ = orc.bpgd(s, **g["kwargs"])
@@ -63,7 +64,7 @@ def test_osd_window_matches_reference(name, oracle_mod):
         if i < 8 and not g["conv"][i] or (i < 8 and g["bp_iteration"][i] >= 4 and False):
             pass
     # posterior history: bit-exact where the reference's ring was fully rewritten by this decode
-    for i in range(min(8, len(g["synd"]))):
+    for i in range(min(len(g["lpr_first8"]), len(g["synd"]))):
         r = orc.osd_window(g["synd"][i], **g["kwargs"])
         if r["bp_iteration"] >= 4:
             assert np.array_equal(r["log_prob_ratios"], g["lpr_first8"][i]), i
