@@ -12,6 +12,7 @@ all-reduce of the failure counters.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -59,6 +60,12 @@ WORKLOADS = {
                    kw=dict(pre_max_iter=8, post_max_iter=100, osd_method="osd_cs", osd_order=10),
                    name="SHYPS r=3 memory experiment p=0.003, 6 rounds, sliding window W=3 F=1, BP+OSD-CS10 per window",
                    decoder_name="osd_window(pre_max_iter=8, post_max_iter=100, osd_cs, order 10)"),
+    # the un-windowed [[144,12,12]] DEM of IBM.ipynb cell 2 (936 x 8784, 30672 edges): messages exceed one SM's shared memory, the
+    # full-window BP runs HBM-streamed (swd_stream.cuh); decoder kwargs of IBM.ipynb:122-123
+    "g144_osd": dict(code="global", N=144, p=0.004, rounds=12, decoder="osd",
+                     kw=dict(pre_max_iter=16, post_max_iter=1000, osd_method="osd_cs", osd_order=10),
+                     name="[[144,12,12]] circuit-level p=0.004, 12 rounds, un-windowed DEM 936 x 8784 (IBM.ipynb), BP+OSD-CS10 on the whole DEM",
+                     decoder_name="osd_window(pre_max_iter=16, post_max_iter=1000, osd_cs, order 10)"),
 }
 WL = WORKLOADS["c3_gdg"]
 METRIC = {"gdg": "decoded shots/sec (sliding-window GDG)", "osd": "decoded shots/sec (sliding-window BP+OSD)"}
@@ -89,6 +96,12 @@ def build_plan():
     code, A, B = bb_code(WL["N"])
     circ = bb_memory_circuit(code, A, B, WL["p"], WL["rounds"], z_basis=True)
     chk, obs, pri = dem_to_check_matrices(detector_error_model(circ))
+    if WL.get("code") == "global":          # one "window" = the whole DEM, every column committed
+        from scipy.sparse import csc_matrix
+        from slidingwindowdecoder_b200.windows import WindowPlan, Window
+        chk, obs = csc_matrix(chk), csc_matrix(obs)
+        win = Window(0, chk, pri, 0, chk.shape[0], 0, chk.shape[1], chk.shape[1], True)
+        return WindowPlan(chk, obs, pri, [(0, 0), chk.shape], [win], code.N // 2, 1, 1)
     return build_windows(chk, obs, pri, code.N, W=WL["W"], F=WL["F"], method=WL["method"])
 
 
@@ -186,11 +199,82 @@ class CpuArm:
         self.pool.join()
 
 
-def calibrate_cpu_sample(arm, plan, target_s):
-    det, obs = sample_host(plan, arm.cores * 4, 999)
-    dt, _, _ = arm.run(det, obs)
-    rate = det.shape[0] / max(dt, 1e-6)
-    return int(max(arm.cores * 4, min(20000, rate * target_s)))
+def _quiet_stderr():
+    """the reference prints "Error setting thread affinity" per thread on hosts with < 15 cores"""
+    class _Q:
+        def __enter__(self):
+            self.devnull = os.open(os.devnull, os.O_WRONLY); self.saved = os.dup(2); os.dup2(self.devnull, 2)
+        def __exit__(self, *a):
+            os.dup2(self.saved, 2); os.close(self.devnull); os.close(self.saved)
+    return _Q()
+
+
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def _rate(arm, plan, shots, seed):
+    det, obs = sample_host(plan, shots, seed)
+    dt, fl, fa = arm.run(det, obs)
+    return shots / max(dt, 1e-9), dt, fa
+
+
+def cpu_reference_modes(plan, calib_s=3.0):
+    """Which way of running the reference's CPU implementation on this host is fastest ("all the host threads it can use"):
+      ref xP  : oracle/_ref = the reference's own bpgd.cpp / mod2sparse.c compiled in place (BPGD_main_thread::do_work, 15
+                std::threads per decode, as bpgdg_decoder(multi_thread=True) runs it), P processes over disjoint shot shards
+      port    : the C restatement (oracle/swd_oracle.c, gcc -O2), one process per core
+    -> (modes: {name: shots/s}, best real-reference (procs, rate) or None, port rate)."""
+    from oracle.oracle import ref_lib
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    modes, best = {}, None
+    if ref_lib() is not None and WL["decoder"] == "gdg":
+        with _quiet_stderr():
+            for P in sorted({1, max(1, cores // 8), max(1, cores // 4), max(1, cores // 2), cores}):
+                arm = CpuArm(plan, use_ref=True, procs=P)
+                r0, _, _ = _rate(arm, plan, max(8, 2 * P), 990 + P)                    # warm-up / first estimate
+                r, _, _ = _rate(arm, plan, int(max(4 * P, min(4000, r0 * calib_s))), 995 + P)
+                arm.close()
+                modes[f"ref_x{P}"] = round(r, 2)
+                if best is None or r > best[1]:
+                    best = (P, r)
+    arm = CpuArm(plan)
+    r0, _, _ = _rate(arm, plan, arm.cores * 4, 999)
+    rp, _, _ = _rate(arm, plan, int(max(arm.cores * 4, min(20000, r0 * calib_s))), 998)
+    arm.close()
+    modes["port_per_core"] = round(rp, 2)
+    return modes, best, rp, cores
+
+
+def cpu_baseline_block(plan, target_s):
+    """cpu_baseline of the contract: the reference's CPU path on this box's host cores, bounded sample (~target_s of work)."""
+    modes, best, rp, cores = cpu_reference_modes(plan)
+    if best is not None:
+        P, r = best
+        n = int(max(1000, min(50000, r * target_s)))
+        with _quiet_stderr():
+            arm = CpuArm(plan, use_ref=True, procs=P)
+            rate, dt, fa = _rate(arm, plan, n, 4321)
+            arm.close()
+        kind = "reference"
+        how = (f"{n} shots x {len(plan.windows)} windows through oracle/_ref (the reference's own bpgd.cpp + mod2sparse.c, g++ -O2; "
+               f"do_work with 15 std::threads per decode), {P} process(es) = the fastest of {modes}; {dt:.1f} s; failed {fa}/{n}")
+    else:
+        arm = CpuArm(plan)
+        n = int(max(arm.cores * 4, min(50000, rp * target_s)))
+        rate, dt, fa = _rate(arm, plan, n, 4321)
+        arm.close()
+        kind = "port"
+        how = (f"{n} shots x {len(plan.windows)} windows through the oracle port (C restatement of the reference, gcc -O2), one process "
+               f"per core; {dt:.1f} s; failed {fa}/{n}" + ("" if WL["decoder"] == "gdg" else " (oracle/_ref binds the GDG path only)"))
+    return {"value": round(rate, 2), "unit": "shots/s", "cores": cores, "kind": kind, "sample": how, "modes_shots_per_s": modes,
+            "port_per_core_shots_per_s": round(rp, 2), "cpu_model": _cpu_model(), "nproc": os.cpu_count(), "compiler_flags": "-O2 (as the reference's setup.py)"}
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -247,6 +331,12 @@ def gpu_sample(swd, shots, seed):
     return swd.sample_device(shots, seed=seed)
 
 
+def config_block(args):
+    """The workload the metric is quoted on - the same dict in the product arm and in the reference arm."""
+    return {"workload": WL["name"], "shots_per_step_per_gpu": args.batch, "decoder": WL["decoder_name"], "streams": args.streams,
+            "inputs": "synthetic DEM samples (independent Bernoulli per DEM column), a distinct batch per step; working set > L2, no L2 flush"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -285,10 +375,20 @@ def run_ours(args):
         return swd.decode_device(det, obs, streams=1)["counts"]
 
     def step_e2e(i):
-        det = h_det[i].to(dev, non_blocking=True); obs = h_obs[i].to(dev, non_blocking=True)
-        out = swd.decode_device(det, obs)
-        h_counts[i].copy_(out["counts"], non_blocking=True)
-        return out["counts"]
+        # the public host-buffer entry: pinned host syndromes in, python ints (flagged, failed) out - H2D, all windows, D2H
+        r = swd.decode(h_det[i], h_obs[i])
+        return torch.tensor([r["flagged"], r["failed"]], dtype=torch.int64, device=dev)
+
+    from slidingwindowdecoder_b200.decoders import pack_bits
+    wc = (swd.num_col + 63) // 64
+    h_detp = torch.from_numpy(pack_bits(h_det.view(-1, h_det.shape[2]).numpy()).view(np.int64)).view(nsteps, B, -1).pin_memory()
+    h_obsp = torch.from_numpy(pack_bits(h_obs.view(-1, h_obs.shape[2]).numpy()).view(np.int64)).view(nsteps, B, -1).pin_memory()
+    h_corrp = torch.empty((B, wc), dtype=torch.int64, pin_memory=True)
+
+    def step_e2e_corr(i):
+        # bit-packed host buffers in, bit-packed corrections (total_e_hat) + counts back to the host
+        r = swd.decode_packed(h_detp[i], h_obsp[i], return_corrections=True, pinned_out=h_corrp)
+        return torch.tensor([r["flagged"], r["failed"]], dtype=torch.int64, device=dev)
 
     def timed(fn, profile, K=K):
         for i in range(W):
@@ -322,6 +422,8 @@ def run_ours(args):
     ms_res, counts_res = timed(step_resident, False)
     ctr_timed = read_counters()
     ms_e2e, counts_e2e = timed(step_e2e, False)
+    ms_e2ec, counts_e2ec = timed(step_e2e_corr, False)
+    assert np.array_equal(counts_e2e, counts_res) and np.array_equal(counts_e2ec, counts_res), "e2e legs disagree with the resident leg"
     clocks = sampler.stop() if rank == 0 else None
     # per-kernel CUDA-event times + work counters for the roofline: same batches, one stream (with several streams
     # the kernels of different sub-batches overlap and their individual durations are not additive)
@@ -354,65 +456,105 @@ def run_ours(args):
     total_shots = world * B * K
     value = total_shots / (ms_res / 1e3)
     e2e = total_shots / (ms_e2e / 1e3)
-    # ---- roofline of the dominant kernel (path_kernel: GDG branch paths, both phases)
+    # ---- roofline: every message-passing kernel against the roof that binds it, peaks MEASURED on this
+    # pool's B200s: HBM copy bandwidth from MEASURED_PEAKS.json (driver-written), shared-memory LDS.64+STS.64 streaming
+    # and issue rate from profiles/onchip_peaks.json (tools/onchip_peak.cu at the path kernel's launch shape).
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
-        peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        hbm_peak = float(json.load(open(peaks_path))["hbm_gbs"]); hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
-        peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
+        hbm_peak = 6650.0; hbm_src = "fallback (B200_PROFILING.md)"
+    onchip = {}
+    op = os.path.join(ROOT, "profiles", "onchip_peaks.json")
+    if os.path.exists(op):
+        onchip = json.load(open(op))
+    shapes = {sh["threads"]: sh for sh in onchip.get("shapes", [])}
+    small, large = shapes.get(128, {}), shapes.get(1024, {})
+    smem_peak = float(small.get("smem_ld64_st64_gbs", 148 * 128 * 1.965))
+    smem_src = "measured (profiles/onchip_peaks.json: conflict-free LDS.64 + STS.64, 128-thread CTAs x 8 per SM)" if small else \
+               "datasheet (148 SMs x 128 B/clk x 1.965 GHz) - profiles/onchip_peaks.json missing"
+    issue_peak = float(small.get("issue_gwarp_inst_per_s", 148 * 4 * 1.965))
     gdg = WL["decoder"] == "gdg"
-    dom = ("path_main", "path_side", "path_trunk") if gdg else ("post_bp",)   # osd_window: masked min-sum on the shortened graph
-    path_ms = sum(ktimes.get(k, [0, 0])[0] for k in dom)
-    path_launches = sum(ktimes.get(k, [0, 0])[1] for k in dom)
-    # B_iter = 4 E w + 2 n_a w + (n_a + m_a)/8 with w = 8, summed over executed iterations
-    path_bytes = 32.0 * ctr["path_edge_iters"] + 16.0 * ctr["path_vn_iters"] + (ctr["path_vn_iters"] + ctr["path_cn_iters"]) / 8.0
-    pre_bytes = 32.0 * ctr["pre_bp_edge_iters"]
-    achieved = path_bytes / (path_ms / 1e3) / 1e9 if path_ms > 0 else 0.0
-    traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath)).get("path_kernel" if gdg else "osd_pipeline", {})
-        if tj.get("batch") == B:                 # the capture was taken at this batch size
-            traffic = int(tj["dram_bytes_per_launch_avg"]); traffic_src = tj.get("source")
+    n_win = len(plan.windows)
+    streamed = any(d.streamed_bp for d in decs)
     kernel_ms = {k: round(v[0], 3) for k, v in ktimes.items() if v[1]}
     tot_k = sum(kernel_ms.values()) or 1.0
-    roofline = {"kernel": "path_kernel (GDG branch paths: shared-prefix nodes + main/tree + side launches)" if gdg else
-                          "post_bp_kernel (masked min-sum on the shortened graph; the bit-packed GF(2) osd_kernel is timed separately in kernel_ms)",
-                "bound": "hbm", "achieved": round(achieved, 1),
-                "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": round(path_bytes / max(1, path_launches)),
-                "avg_launch_ms": round(path_ms / max(1, path_launches), 4), "launches": path_launches,
-                "share_of_kernel_time": round(path_ms / tot_k, 4),
-                "note": "messages are held in shared memory, so algorithmic message bytes/s is compared with the HBM "
-                        "roof only to show on-chip residency; see smem_achieved_gbs for the binding on-chip roof",
-                "smem": {"achieved": round(achieved, 1), "peak": round(148 * 128 * 1.965, 1), "unit": "GB/s",
-                         "frac": round(achieved / (148 * 128 * 1.965), 4),
-                         "note": "same algorithmic bytes against the shared-memory roof (148 SMs x 128 B/clk x 1.965 GHz)"},
-                "pre_bp_achieved_gbs": round(pre_bytes / (ktimes.get("pre_bp", [1e-9, 0])[0] / 1e3) / 1e9, 1) if ktimes.get("pre_bp", [0, 0])[0] else None,
-                "kernel_ms": kernel_ms, "kernel_ms_steps": Kp, "single_stream_ms_per_step": round(ms_prof / Kp, 3)}
-    # ---- CPU baseline on a bounded sample
-    if args.skip_cpu or world > 1:        # the CPU baseline is timed on rank 0 of the 1-GPU run only
-        cpu_baseline = None
+
+    def kt(*keys):
+        return sum(ktimes.get(k, [0, 0])[0] for k in keys), sum(ktimes.get(k, [0, 0])[1] for k in keys)
+
+    def block(name, bound, bytes_, ms, launches, peak, peak_src, extra=None):
+        ach = bytes_ / (ms / 1e3) / 1e9 if ms > 0 else 0.0
+        out = {"kernel": name, "bound": bound, "achieved": round(ach, 1), "peak": round(peak, 1), "unit": "GB/s",
+               "frac": round(ach / peak, 4) if peak else None, "peak_source": peak_src,
+               "algorithmic_bytes_per_launch": round(bytes_ / max(1, launches)), "avg_launch_ms": round(ms / max(1, launches), 4),
+               "launches": launches, "share_of_kernel_time": round(ms / tot_k, 4)}
+        out.update(extra or {})
+        return out
+
+    # B_iter = 4 E w + 2 n_a w + (n_a + m_a)/8 with w = 8, summed over executed iterations (device counters)
+    path_bytes = 32.0 * ctr["path_edge_iters"] + 16.0 * ctr["path_vn_iters"] + (ctr["path_vn_iters"] + ctr["path_cn_iters"]) / 8.0
+    path_ms, path_launches = kt("path_main", "path_side", "path_trunk") if gdg else kt("post_bp")
+    blocks = {}
+    live_slots = ctr["path_edge_iters"] / max(1, ctr.get("path_slot_iters", 0)) if ctr.get("path_slot_iters") else None
+    blocks["path" if gdg else "post_bp"] = block(
+        "path_kernel (GDG branch paths: shared-prefix nodes + main/tree + side launches)" if gdg else
+        "post_bp_kernel (masked min-sum on the shortened graph)", "smem", path_bytes, path_ms, path_launches, smem_peak, smem_src,
+        {"hbm_equivalent_frac": round(path_bytes / (path_ms / 1e3) / 1e9 / hbm_peak, 4) if path_ms else None,
+         "live_slot_fraction": round(live_slots, 4) if live_slots else None,
+         "note": "messages live in shared memory: algorithmic message bytes/s against the measured shared-memory streaming roof; "
+                 "hbm_equivalent_frac > 1 would be impossible for an HBM-streaming design; live_slot_fraction = active edges / "
+                 "message slots scanned by the check passes (the rest are decided-VN and pad slots)"})
+    pre_ms, pre_l = kt("pre_bp")
+    n_cols = float(np.mean([w.mat.shape[1] for w in plan.windows])); nnz_w = float(np.mean([w.mat.nnz for w in plan.windows]))
+    if streamed:
+        pre_bytes = ctr["pre_bp_edge_iters"] * (32.0 + 8.0 * n_cols / nnz_w)       # + one posterior per column and iteration
+        blocks["pre_bp"] = block("pre_bp_stream_kernel (HBM-streamed full-window min-sum, one thread per shot)", "hbm", pre_bytes, pre_ms,
+                                 pre_l, hbm_peak, hbm_src,
+                                 {"note": "32 B x edges x iterations (read + write in both passes) + 8 B x columns x iterations of posterior "
+                                          "history: what the kernel moves through HBM by construction"})
     else:
-        arm = CpuArm(plan)
-        nsample = calibrate_cpu_sample(arm, plan, 12.0)
-        cdet, cobs = sample_host(plan, nsample, 4321)
-        dt, cflag, cfail = arm.run(cdet, cobs)
-        arm.close()
-        cpu_baseline = {"value": round(nsample / dt, 2), "unit": "shots/s", "cores": arm.cores, "kind": "port",
-                        "sample": f"{nsample} shots x {len(plan.windows)} windows through the oracle port (C restatement, gcc -O2), "
-                                  f"one process per core, {dt:.1f} s; failed {cfail}/{nsample}"}
+        pre_bytes = 32.0 * ctr["pre_bp_edge_iters"]
+        blocks["pre_bp"] = block("pre_bp_kernel (full-window min-sum, messages in shared memory)", "smem", pre_bytes, pre_ms, pre_l, smem_peak, smem_src)
+    if not gdg:
+        osd_ms, osd_l = kt("osd")
+        mrows = float(np.mean([w.mat.shape[0] for w in plan.windows])); w64 = math.ceil(mrows / 64)
+        dbar = nnz_w / n_cols
+        # GF(2) elimination: every scanned column gathers its <= 6 rows of T (W64 words each); every pivot is folded into
+        # all m + 1 columns of T (read + write)
+        osd_bytes = 8.0 * w64 * (ctr.get("osd_cols_scanned", 0) * dbar + 2.0 * ctr.get("osd_pivots", 0) * (mrows + 1))
+        blocks["osd"] = block("osd_kernel (bit-packed GF(2) Gauss-Jordan + OSD-CS candidates)", "smem", osd_bytes, osd_ms, osd_l,
+                              float(large.get("smem_ld64_st64_gbs", smem_peak)), smem_src.replace("128-thread CTAs x 8", "one 1024-thread CTA"))
+    dom = max(blocks, key=lambda k: blocks[k]["share_of_kernel_time"])
+    traffic, traffic_src, ncu_facts = None, None, None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath)).get({"path": "path_kernel", "post_bp": "osd_pipeline", "pre_bp": "pre_bp_" + args.workload, "osd": "osd_kernel"}[dom], {})
+        if tj.get("batch") == B and tj.get("workload", "c3_gdg") == args.workload:   # the capture was taken on this workload at this batch size
+            traffic = int(tj["dram_bytes_per_launch_avg"]); traffic_src = tj.get("source"); ncu_facts = tj.get("ncu")
+    roofline = dict(blocks[dom])
+    roofline.update({"traffic": traffic, "traffic_source": traffic_src, "ncu": ncu_facts,
+                     "issue_peak_gwarp_inst_per_s": round(issue_peak, 1),
+                     "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
+                     "kernels": {k: v for k, v in blocks.items() if k != dom},
+                     "kernel_ms": kernel_ms, "kernel_ms_steps": Kp, "single_stream_ms_per_step": round(ms_prof / Kp, 3)})
+    # ---- CPU baseline on a bounded sample (rank 0, at every N)
+    cpu_baseline = None if args.skip_cpu else cpu_baseline_block(plan, 12.0)
     launches = ctr_timed["kernel_launches"] + K * args.streams * (2 * len(plan.windows) + 1)
     line = {
         "metric": METRIC[WL["decoder"]], "value": round(value, 1), "unit": "shots/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": round(ms_res / K, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WL["name"], "shots_per_step_per_gpu": B, "decoder": WL["decoder_name"],
-                   "streams": args.streams,
-                   "inputs": "DEM samples drawn on the device (Philox, independent Bernoulli per column); distinct batch per step, "
-                             f"{(B * (det_all.shape[2] + obs_all.shape[2]) * nsteps) >> 20} MiB of syndromes in total (> L2), no L2 flush"},
+        "config": config_block(args),
+        "inputs": "DEM samples drawn on the device (Philox, independent Bernoulli per column); distinct batch per step, "
+                  f"{(B * (det_all.shape[2] + obs_all.shape[2]) * nsteps) >> 20} MiB of syndromes in total (> L2), no L2 flush",
         "e2e": {"value": round(e2e, 1), "unit": "shots/s", "h2d_bytes_per_step": int(B * (det_all.shape[2] + obs_all.shape[2])),
-                "d2h_bytes_per_step": 16, "ms_per_step": round(ms_e2e / K, 3)},
+                "d2h_bytes_per_step": 16 + 8 * n_win, "ms_per_step": round(ms_e2e / K, 3),
+                "api": "SlidingWindowDecoder.decode(pinned host det, obs) -> flagged / failed counts (one byte per bit in)"},
+        "e2e_corrections": {"value": round(total_shots / (ms_e2ec / 1e3), 1), "unit": "shots/s",
+                            "h2d_bytes_per_step": int(8 * B * (h_detp.shape[2] + h_obsp.shape[2])),
+                            "d2h_bytes_per_step": int(8 * B * wc) + 16 + 8 * n_win, "ms_per_step": round(ms_e2ec / K, 3),
+                            "api": "SlidingWindowDecoder.decode_packed(bit-packed host det, obs) -> bit-packed total_e_hat + counts"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "window_latency_ms": {"p50_at_batch": round(p50_b, 4), "p99_at_batch": round(p99_b, 4), "p50_batch1": round(p50_1, 4), "p99_batch1": round(p99_1, 4)},
         "results": {"shots": int(total_shots), "flagged": int(counts_res[0]), "failed": int(counts_res[1]),
@@ -425,46 +567,39 @@ def run_ours(args):
 
 
 def run_reference(args):
+    """The reference's own CPU implementation of the path on this box's host cores, same metric / config / steps contract.
+    Each step is a bounded sample of the workload (the CPU needs minutes for what the GPU does per step): shots per step are
+    sized so that warm-up + steps finish in ~90 s; throughput = shots / time over the timed steps."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     plan = build_plan()
-    # (i) the reference as shipped: ONE process, bpgd.cpp's own 15 std::threads per decode (oracle/_ref), if it was built
-    as_shipped = None
-    from oracle.oracle import ref_lib
-    if ref_lib() is not None and WL["decoder"] == "gdg":
-        devnull = os.open(os.devnull, os.O_WRONLY)
-        saved = os.dup(2); os.dup2(devnull, 2)          # "Error setting thread affinity" spam on hosts with < 15 cores
-        try:
-            a1 = CpuArm(plan, use_ref=True, procs=1)
-            det, obs = sample_host(plan, 48, 7)
-            dt, _, _ = a1.run(det, obs)
-            a1.close()
-            as_shipped = round(48 / dt, 2)
-        finally:
-            os.dup2(saved, 2)
-    # (ii) all-core: one process per core, each running the C port on a shard of the shots
-    arm = CpuArm(plan)
-    nsample = calibrate_cpu_sample(arm, plan, 8.0)
-    K, W = args.steps, args.warmup
-    K = max(1, min(K, 6)); W = max(0, min(W, 1))      # bounded: the whole run must end within minutes
+    modes, best, rp, cores = cpu_reference_modes(plan, calib_s=min(3.0, args.ref_seconds / 10.0))
+    K, W = max(1, args.steps), max(0, args.warmup)
+    use_ref = best is not None
+    P, rate0 = (best if use_ref else (None, rp))
+    nsample = int(max(4 * (P or cores), min(20000, rate0 * args.ref_seconds / (K + W))))
     times, fails, n = [], 0, 0
-    for i in range(W + K):
-        det, obs = sample_host(plan, nsample, 100 + i)
-        dt, fl, fa = arm.run(det, obs)
-        if i >= W:
-            times.append(dt); fails += fa; n += nsample
-    arm.close()
+    with _quiet_stderr():
+        arm = CpuArm(plan, use_ref=use_ref, procs=P)
+        for i in range(W + K):
+            det, obs = sample_host(plan, nsample, 100 + i)
+            dt, fl, fa = arm.run(det, obs)
+            if i >= W:
+                times.append(dt); fails += fa; n += nsample
+        arm.close()
     v = n / sum(times)
+    how = (f"{nsample} shots x {len(plan.windows)} windows per step through oracle/_ref (the reference's own bpgd.cpp + mod2sparse.c, "
+           f"g++ -O2; do_work with 15 std::threads per decode), {P} process(es) = the fastest of {modes}") if use_ref else \
+          (f"{nsample} shots x {len(plan.windows)} windows per step through the oracle port (C restatement, gcc -O2), one process per core"
+           + ("" if WL["decoder"] == "gdg" else " (oracle/_ref binds the GDG path only)"))
     line = {"impl": "reference", "metric": METRIC[WL["decoder"]], "value": round(v, 2), "unit": "shots/s",
             "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": K, "warmup": W, "ms_per_step": round(1e3 * sum(times) / K, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WL["name"], "shots_per_step": nsample},
-            "cpu_baseline": {"value": round(v, 2), "unit": "shots/s", "cores": arm.cores, "kind": "port",
-                             "sample": f"{nsample} shots x {len(plan.windows)} windows per step, oracle port (C restatement), one process per core",
-                             "reference_as_shipped_shots_per_s": as_shipped,
-                             "reference_as_shipped_note": "oracle/_ref = the reference's own bpgd.cpp/mod2sparse.c, one process, "
-                                                          "15 std::threads per decode, 48 shots" if as_shipped else "oracle/_ref not built"},
+            "config": config_block(args), "sample_shots_per_step": nsample,
+            "cpu_baseline": {"value": round(v, 2), "unit": "shots/s", "cores": cores, "kind": "reference" if use_ref else "port", "sample": how,
+                             "modes_shots_per_s": modes, "port_per_core_shots_per_s": round(rp, 2), "cpu_model": _cpu_model(),
+                             "nproc": os.cpu_count(), "compiler_flags": "-O2 (as the reference's setup.py)"},
             "e2e": {"value": round(v, 2), "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "results": {"shots": n, "failed": fails}}
     print(json.dumps(line), file=_STDOUT, flush=True)
@@ -480,6 +615,7 @@ def main():
     ap.add_argument("--workload", default="c3_gdg", choices=sorted(WORKLOADS), help="default: BASELINE.json configs[2], the metric's configuration")
     ap.add_argument("--streams", type=int, default=3, help="concurrent sub-batches per GPU (fills kernel tails)")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: do not time the CPU baseline")
+    ap.add_argument("--ref-seconds", type=float, default=90.0, help="--impl reference: CPU seconds spent on warm-up + timed steps together")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
     # the contract is ONE JSON line on stdout: libraries that write to fd 1 themselves (NCCL prints its version banner

@@ -93,6 +93,9 @@ typedef struct swd_counters {
     uint64_t bp_calls;            /* min_sum_log-equivalent calls over all branch paths          */
     uint64_t path_vn_iters;       /* active variable nodes x iterations inside GDG/GD/post-BP    */
     uint64_t path_cn_iters;       /* active check nodes x iterations inside GDG/GD/post-BP       */
+    uint64_t path_slot_iters;     /* message slots (live, dead, pad) scanned by those check passes */
+    uint64_t osd_cols_scanned;    /* columns gathered against T by osd_kernel's elimination scan */
+    uint64_t osd_pivots;          /* pivots found (= rank x OSD shots)                           */
 } swd_counters;
 
 /* Kernel classes for swd_get_kernel_times */
@@ -120,6 +123,21 @@ int  swd_decode_batch_host(swd_decoder *d, const uint8_t *synd, int64_t B,
                            uint8_t *corr, uint8_t *converge, double *min_pm);
 int  swd_decode_batch_device(swd_decoder *d, const uint8_t *d_synd, int64_t B,
                              uint8_t *d_corr, uint8_t *d_converge, double *d_min_pm, void *stream);
+
+/* Bit-packed shot I/O (8x fewer bytes over PCIe / HBM at the boundary): row b of a packed array holds ceil(nbits / 64)
+ * uint64 words, bit j of the row = (word[j >> 6] >> (j & 63)) & 1  (numpy: packbits(bitorder="little").view(uint64)).
+ * synd_packed [B, ceil(m/64)], corr_packed [B, ceil(n/64)]; converge / min_pm as above.  Same decode(syndrome) semantics
+ * as the byte entry points (bp_guessing_decoder.pyx:221-252, osd_window.pyx:158-199).  The _device variant unpacks into /
+ * packs from the decoder's own staging buffers on `stream`: calls on one decoder must be stream-ordered. */
+int  swd_decode_batch_host_packed(swd_decoder *d, const uint64_t *synd_packed, int64_t B,
+                                  uint64_t *corr_packed, uint8_t *converge, double *min_pm);
+int  swd_decode_batch_device_packed(swd_decoder *d, const uint64_t *d_synd_packed, int64_t B,
+                                    uint64_t *d_corr_packed, uint8_t *d_converge, double *d_min_pm, void *stream);
+/* the two conversions on their own (device pointers), for callers that keep shot data packed (window driver, samplers) */
+int  swd_pack_bits(int device, const uint8_t *d_bytes, int64_t B, int nbits, uint64_t *d_packed, void *stream);
+int  swd_unpack_bits(int device, const uint64_t *d_packed, int64_t B, int nbits, uint8_t *d_bytes, void *stream);
+/* 1 if the full-window BP of this decoder streams its messages from HBM (graph beyond one SM's shared memory), else 0 */
+int  swd_is_streamed(swd_decoder *d);
 
 /* osd_window read-only properties of the LAST batch (osd_window.pyx:487-517), host copies.
  * Any pointer may be NULL.  bp_dec/osd0/osdw: [B*n]; log_prob_ratios: [B*n*4]; bp_iteration: [B]. */

@@ -22,7 +22,8 @@ class SwdConfig(C.Structure):
 
 class SwdCounters(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("shots", "pre_bp_edge_iters", "path_edge_iters", "gdg_shots", "osd_shots",
-                                          "kernel_launches", "paths_run", "bp_calls", "path_vn_iters", "path_cn_iters")]
+                                          "kernel_launches", "paths_run", "bp_calls", "path_vn_iters", "path_cn_iters",
+                                          "path_slot_iters", "osd_cols_scanned", "osd_pivots")]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
@@ -32,7 +33,8 @@ KIND_BPGDG, KIND_BPGD, KIND_OSD_WINDOW = 0, 1, 2
 KERNEL_CLASSES = ["pre_bp", "sort_reset", "path_main", "path_side", "select", "osd", "path_trunk", "post_bp"]
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4
 
-EXPORTS = ["swd_create", "swd_destroy", "swd_decode_batch_host", "swd_decode_batch_device", "swd_osd_last_outputs",
+EXPORTS = ["swd_create", "swd_destroy", "swd_decode_batch_host", "swd_decode_batch_device", "swd_decode_batch_host_packed",
+           "swd_decode_batch_device_packed", "swd_pack_bits", "swd_unpack_bits", "swd_is_streamed", "swd_osd_last_outputs",
            "swd_set_profiling", "swd_get_kernel_times", "swd_get_counters", "swd_reset_counters", "swd_rank", "swd_new_n", "swd_window_create", "swd_window_destroy",
            "swd_window_extract", "swd_window_commit", "swd_window_count_failures", "swd_window_set_priors", "swd_window_sample", "swd_bp4_create", "swd_bp4_destroy", "swd_bp4_rank", "swd_bp4_decode_batch_host", "swd_bp4_camel_decode_batch_host", "swd_bp4_decode_batch_device", "swd_bp4_camel_decode_batch_device", "swd_strerror", "swd_last_error",
            "swd_version"]
@@ -58,6 +60,16 @@ def load():
     lib.swd_decode_batch_host.restype = C.c_int
     lib.swd_decode_batch_device.argtypes = [vp, u8p, C.c_int64, u8p, u8p, dp, vp]
     lib.swd_decode_batch_device.restype = C.c_int
+    lib.swd_decode_batch_host_packed.argtypes = [vp, vp, C.c_int64, vp, u8p, dp]
+    lib.swd_decode_batch_host_packed.restype = C.c_int
+    lib.swd_decode_batch_device_packed.argtypes = [vp, vp, C.c_int64, vp, u8p, dp, vp]
+    lib.swd_decode_batch_device_packed.restype = C.c_int
+    lib.swd_pack_bits.argtypes = [C.c_int, vp, C.c_int64, C.c_int, vp, vp]
+    lib.swd_pack_bits.restype = C.c_int
+    lib.swd_unpack_bits.argtypes = [C.c_int, vp, C.c_int64, C.c_int, vp, vp]
+    lib.swd_unpack_bits.restype = C.c_int
+    lib.swd_is_streamed.argtypes = [vp]
+    lib.swd_is_streamed.restype = C.c_int
     lib.swd_osd_last_outputs.argtypes = [vp, C.c_int64, u8p, u8p, u8p, dp, vp]
     lib.swd_osd_last_outputs.restype = C.c_int
     lib.swd_get_counters.argtypes = [vp, C.POINTER(SwdCounters)]

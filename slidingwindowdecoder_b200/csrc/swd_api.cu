@@ -73,7 +73,7 @@ struct swd_decoder {
     OsdWork ow{};
     void *ws_block = nullptr;
     // staging for the host entry point
-    u8 *d_synd = nullptr, *d_corr = nullptr, *d_conv = nullptr; double *d_pm = nullptr;
+    u8 *d_synd = nullptr, *d_corr = nullptr, *d_conv = nullptr; double *d_pm = nullptr; u64 *d_psynd = nullptr, *d_pcorr = nullptr;
     u8 *h_pin = nullptr; size_t h_pin_bytes = 0;
     long long stage_cap = 0;
     cudaStream_t stream = nullptr;
@@ -140,6 +140,7 @@ static int host_rank(int m, int n, const std::vector<int> &cp, const std::vector
 }
 
 static int setup_kernels(swd_decoder *d);
+static int ensure_stage(swd_decoder *d, long long B);
 static int alloc_workspace(swd_decoder *d, long long want_cap);
 
 static int create_impl(const swd_config *cfg, int m, int n, const int32_t *colptr, const int32_t *rowidx,
@@ -273,6 +274,8 @@ extern "C" void swd_destroy(swd_decoder *d) {
     if (d->d_corr) cudaFree(d->d_corr);
     if (d->d_conv) cudaFree(d->d_conv);
     if (d->d_pm) cudaFree(d->d_pm);
+    if (d->d_psynd) cudaFree(d->d_psynd);
+    if (d->d_pcorr) cudaFree(d->d_pcorr);
     if (d->h_pin) cudaFreeHost(d->h_pin);
     for (auto &e : d->ev_used) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto &e : d->ev_free) cudaEventDestroy(e);
@@ -581,6 +584,7 @@ static int pull_stats(swd_decoder *d, cudaStream_t s) {
     CK(cudaStreamSynchronize(s));
     d->ctr.pre_bp_edge_iters = h[0]; d->ctr.path_edge_iters = h[1]; d->ctr.paths_run = h[2]; d->ctr.bp_calls = h[3];
     d->ctr.osd_shots = h[4]; d->ctr.gdg_shots = h[5]; d->ctr.path_vn_iters = h[6]; d->ctr.path_cn_iters = h[7];
+    d->ctr.path_slot_iters = h[8]; d->ctr.osd_cols_scanned = h[9]; d->ctr.osd_pivots = h[10];
     return SWD_OK;
 }
 
@@ -726,14 +730,7 @@ extern "C" int swd_decode_batch_host(swd_decoder *d, const uint8_t *synd, int64_
     if (!d || B < 0 || (B > 0 && (!synd || !corr || !conv))) { set_err("decode: null argument"); return SWD_ERR_INVALID; }
     if (B == 0) return SWD_OK;
     CK(cudaSetDevice(d->device));
-    if (B > d->stage_cap) {
-        if (d->d_synd) { cudaFree(d->d_synd); cudaFree(d->d_corr); cudaFree(d->d_conv); cudaFree(d->d_pm); d->d_synd = nullptr; }
-        CK(cudaMalloc(&d->d_synd, (size_t)B * d->m));
-        CK(cudaMalloc(&d->d_corr, (size_t)B * d->n));
-        CK(cudaMalloc(&d->d_conv, (size_t)B));
-        CK(cudaMalloc(&d->d_pm, (size_t)B * 8));
-        d->stage_cap = B;
-    }
+    { int st0 = ensure_stage(d, B); if (st0) return st0; }
     cudaStream_t s = d->stream;
     CK(cudaMemcpyAsync(d->d_synd, synd, (size_t)B * d->m, cudaMemcpyHostToDevice, s));
     int st = swd_decode_batch_device(d, d->d_synd, B, d->d_corr, d->d_conv, d->d_pm, s);
@@ -744,6 +741,80 @@ extern "C" int swd_decode_batch_host(swd_decoder *d, const uint8_t *synd, int64_
     CK(cudaStreamSynchronize(s));
     return SWD_OK;
 }
+
+// ---- bit-packed shot I/O ------------------------------------------------------------------------------------------
+static int launch_pack(const u8 *d_bytes, long long B, int nbits, u64 *d_packed, cudaStream_t s) {
+    const int w64 = (nbits + 63) / 64; const long long warps = B * ((w64 * 2 + 31) / 32);
+    if (warps > 0) pack_bits_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(d_bytes, B, nbits, w64, (u32 *)d_packed);
+    CK(cudaGetLastError());
+    return SWD_OK;
+}
+static int launch_unpack(const u64 *d_packed, long long B, int nbits, u8 *d_bytes, cudaStream_t s) {
+    const int w64 = (nbits + 63) / 64; const long long warps = B * ((w64 * 2 + 31) / 32);
+    if (warps > 0) unpack_bits_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>((const u32 *)d_packed, B, nbits, w64, d_bytes);
+    CK(cudaGetLastError());
+    return SWD_OK;
+}
+extern "C" int swd_pack_bits(int device, const uint8_t *d_bytes, int64_t B, int nbits, uint64_t *d_packed, void *stream) {
+    if (B < 0 || nbits <= 0 || (B > 0 && (!d_bytes || !d_packed))) { set_err("pack: bad argument"); return SWD_ERR_INVALID; }
+    CK(cudaSetDevice(device));
+    return launch_pack(d_bytes, B, nbits, (u64 *)d_packed, (cudaStream_t)stream);
+}
+extern "C" int swd_unpack_bits(int device, const uint64_t *d_packed, int64_t B, int nbits, uint8_t *d_bytes, void *stream) {
+    if (B < 0 || nbits <= 0 || (B > 0 && (!d_bytes || !d_packed))) { set_err("unpack: bad argument"); return SWD_ERR_INVALID; }
+    CK(cudaSetDevice(device));
+    return launch_unpack((const u64 *)d_packed, B, nbits, d_bytes, (cudaStream_t)stream);
+}
+
+static int ensure_stage(swd_decoder *d, long long B) {
+    if (B > d->stage_cap) {
+        if (d->d_synd) { cudaFree(d->d_synd); cudaFree(d->d_corr); cudaFree(d->d_conv); cudaFree(d->d_pm); cudaFree(d->d_psynd); cudaFree(d->d_pcorr); d->d_synd = nullptr; }
+        CK(cudaMalloc(&d->d_synd, (size_t)B * d->m));
+        CK(cudaMalloc(&d->d_corr, (size_t)B * d->n));
+        CK(cudaMalloc(&d->d_conv, (size_t)B));
+        CK(cudaMalloc(&d->d_pm, (size_t)B * 8));
+        CK(cudaMalloc(&d->d_psynd, (size_t)B * ((d->m + 63) / 64) * 8));
+        CK(cudaMalloc(&d->d_pcorr, (size_t)B * ((d->n + 63) / 64) * 8));
+        d->stage_cap = B;
+    }
+    return SWD_OK;
+}
+
+// packed device pointers; the byte images live in the decoder's staging buffers (calls on one decoder must be stream-ordered)
+extern "C" int swd_decode_batch_device_packed(swd_decoder *d, const uint64_t *d_synd_packed, int64_t B, uint64_t *d_corr_packed,
+                                              uint8_t *d_conv, double *d_pm, void *stream) {
+    if (!d || B < 0 || (B > 0 && (!d_synd_packed || !d_corr_packed || !d_conv))) { set_err("decode: null argument"); return SWD_ERR_INVALID; }
+    if (B == 0) return SWD_OK;
+    CK(cudaSetDevice(d->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int st = ensure_stage(d, B);
+    if (st) return st;
+    if ((st = launch_unpack((const u64 *)d_synd_packed, B, d->m, d->d_synd, s))) return st;
+    if ((st = swd_decode_batch_device(d, d->d_synd, B, d->d_corr, d_conv, d_pm, s))) return st;
+    d->ctr.kernel_launches += 2;
+    return launch_pack(d->d_corr, B, d->n, (u64 *)d_corr_packed, s);
+}
+
+// packed host pointers: 8x fewer bytes over PCIe in both directions
+extern "C" int swd_decode_batch_host_packed(swd_decoder *d, const uint64_t *synd_packed, int64_t B, uint64_t *corr_packed, uint8_t *conv,
+                                            double *pm) {
+    if (!d || B < 0 || (B > 0 && (!synd_packed || !corr_packed || !conv))) { set_err("decode: null argument"); return SWD_ERR_INVALID; }
+    if (B == 0) return SWD_OK;
+    CK(cudaSetDevice(d->device));
+    int st = ensure_stage(d, B);
+    if (st) return st;
+    cudaStream_t s = d->stream;
+    const size_t ws = (size_t)((d->m + 63) / 64) * 8, wc = (size_t)((d->n + 63) / 64) * 8;
+    CK(cudaMemcpyAsync(d->d_psynd, synd_packed, (size_t)B * ws, cudaMemcpyHostToDevice, s));
+    if ((st = swd_decode_batch_device_packed(d, (const uint64_t *)d->d_psynd, B, (uint64_t *)d->d_pcorr, d->d_conv, d->d_pm, s))) return st;
+    CK(cudaMemcpyAsync(corr_packed, d->d_pcorr, (size_t)B * wc, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(conv, d->d_conv, (size_t)B, cudaMemcpyDeviceToHost, s));
+    if (pm) CK(cudaMemcpyAsync(pm, d->d_pm, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SWD_OK;
+}
+
+extern "C" int swd_is_streamed(swd_decoder *d) { return d ? (d->stream_mode ? 1 : 0) : -1; }
 
 extern "C" int swd_osd_last_outputs(swd_decoder *d, int64_t B, uint8_t *bp_dec, uint8_t *osd0, uint8_t *osdw,
                                     double *lpr, int32_t *bp_iteration) {

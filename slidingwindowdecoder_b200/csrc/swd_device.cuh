@@ -103,6 +103,7 @@ struct Workspace {              // per-batch device buffers
     u8 *side;                   // [cap][n_side][side_stride]
     u8 *node;                   // [cap][n_nodes][node_stride] shared-prefix snapshots (masks, messages, history)
     u64 *stats;                 // device counters: [0] pre edge-iters [1] path edge-iters [2] paths [3] bp calls [4] osd shots
+                                // [5] gdg shots [6] vn iters [7] cn iters [8] check-pass slots scanned [9] osd columns scanned [10] osd pivots
     // work lists of the branch-path launches: list `l` holds counters[SWD_WL_CNT + l] packed items at wl + l * wl_stride.
     // A launch only draws tickets for work that exists (a node that died or converged lists no children), and the item
     // itself carries what the set-up needs first (slot, branch path, message-slot count), so the shot's graph can be
@@ -741,7 +742,7 @@ __device__ __forceinline__ double vn_update(Ctx &c, const int j, const int e0, c
 // On a converged return the messages may already hold the next check pass; they are never used then.
 template <int VPT, int DMAX>
 __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter, u64 &edge_iters, u32 &vn_iters, u32 &cn_iters,
-                                      int *iters_done = nullptr) {
+                                      u64 &slot_iters, int *iters_done = nullptr) {
     const int T = blockDim.x, tid = threadIdx.x;
     const double fpos = c.factor, fneg = -c.factor;
     // ---- active checks of this call, compacted in rank order (cn_mask does not change inside a call; an
@@ -779,7 +780,11 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
         const int sl = own_slot(i, tid, T);
         if (sl < c.nn) { const int j = c.vperm[sl]; if (c.vn_mask[j] < 0) { my_vn++; my_edges += (u32)(c.voff[j + 1] - c.voff[j]); } }
     }
-    for (int i = 0; i * T < na; i++) my_cn += (own_slot(i, tid, T) < na);
+    u32 my_slots = 0;                                       // message slots (live + dead + pad) of the owned active rows
+    for (int i = 0; i * T < na; i++) {
+        const int k = own_slot(i, tid, T);
+        if (k < na) { const int q = alist[k]; my_cn++; my_slots += (u32)(c.coff[q + 1] - c.coff[q]); }
+    }
     int it = 0, conv = 0;
     for (;; it++) {
         // ---- check pass (+ convergence test of the previous iteration)
@@ -826,7 +831,7 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
     // `it` variable passes were executed; check updates: one per variable pass, plus one more when the call converged
     // before the last iteration (the messages of that extra pass are never used)
     const u32 vp = (u32)it, cp = (u32)(conv ? (it < num_iter ? it + 1 : it) : it);
-    edge_iters += (u64)my_edges * vp; vn_iters += my_vn * vp; cn_iters += my_cn * cp;
+    edge_iters += (u64)my_edges * vp; vn_iters += my_vn * vp; cn_iters += my_cn * cp; slot_iters += (u64)my_slots * cp;
     if (iters_done) *iters_done = conv ? it : (num_iter > 0 ? num_iter : 0);
     return conv;
 }

@@ -510,7 +510,7 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
         c.misc[8] = n1; c.misc[9] = npaths * n1; c.misc[10] = npaths * n1 + n2;
     }
     const int ticket = (node_level >= 0) ? 16 + 2 * node_level + tier : 1 + phase + 3 * tier;
-    u64 edge_iters = 0, bp_calls = 0, paths_run = 0;
+    u64 edge_iters = 0, bp_calls = 0, paths_run = 0, slot_iters = 0;
     u32 vn_iters = 0, cn_iters = 0;
 
     for (;;) {
@@ -663,7 +663,7 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
                     if (depth == 0) c.A_sum = -16;
                 }
                 if (role == R_TREE && stage == 0 && depth > 0 && !on_side) c.A_sum = -12;         // :450
-                conv = bp_run<VPT, DMAX>(c, h, P.num_iter, edge_iters, vn_iters, cn_iters); bp_calls++;
+                conv = bp_run<VPT, DMAX>(c, h, P.num_iter, edge_iters, vn_iters, cn_iters, slot_iters); bp_calls++;
                 steps++;
                 if (role == R_GD) {
                     // bpgd_decoder.gd (pyx:540-553) with decimate_vn_reliable (bpgd.cpp:258-286)
@@ -823,6 +823,9 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { vi += __shfl_xor_sync(FULLMASK, vi, o); ci += __shfl_xor_sync(FULLMASK, ci, o); }
     if (lane == 0) { if (vi) atomicAdd(&ws.stats[6], vi); if (ci) atomicAdd(&ws.stats[7], ci); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) slot_iters += __shfl_xor_sync(FULLMASK, slot_iters, o);
+    if (lane == 0 && slot_iters) atomicAdd(&ws.stats[8], slot_iters);
     if (tid == 0) { if (paths_run) atomicAdd(&ws.stats[2], paths_run); if (bp_calls) atomicAdd(&ws.stats[3], bp_calls); }
 }
 

@@ -88,7 +88,7 @@ post_bp_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, in
     __syncthreads();
     u32 mphase = 0;
     const int count = (tier == 1 && ws.counters[8] == 0) ? 0 : ws.counters[0];
-    u64 edge_iters = 0, bp_calls = 0, paths_run = 0; u32 vn_iters = 0, cn_iters = 0;
+    u64 edge_iters = 0, bp_calls = 0, paths_run = 0, slot_iters = 0; u32 vn_iters = 0, cn_iters = 0;
     for (;;) {
         __syncthreads();
         if (tid == 0) c.misc[2] = atomicAdd(&ws.counters[1 + 3 * tier], 1);
@@ -141,7 +141,7 @@ post_bp_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, in
         __syncthreads();
         paths_run++;
         int iters = 0;
-        const int conv = bp_run<VPT, DMAX>(c, h, P.post_max_iter, edge_iters, vn_iters, cn_iters, &iters); bp_calls++;
+        const int conv = bp_run<VPT, DMAX>(c, h, P.post_max_iter, edge_iters, vn_iters, cn_iters, slot_iters, &iters); bp_calls++;
         const long long shot = gh.shot;
         // outputs: bp_decoding, log_prob_ratios, bp_iteration; sort keys for OSD (osd_window.pyx:205-213)
         double *key = ws.sum + (size_t)slot * n;
@@ -177,6 +177,9 @@ post_bp_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, in
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { vi += __shfl_xor_sync(FULLMASK, vi, o); ci += __shfl_xor_sync(FULLMASK, ci, o); }
     if (lane == 0) { if (vi) atomicAdd(&ws.stats[6], vi); if (ci) atomicAdd(&ws.stats[7], ci); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) slot_iters += __shfl_xor_sync(FULLMASK, slot_iters, o);
+    if (lane == 0 && slot_iters) atomicAdd(&ws.stats[8], slot_iters);
     if (tid == 0) { if (paths_run) atomicAdd(&ws.stats[2], paths_run); if (bp_calls) atomicAdd(&ws.stats[3], bp_calls); }
 }
 
@@ -191,7 +194,7 @@ osd_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayout L, G
     u16 *idx = (u16 *)(smem + S.off_idx);               // after the sort: scan order of the columns
     u64 *tcol = (u64 *)(smem + S.off_tcol);             // [(m+1)][W64]; column m carries T*syndrome
     u64 *vt = S.big ? (u64 *)(ow.big_scratch + (size_t)blockIdx.x * S.big_stride) : (u64 *)(smem + S.off_vt);   // [k][W64] reduced non-pivot columns
-    u16 *colinfo = (u16 *)(smem + S.off_colinfo);       // per column: 0xffff none | pivot row | 0x8000 + T index
+    u16 *colinfo = S.big ? (u16 *)(ow.big_scratch + (size_t)blockIdx.x * S.big_stride + (size_t)S.off_colinfo) : (u16 *)(smem + S.off_colinfo);   // per column: 0xffff none | pivot row | 0x8000 + T index
     u32 *ent = (u32 *)(smem + S.off_ent);               // [nn'] (col << 16 | info), ascending col
     u64 *pivmask = (u64 *)(smem + S.off_piv);           // [W64]
     u32 *scan = S.big ? (u32 *)(ow.big_scratch + (size_t)blockIdx.x * S.big_stride + (size_t)S.off_scan) : (u32 *)(smem + S.off_scan);   // [n+1]
@@ -205,7 +208,7 @@ osd_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayout L, G
     const int m = g.m, n = g.n, nn = L.nn, W64 = S.W64, NP2 = S.np2, k = S.k;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     const int count = ws.counters[0];
-    u64 osd_shots = 0;
+    u64 osd_shots = 0, osd_cols = 0, osd_piv = 0;
 
     for (;;) {
         __syncthreads();
@@ -323,6 +326,7 @@ osd_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayout L, G
             pos += nw;
             if (stop || pos >= n) break;
         }
+        osd_cols += (u64)min(pos, n); osd_piv += (u64)found;
         __syncthreads();
         if (pcount > 0) {
             for (int r = tid; r <= m; r += T) {
@@ -449,7 +453,7 @@ osd_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayout L, G
         }
         if (tid == 0 && pm_out) pm_out[shot] = use_w ? best : pm0;
     }
-    if (tid == 0 && osd_shots) atomicAdd(&ws.stats[4], osd_shots);
+    if (tid == 0 && osd_shots) { atomicAdd(&ws.stats[4], osd_shots); atomicAdd(&ws.stats[9], osd_cols); atomicAdd(&ws.stats[10], osd_piv); }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -536,7 +540,6 @@ static inline int osd_setup(int m, int n, int nn, int rank, int method, int orde
         o = 0;
         S->off_key = 0; S->off_tcol = 0; o = osd_r16(ta > ka ? ta : ka);
         S->off_idx = o; o += 2 * np2; o = osd_r16(o);
-        S->off_colinfo = o; o += 2 * n; o = osd_r16(o);
         S->off_ent = o; o += 4 * (nn + rank + 1); o = osd_r16(o);
         S->off_vbuf = o; o += 8 * S->W64; o = osd_r16(o);
         S->off_piv = o; o += 8 * S->W64; o = osd_r16(o);
@@ -550,6 +553,7 @@ static inline int osd_setup(int m, int n, int nn, int rank, int method, int orde
         long long q = (long long)8 * (S->k > 0 ? S->k : 1) * S->W64; q = (q + 255) & ~255ll;
         S->off_vt = 0; S->off_scan = (int)q;               // offsets inside the per-CTA HBM scratch
         q += (long long)4 * (n + 1); q = (q + 255) & ~255ll;
+        S->off_colinfo = (int)q; q += (long long)2 * n; q = (q + 255) & ~255ll;
         S->big_stride = q;
         if (S->total > 227 * 1024) return -2;
     }

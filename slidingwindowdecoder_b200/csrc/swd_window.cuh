@@ -103,3 +103,43 @@ __global__ void window_sample_kernel(const u32 *__restrict__ thr, int num_col, c
         __syncwarp();
     }
 }
+
+// ----------------------------------------------------------------------------------------------
+// bit-packed shot I/O (SURVEY 7 step 1 / 8(b) "or bit-packed"): row b of `packed` holds ceil(nbits / 64) 64-bit words,
+// bit j of the row = (word[j >> 6] >> (j & 63)) & 1 (numpy: packbits(bitorder="little") viewed as uint64).
+// One warp per 1024 bits of a row: 32 coalesced 32-byte reads + ballots, one coalesced 128-byte store (and the reverse).
+// ----------------------------------------------------------------------------------------------
+__global__ void pack_bits_kernel(const u8 *__restrict__ bytes, long long B, int nbits, int words64, u32 *__restrict__ packed) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int segs = (words64 * 2 + 31) / 32;                   // segments of 32 32-bit words per row
+    if (warp >= B * segs) return;
+    const long long b = warp / segs; const int seg = (int)(warp % segs);
+    const u8 *row = bytes + b * nbits;
+    u32 mine = 0;
+#pragma unroll 4
+    for (int k = 0; k < 32; k++) {
+        const int j = (seg * 32 + k) * 32 + lane;
+        const u32 w = __ballot_sync(FULLMASK, j < nbits && row[j] != 0);
+        if (lane == k) mine = w;
+    }
+    const int wi = seg * 32 + lane;
+    if (wi < words64 * 2) packed[b * words64 * 2 + wi] = mine;
+}
+
+__global__ void unpack_bits_kernel(const u32 *__restrict__ packed, long long B, int nbits, int words64, u8 *__restrict__ bytes) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int segs = (words64 * 2 + 31) / 32;
+    if (warp >= B * segs) return;
+    const long long b = warp / segs; const int seg = (int)(warp % segs);
+    const int wi = seg * 32 + lane;
+    const u32 mine = (wi < words64 * 2) ? packed[b * words64 * 2 + wi] : 0u;
+    u8 *row = bytes + b * nbits;
+#pragma unroll 4
+    for (int k = 0; k < 32; k++) {
+        const u32 w = __shfl_sync(FULLMASK, mine, k);
+        const int j = (seg * 32 + k) * 32 + lane;
+        if (j < nbits) row[j] = (u8)((w >> lane) & 1u);
+    }
+}

@@ -27,9 +27,38 @@ _BP_METHODS = {"minimum_sum": 0, "ms": 0, "min_sum": 0, "msl": 0, "0": 0,
 
 
 def _libm_llr(channel_probs, n):
-    # log((1-p)/p) with libm's log, as bp_guessing_decoder.pyx:46 (numpy's vector log differs by ulps)
-    return np.array([math.log((1.0 - float(channel_probs[v])) / float(channel_probs[v])) for v in range(n)],
-                    dtype=np.float64)
+    """log((1-p)/p) with libm's log, as bp_guessing_decoder.pyx:46 (numpy's vector log differs by ulps).  The reference only
+    fills channel_llr when channel_probs[0] is not None (pyx:19-23, :44-46) - the LLRs then stay 0 - and its cdivision
+    arithmetic gives +inf for p = 0 (-inf for p = 1) instead of raising."""
+    out = np.zeros(n, dtype=np.float64)
+    if channel_probs[0] is None:
+        return out
+    for v in range(n):
+        p = float(channel_probs[v])
+        if p <= 0.0:
+            out[v] = math.inf
+        elif p >= 1.0:
+            out[v] = -math.inf
+        else:
+            out[v] = math.log((1.0 - p) / p)
+    return out
+
+
+def pack_bits(a):
+    """[B, k] array of 0/1 -> [B, ceil(k/64)] uint64, bit j of a row = (word[j >> 6] >> (j & 63)) & 1 (the C-ABI's packed layout)."""
+    a = np.ascontiguousarray(np.asarray(a), dtype=np.uint8)
+    B, k = a.shape
+    w = (k + 63) // 64
+    out = np.zeros((B, w * 8), dtype=np.uint8)
+    pk = np.packbits(a, axis=1, bitorder="little")
+    out[:, :pk.shape[1]] = pk
+    return out.view(np.uint64)
+
+
+def unpack_bits(p, k):
+    """inverse of pack_bits: [B, ceil(k/64)] uint64 -> [B, k] uint8"""
+    p = np.ascontiguousarray(p, dtype=np.uint64)
+    return np.unpackbits(p.view(np.uint8), axis=1, bitorder="little")[:, :k]
 
 
 def _is_torch_cuda(x):
@@ -100,6 +129,46 @@ class _window_decoder_base:
         _lib.check(st, "swd_decode_batch_host")
         self._last_B = B
         return (corr, conv, pm) if return_pm else (corr, conv)
+
+    def decode_batch_packed(self, synd_packed, return_pm=False):
+        """Bit-packed twin of decode_batch (swd_decode_batch_host_packed / _device_packed): synd_packed [B, ceil(m/64)] uint64
+        (see pack_bits) -> (corrections [B, ceil(n/64)] uint64, converge [B] uint8[, min_pm]).  numpy in -> numpy out with the
+        copies inside the call; torch CUDA int64/uint64 tensor in -> torch CUDA tensors out on the current stream."""
+        wm, wn = (self.m + 63) // 64, (self.n + 63) // 64
+        if _is_torch_cuda(synd_packed):
+            import torch
+            s = synd_packed.contiguous()
+            if s.dim() != 2 or s.shape[1] != wm or s.element_size() != 8:
+                raise ValueError(f"decode_batch_packed expects 64-bit words of shape [B, {wm}], got {tuple(s.shape)}")
+            if s.device.index != self._device:
+                raise ValueError(f"syndromes live on cuda:{s.device.index}, decoder on cuda:{self._device}")
+            B = s.shape[0]
+            corr = torch.empty((B, wn), dtype=torch.int64, device=s.device)
+            conv = torch.empty(B, dtype=torch.uint8, device=s.device)
+            pm = torch.empty(B, dtype=torch.float64, device=s.device)
+            stream = torch.cuda.current_stream(s.device).cuda_stream
+            st = self._lib.swd_decode_batch_device_packed(self._handle, s.data_ptr(), B, corr.data_ptr(), conv.data_ptr(), pm.data_ptr(),
+                                                          C.c_void_p(stream))
+            _lib.check(st, "swd_decode_batch_device_packed")
+            self._last_B = B
+            self._keepalive = s
+            return (corr, conv, pm) if return_pm else (corr, conv)
+        s = np.ascontiguousarray(synd_packed, dtype=np.uint64)
+        if s.ndim != 2 or s.shape[1] != wm:
+            raise ValueError(f"decode_batch_packed expects uint64 words of shape [B, {wm}], got {s.shape}")
+        B = s.shape[0]
+        corr = np.empty((B, wn), dtype=np.uint64)
+        conv = np.empty(B, dtype=np.uint8)
+        pm = np.empty(B, dtype=np.float64)
+        st = self._lib.swd_decode_batch_host_packed(self._handle, s.ctypes.data, B, corr.ctypes.data, conv.ctypes.data, pm.ctypes.data)
+        _lib.check(st, "swd_decode_batch_host_packed")
+        self._last_B = B
+        return (corr, conv, pm) if return_pm else (corr, conv)
+
+    @property
+    def streamed_bp(self):
+        """True if the full-window BP streams its messages from HBM (the window graph exceeds one SM's shared memory)."""
+        return bool(self._lib.swd_is_streamed(self._handle) == 1)
 
     def _decode_batch_torch(self, syndromes, return_pm):
         import torch

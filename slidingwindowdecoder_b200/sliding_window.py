@@ -228,12 +228,55 @@ class SlidingWindowDecoder:
             out["total_e_hat"] = total
         return out
 
-    def decode(self, det_data, obs_data, return_corrections=False):
-        """Host entry point (numpy uint8 in, python ints out): H2D copy, all windows, D2H of the counters."""
+    def decode_packed(self, det_packed, obs_packed, return_corrections=True, pinned_out=None):
+        """Host entry point with bit-packed shot data (decoders.pack_bits layout): det_packed [B, ceil(num_det/64)] and
+        obs_packed [B, ceil(num_obs/64)] uint64 (numpy or pinned torch CPU tensors) -> dict(flagged, failed,
+        window_unconverged, total_e_hat_packed [B, ceil(num_col/64)] uint64).  8x fewer bytes cross PCIe than with one byte
+        per bit (configs[2]: 82 MB instead of 658 MB of corrections per 32768 shots).  pinned_out: optional pinned torch
+        int64 CPU tensor [B, ceil(num_col/64)] that receives the packed corrections."""
         torch = self.torch
         dev = torch.device("cuda", self.device)
-        det = torch.from_numpy(np.ascontiguousarray(det_data, dtype=np.uint8)).to(dev, non_blocking=True)
-        obs = torch.from_numpy(np.ascontiguousarray(obs_data, dtype=np.uint8)).to(dev, non_blocking=True)
+
+        def to_dev(x):
+            t = x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x).view(np.int64))
+            return t.to(dev, non_blocking=True)
+        dp, op = to_dev(det_packed), to_dev(obs_packed)
+        B = dp.shape[0]
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        det = torch.empty((B, self.num_det), dtype=torch.uint8, device=dev)
+        obs = torch.empty((B, self.num_obs), dtype=torch.uint8, device=dev)
+        _lib.check(self.lib.swd_unpack_bits(self.device, dp.data_ptr(), B, self.num_det, det.data_ptr(), stream), "unpack det")
+        if self.num_obs:
+            _lib.check(self.lib.swd_unpack_bits(self.device, op.data_ptr(), B, self.num_obs, obs.data_ptr(), stream), "unpack obs")
+        out = self.decode_device(det, obs, return_corrections)
+        res = {}
+        if return_corrections:
+            wn = (self.num_col + 63) // 64
+            packed = torch.empty((B, wn), dtype=torch.int64, device=dev)
+            _lib.check(self.lib.swd_pack_bits(self.device, out["total_e_hat"].data_ptr(), B, self.num_col, packed.data_ptr(), stream), "pack e_hat")
+            if pinned_out is not None:
+                pinned_out.copy_(packed, non_blocking=True)
+                host = pinned_out
+            else:
+                host = packed.cpu()
+            res["total_e_hat_packed"] = host
+        counts = out["counts"].cpu().numpy()          # synchronises the stream: the packed corrections have landed as well
+        res.update(shots=int(B), flagged=int(counts[0]), failed=int(counts[1]),
+                   window_unconverged=out["window_unconverged"].cpu().numpy().tolist())
+        if return_corrections and not torch.is_tensor(det_packed):
+            res["total_e_hat_packed"] = res["total_e_hat_packed"].numpy().view(np.uint64)
+        return res
+
+    def decode(self, det_data, obs_data, return_corrections=False):
+        """Host entry point (numpy uint8 - or torch CPU tensors, e.g. pinned - in, python ints out): H2D copy, all windows,
+        D2H of the counters (and of the corrections, one byte per bit, if asked for; decode_packed moves 8x less)."""
+        torch = self.torch
+        dev = torch.device("cuda", self.device)
+
+        def to_dev(x):
+            t = x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.uint8))
+            return t.to(dev, non_blocking=True)
+        det, obs = to_dev(det_data), to_dev(obs_data)
         out = self.decode_device(det, obs, return_corrections)
         counts = out["counts"].cpu().numpy()
         res = dict(shots=int(det.shape[0]), flagged=int(counts[0]), failed=int(counts[1]),

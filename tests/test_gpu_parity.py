@@ -747,6 +747,69 @@ def test_unwindowed_144_limits_lifted():
         assert not ((corr.astype(np.int64) @ H.T.toarray() + synd) % 2).any()
 
 
+def test_bit_packed_entry_points_equal_byte_entry_points():
+    """swd_decode_batch_host_packed / _device_packed (bit-packed syndromes in, bit-packed corrections out, the layout of
+    decoders.pack_bits) return exactly what the byte entry points return; SlidingWindowDecoder.decode_packed returns the packed
+    image of decode(return_corrections=True)."""
+    import torch
+    from slidingwindowdecoder_b200 import bpgdg_decoder, osd_window
+    from slidingwindowdecoder_b200.decoders import pack_bits, unpack_bits
+    for name, cls in (("c3_w5_gdg_mt1", bpgdg_decoder), ("c2_w1_osdw_cs10", osd_window), ("c5_w0_gdg_mt1", bpgdg_decoder)):
+        g = load_golden(name)
+        dec = cls(g["mat"], channel_probs=g["priors"], **g["kwargs"])
+        corr, conv, pm = dec.decode_batch(g["synd"], return_pm=True)
+        pc, pconv, ppm = dec.decode_batch_packed(pack_bits(g["synd"]), return_pm=True)
+        assert pc.dtype == np.uint64 and pc.shape == (len(corr), (dec.n + 63) // 64)
+        assert np.array_equal(unpack_bits(pc, dec.n), corr) and np.array_equal(pconv, conv) and np.array_equal(ppm, pm)
+        assert np.array_equal(pc, pack_bits(corr))                       # pad bits are zero
+        t = torch.from_numpy(pack_bits(g["synd"]).view(np.int64)).cuda()
+        dc, dconv = dec.decode_batch_packed(t)
+        torch.cuda.synchronize()
+        assert np.array_equal(dc.cpu().numpy().view(np.uint64), pc) and np.array_equal(dconv.cpu().numpy(), conv)
+    from slidingwindowdecoder_b200.codes import bb_code
+    from slidingwindowdecoder_b200.dem import bb_memory_circuit, detector_error_model, dem_to_check_matrices
+    from slidingwindowdecoder_b200.windows import build_windows
+    from slidingwindowdecoder_b200.sliding_window import SlidingWindowDecoder
+    code, A, B = bb_code(72)
+    chk, obs, pri = dem_to_check_matrices(detector_error_model(bb_memory_circuit(code, A, B, 0.004, 5)))
+    plan = build_windows(chk, obs, pri, code.N, W=3, F=1, method=1)
+    swd = SlidingWindowDecoder(plan, decoder="gdg", streams=2, max_iter=8, multi_thread=True)
+    det, ob = swd.sample_device(777, seed=11)
+    hdet, hob = det.cpu().numpy(), ob.cpu().numpy()
+    a = swd.decode(hdet, hob, return_corrections=True)
+    b = swd.decode_packed(pack_bits(hdet), pack_bits(hob))
+    assert (a["flagged"], a["failed"], a["window_unconverged"]) == (b["flagged"], b["failed"], b["window_unconverged"])
+    assert np.array_equal(b["total_e_hat_packed"], pack_bits(a["total_e_hat"]))
+
+
+@pytest.mark.parametrize("N", [360, 756])
+def test_large_bb_code_windows(N, oracle_mod):
+    """codes.bb_code / drivers accept N = 360 and N = 756 (guessing.py:35-37).  A (3,1) window of the [[756,16,<=34]]
+    code is 1134 x 9072 with 31374 edges - beyond one SM's shared memory: pre-BP runs HBM-streamed, the column selection takes
+    the n > 8192 path.  GDG and BP+OSD corrections on sampled window syndromes are bit-exact vs the oracle."""
+    from slidingwindowdecoder_b200 import bpgdg_decoder, osd_window
+    from slidingwindowdecoder_b200.codes import bb_code
+    from slidingwindowdecoder_b200.dem import bb_memory_circuit, detector_error_model, dem_to_check_matrices
+    from slidingwindowdecoder_b200.windows import build_windows
+    from slidingwindowdecoder_b200.sliding_window import sample_dem
+    code, A, B = bb_code(N)
+    chk, obs, pri = dem_to_check_matrices(detector_error_model(bb_memory_circuit(code, A, B, 0.003, 4, z_basis=True)))
+    plan = build_windows(chk, obs, pri, code.N, W=3, F=1, method=1)
+    det, _, _ = sample_dem(plan.chk, plan.obs, plan.priors, 64, np.random.default_rng(N))
+    w = plan.windows[1]
+    s = det[:, w.row0:w.row1]
+    s = s[np.nonzero(s.any(axis=1))[0][:10]]
+    orc = oracle_mod.Oracle(w.mat, w.prior)
+    kw = dict(max_iter=8, multi_thread=True)
+    corr, conv = bpgdg_decoder(w.mat, channel_probs=w.prior, **kw).decode_batch(s)
+    o_dec, o_conv, _, _ = orc.bpgdg_batch(s, **kw)
+    assert np.array_equal(conv, o_conv.astype(np.uint8)) and np.array_equal(corr, o_dec.astype(np.uint8))
+    kw = dict(pre_max_iter=8, post_max_iter=100, osd_method="osd_cs", osd_order=10)
+    corr, conv = osd_window(w.mat, channel_probs=w.prior, **kw).decode_batch(s)
+    o_dec, o_conv, _, _ = orc.osd_window_batch(s, **kw)
+    assert np.array_equal(conv, np.asarray(o_conv).astype(np.uint8)) and np.array_equal(corr, np.asarray(o_dec).astype(np.uint8))
+
+
 def test_bp4_device_pointer_entry_points_match_host_calls():
     """swd_bp4_decode_batch_device / swd_bp4_camel_decode_batch_device (torch CUDA tensors in and out, caller's stream) return
     exactly what the host-buffer calls return."""

@@ -159,7 +159,7 @@ def test_bench_reference_arm_prints_one_contract_line():
     JSON line with the contract's keys, the arm's own `cpu_baseline` and an `e2e` that repeats the line's value."""
     import json, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--ref-seconds", "9"],
                        capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
@@ -171,3 +171,8 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "shots/s" and d["value"] > 0 and d["vs_baseline"] is None
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
+    assert d["steps"] == 2 and d["warmup"] == 1                      # the contract's steps / warm-up are honoured, not clamped
+    sys.path.insert(0, root)
+    import argparse, bench
+    assert d["config"] == bench.config_block(argparse.Namespace(batch=32768, streams=3))     # the product arm's config, verbatim
+    assert "modes_shots_per_s" in d["cpu_baseline"] and d["cpu_baseline"]["nproc"] >= 1
