@@ -353,6 +353,8 @@ def run_ours(args):
     B, K, W = args.batch, args.steps, args.warmup
     nsteps = K + W
     torch.backends.cuda.matmul.allow_tf32 = False
+    if args.total_shots:
+        return run_strong(args, swd, plan, rank, world, dev, dist)
     det_all, obs_all = gpu_sample(swd, B * nsteps, 1234 + rank)
     det_all = det_all.view(nsteps, B, -1); obs_all = obs_all.view(nsteps, B, -1)
     h_det = torch.empty(det_all.shape, dtype=torch.uint8, pin_memory=True); h_det.copy_(det_all)
@@ -566,6 +568,57 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_strong(args, swd, plan, rank, world, dev, dist):
+    """BASELINE configs[2] as written: ONE fixed job of --total-shots shots (10^7) sharded over the ranks with shard_range,
+    every shot drawn on the device (Philox counter = global shot index: the job's syndromes do not depend on the number of
+    GPUs) and decoded through all windows; sampling is inside the clock.  Strong scaling: the line reports wall seconds."""
+    import torch
+    from slidingwindowdecoder_b200.distributed import shard_range, reduce_counters, max_over_ranks
+    total, B = int(args.total_shots), args.batch
+    lo, hi = shard_range(total, rank, world)
+
+    def job(limit=None):
+        counts = torch.zeros(2, dtype=torch.int64, device=dev)
+        s0 = lo
+        end = hi if limit is None else min(hi, lo + limit)
+        while s0 < end:
+            nb = min(B, end - s0)
+            det, obs = swd.sample_device(nb, seed=20261017, shot_offset=s0)
+            counts += swd.decode_device(det, obs)["counts"]
+            s0 += nb
+        return counts
+
+    job(limit=2 * B)                                        # warm-up: workspaces, lazy module loads
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(); torch.cuda.synchronize()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", 0)))
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    counts = job()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(); torch.cuda.synchronize()
+    wall = max_over_ranks(time.perf_counter() - t0, dev)
+    ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    counts = reduce_counters(counts, dev)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        line = {"metric": METRIC[WL["decoder"]], "value": round(total / (ms / 1e3), 1), "unit": "shots/s", "n_gpus": world, "steps": 1, "warmup": 1,
+                "ms_per_step": round(ms, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": dict(config_block(args), total_shots=total),
+                "job": {"total_shots": total, "seconds_device_max_over_ranks": round(ms / 1e3, 3), "seconds_wall_max_over_ranks": round(wall, 3),
+                        "includes": "on-device DEM sampling (Philox) + all windows + counter reduction; shots sharded with shard_range, no data-path collective"},
+                "results": {"shots": total, "flagged": int(counts[0]), "failed": int(counts[1])}, "clocks": clocks}
+        print(json.dumps(line), file=_STDOUT, flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     """The reference's own CPU implementation of the path on this box's host cores, same metric / config / steps contract.
     Each step is a bounded sample of the workload (the CPU needs minutes for what the GPU does per step): shots per step are
@@ -615,6 +668,8 @@ def main():
     ap.add_argument("--workload", default="c3_gdg", choices=sorted(WORKLOADS), help="default: BASELINE.json configs[2], the metric's configuration")
     ap.add_argument("--streams", type=int, default=3, help="concurrent sub-batches per GPU (fills kernel tails)")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: do not time the CPU baseline")
+    ap.add_argument("--total-shots", type=int, default=0, help="strong scaling: decode ONE job of this many shots (configs[2]: 10000000), sharded over the GPUs; "
+                                                            "sampling inside the clock; prints wall seconds")
     ap.add_argument("--ref-seconds", type=float, default=90.0, help="--impl reference: CPU seconds spent on warm-up + timed steps together")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup

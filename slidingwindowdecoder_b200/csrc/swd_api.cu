@@ -141,7 +141,7 @@ static int host_rank(int m, int n, const std::vector<int> &cp, const std::vector
 
 static int setup_kernels(swd_decoder *d);
 static int ensure_stage(swd_decoder *d, long long B);
-static int alloc_workspace(swd_decoder *d, long long want_cap);
+static int alloc_workspace(swd_decoder *d, long long want_cap, cudaStream_t s);
 
 static int create_impl(const swd_config *cfg, int m, int n, const int32_t *colptr, const int32_t *rowidx,
                        const double *channel_llr, swd_decoder **out, bool osd_only);
@@ -196,7 +196,8 @@ static int create_impl(const swd_config *cfg, int m, int n, const int32_t *colpt
         d->rank = host_rank(m, n, cp, cr);
         int method = cfg->osd_method, order = cfg->osd_order;
         if (method == SWD_OSD_0) order = 0;
-        if (order < 0 || order > d->nn - d->rank) {          // osd_window.pyx:88-92
+        if (order == -1 && method != SWD_OSD_0) { /* BP only: no OSD stage (osd_window.pyx:86,192) */ }
+        else if (order < 0 || order > d->nn - d->rank) {     // osd_window.pyx:88-92
             delete d; set_err("swd_create: osd_order out of range 0..new_n-rank"); return SWD_ERR_INVALID;
         }
         if (method == SWD_OSD_E && order > 20) { delete d; set_err("swd_create: osd_e order > 20 unsupported"); return SWD_ERR_UNSUPPORTED; }
@@ -391,9 +392,10 @@ static int setup_kernels(swd_decoder *d) {
         // messages streamed from HBM, one thread per shot (swd_stream.cuh); syndrome + parity bit words per thread in shared memory
         if (ps) { set_err("product-sum BP: window graph does not fit in shared memory (nnz too large)"); return SWD_ERR_UNSUPPORTED; }
         const int MW = (m + 31) / 32;
-        int ts = 256; while (ts > 32 && (size_t)8 * MW * ts > 200 * 1024) ts -= 32;
-        if ((size_t)8 * MW * ts > 200 * 1024) { set_err("window graph has too many checks for the streamed BP kernel"); return SWD_ERR_UNSUPPORTED; }
-        d->stream_mode = true; d->Ts = ts; d->stream_smem = (size_t)8 * MW * ts;
+        // shared memory per thread: the cp.async ring (SWD_SK doubles) + syndrome and parity bit words; two CTAs per SM
+        int ts = 256; while (ts > 32 && (size_t)(8 * MW + 8 * SWD_SK) * ts > 110 * 1024) ts -= 32;
+        if ((size_t)(8 * MW + 8 * SWD_SK) * ts > 110 * 1024) { set_err("window graph has too many checks for the streamed BP kernel"); return SWD_ERR_UNSUPPORTED; }
+        d->stream_mode = true; d->Ts = ts; d->stream_smem = (size_t)(8 * MW + 8 * SWD_SK) * ts;
         S1.total = 0;
     }
     // staged static graph info (per-slot records + CSC->CSR map) if it still fits next to the messages
@@ -532,7 +534,7 @@ static int setup_kernels(swd_decoder *d) {
     return SWD_OK;
 }
 
-static int alloc_workspace(swd_decoder *d, long long want) {
+static int alloc_workspace(swd_decoder *d, long long want, cudaStream_t s) {
     if (want <= d->cap) return SWD_OK;
     CK(cudaSetDevice(d->device));
     size_t budget = (size_t)16 << 30;     // per decoder; 180 GB of HBM3e per GPU
@@ -545,7 +547,13 @@ static int alloc_workspace(swd_decoder *d, long long want) {
     if (osd) per += (size_t)n * 32 + osd_bytes_per_shot(d->m, n);
     long long cap = std::max<long long>(1, std::min<long long>(want, (long long)(budget / per)));
     if (cap <= d->cap) return SWD_OK;
-    if (d->ws_block) { cudaFree(d->ws_block); d->ws_block = nullptr; d->cap = 0; }
+    // growing the workspace: the accumulated work counters (ws.stats) survive the re-allocation
+    u64 keep_stats[16]; bool have_stats = false;
+    if (d->ws_block) {
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(keep_stats, d->ws.stats, sizeof(keep_stats), cudaMemcpyDeviceToHost)); have_stats = true;
+        cudaFree(d->ws_block); d->ws_block = nullptr; d->cap = 0;
+    }
     auto a256 = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t o = 0;
     size_t o_cnt = o; o += a256(64 * sizeof(int));
@@ -563,12 +571,15 @@ static int alloc_workspace(swd_decoder *d, long long want) {
     size_t o_wl = o; o += a256((size_t)wl_stride * SWD_WL_MAX * sizeof(u64));
     cudaError_t e = cudaMalloc(&d->ws_block, o);
     if (e != cudaSuccess) { set_err("workspace cudaMalloc failed"); return SWD_ERR_NOMEM; }
-    CK(cudaMemset(d->ws_block, 0, o_list));
+    // counters / stats / work list zeroed on the caller's stream (the kernels that use them are launched there)
+    CK(cudaMemsetAsync(d->ws_block, 0, o_list, s));
     unsigned char *b = (unsigned char *)d->ws_block;
     d->ws.counters = (int *)(b + o_cnt); d->ws.stats = (u64 *)(b + o_stats); d->ws.gdg_list = (int *)(b + o_list);
     d->ws.sum = (double *)(b + o_sum); d->ws.hist = osd ? (double *)(b + o_hist) : nullptr;
     d->ws.blob = b + o_blob; d->ws.rec = b + o_rec; d->ws.side = b + o_side; d->ws.node = b + o_node;
     d->ws.wl = (u64 *)(b + o_wl); d->ws.wl_stride = wl_stride; d->ws.bak = b + o_bak;
+    if (have_stats) CK(cudaMemcpyAsync(d->ws.stats, keep_stats, sizeof(keep_stats), cudaMemcpyHostToDevice, s));
+    if (have_stats) CK(cudaStreamSynchronize(s));          // keep_stats is a stack buffer
     if (osd) osd_bind(&d->ow, b + o_osd, cap, d->m, n);
     if (osd && d->OS.big && !d->ow.big_scratch) {
         if (cudaMalloc(&d->ow.big_scratch, (size_t)d->grid5 * d->OS.big_stride) != cudaSuccess) { set_err("OSD scratch cudaMalloc failed"); return SWD_ERR_NOMEM; }
@@ -592,10 +603,10 @@ static int pull_stats(swd_decoder *d, cudaStream_t s) {
 static int stream_pre_bp(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_corr, u8 *d_conv, int full_hist, int *iter_out,
                          double *lpr_out, cudaStream_t s) {
     const int Ts = d->Ts, n = d->n;
-    size_t budget = (size_t)24 << 30;
+    size_t budget = (size_t)48 << 30;
     if (const char *e = getenv("SWD_STREAM_BYTES")) budget = (size_t)atoll(e);
     const size_t per_shot = (size_t)8 * (d->nnz + 4 * (size_t)n) + 4 * (size_t)((n + 31) / 32) + 8;
-    long long Gmax = (long long)d->num_sm * Ts;                                   // one CTA per SM
+    long long Gmax = (long long)d->num_sm * Ts * 2;                               // two CTAs per SM
     Gmax = std::max<long long>(Ts, std::min<long long>(Gmax, (long long)(budget / per_shot) / Ts * Ts));
     const long long want = std::min<long long>(Gmax, (B + Ts - 1) / Ts * Ts);
     if (want > d->sw_G) {
@@ -710,9 +721,9 @@ extern "C" int swd_decode_batch_device(swd_decoder *d, const uint8_t *d_synd, in
     if (B == 0) return SWD_OK;
     CK(cudaSetDevice(d->device));
     cudaStream_t s = (cudaStream_t)stream;
-    int st = alloc_workspace(d, B);
+    int st = alloc_workspace(d, B, s);
     if (st) return st;
-    if (d->cfg.kind == SWD_KIND_OSD_WINDOW) { st = osd_reserve_outputs(&d->ow, B, d->n); if (st) { set_err("osd output alloc failed"); return st; } }
+    if (d->cfg.kind == SWD_KIND_OSD_WINDOW) { st = osd_reserve_outputs(&d->ow, B, d->n, s); if (st) { set_err("osd output alloc failed"); return st; } }
     for (long long b0 = 0; b0 < B; b0 += d->cap) {
         const long long nb = std::min<long long>(d->cap, B - b0);
         st = launch_chunk(d, d_synd + b0 * d->m, nb, d_corr + b0 * d->n, d_conv + b0, d_pm ? d_pm + b0 : nullptr, s, b0);
@@ -1059,9 +1070,9 @@ extern "C" int swd_bp4_rank(swd_bp4 *b, int which) { return !b ? -1 : (which == 
 
 // OSD-only pass of an osd_window-kind decoder: ranking keys are supplied, converged shots are skipped
 static int bp4_osd_pass(swd_decoder *d, const u8 *d_synd, const double *d_keys, const u8 *d_conv, long long B, u8 *d_tmp, cudaStream_t s) {
-    int st = alloc_workspace(d, B);
+    int st = alloc_workspace(d, B, s);
     if (st) return st;
-    if ((st = osd_reserve_outputs(&d->ow, B, d->n))) { set_err("osd output alloc failed"); return SWD_ERR_NOMEM; }
+    if ((st = osd_reserve_outputs(&d->ow, B, d->n, s))) { set_err("osd output alloc failed"); return SWD_ERR_NOMEM; }
     for (long long b0 = 0; b0 < B; b0 += d->cap) {
         const long long nb = std::min<long long>(d->cap, B - b0);
         CK(cudaMemsetAsync(d->ws.counters, 0, 64 * sizeof(int), s));

@@ -37,7 +37,7 @@ struct OsdWork {
 static inline size_t osd_bytes_per_shot(int m, int n) { return 2; }   // need_osd[cap] + in_list[cap]
 static inline void osd_bind(OsdWork *ow, unsigned char *base, long long cap, int m, int n) { ow->need_osd = base; }
 
-static inline int osd_reserve_outputs(OsdWork *ow, long long B, int n) {
+static inline int osd_reserve_outputs(OsdWork *ow, long long B, int n, cudaStream_t s) {
     if (B <= ow->out_cap) return 0;
     if (ow->bp_dec) { cudaFree(ow->bp_dec); cudaFree(ow->osd0); cudaFree(ow->osdw); cudaFree(ow->lpr); cudaFree(ow->bp_iter); ow->bp_dec = nullptr; }
     if (cudaMalloc(&ow->bp_dec, (size_t)B * n) != cudaSuccess) return -4;
@@ -45,7 +45,9 @@ static inline int osd_reserve_outputs(OsdWork *ow, long long B, int n) {
     if (cudaMalloc(&ow->osdw, (size_t)B * n) != cudaSuccess) return -4;
     if (cudaMalloc(&ow->lpr, (size_t)B * n * 32) != cudaSuccess) return -4;
     if (cudaMalloc(&ow->bp_iter, (size_t)B * 4) != cudaSuccess) return -4;
-    cudaMemset(ow->osd0, 0, (size_t)B * n); cudaMemset(ow->osdw, 0, (size_t)B * n); cudaMemset(ow->bp_dec, 0, (size_t)B * n);
+    // zero-fill on the caller's stream: the kernels that write these buffers run there (a legacy-stream memset would not be
+    // ordered against a non-blocking stream)
+    cudaMemsetAsync(ow->osd0, 0, (size_t)B * n, s); cudaMemsetAsync(ow->osdw, 0, (size_t)B * n, s); cudaMemsetAsync(ow->bp_dec, 0, (size_t)B * n, s);
     ow->out_cap = B;
     return 0;
 }
@@ -460,18 +462,20 @@ osd_kernel(GraphDev g, const u8 *__restrict__ synd, Workspace ws, SubLayout L, G
 // finish: scatter post-BP results of converged shots, converge flags (BP only, osd_window.pyx:189)
 // ----------------------------------------------------------------------------------------------
 __global__ void osd_finish_kernel(Workspace ws, SubLayout L, GdgDev P, OsdWork ow, int n, u8 *__restrict__ dec_out,
-                                  u8 *__restrict__ conv_out, long long chunk_base) {
+                                  u8 *__restrict__ conv_out, long long chunk_base, int no_osd) {
     const int T = blockDim.x, tid = threadIdx.x;
     const int count = ws.counters[0];
     for (int slot = blockIdx.x; slot < count; slot += gridDim.x) {
         const unsigned char *gblob = ws.blob + (size_t)slot * L.blob_bytes;
         const BlobHeader gh = *(const BlobHeader *)gblob;
         const u16 *col = (const u16 *)(gblob + L.off_col);
-        if (gh.status == 0 && !ow.need_osd[slot]) {
+        // no_osd (osd_order = -1, "BP only", osd_window.pyx:192,199): a shot whose post-BP did not converge returns its
+        // bp_decoding with converge = 0
+        if (gh.status == 0 && (no_osd || !ow.need_osd[slot])) {
             const u8 *rec = ws.rec + (size_t)slot * P.n_rec * P.rec_stride;
             const u32 *bits = (const u32 *)(rec + sizeof(RecHeader));
             for (int j = tid; j < L.nn; j += T) dec_out[(size_t)gh.shot * n + col[j]] = (u8)((bits[j >> 5] >> (j & 31)) & 1u);
-            if (tid == 0) conv_out[gh.shot] = 1;
+            if (tid == 0 && !ow.need_osd[slot]) conv_out[gh.shot] = 1;
         } else if (gh.status != 0) {
             // decimation / peeling contradiction: bp_decoding is what decode() returned (osd_window.pyx:179-186)
             for (int v = tid; v < n; v += T) ow.bp_dec[(size_t)(chunk_base + gh.shot) * n + v] = dec_out[(size_t)gh.shot * n + v];
@@ -593,8 +597,8 @@ static inline int osd_launch(const GraphDev &g, const u8 *d_synd, const Workspac
         if (capA < L.es_max) { post<<<grid3B, T3, smem3B, s>>>(ws, L, LsB, PSB, P, g.n, ow, chunk_base, 1, capA, d_corr); *launches += 1; }
         return cudaGetLastError() == cudaSuccess ? 0 : -3;
     }
-    osd_kernel<<<grid5, T5, OS.total, s>>>(g, d_synd, ws, L, P, OS, ow, method, order_w, rank, d_corr, d_pm, chunk_base);
-    osd_finish_kernel<<<grid5, 128, 0, s>>>(ws, L, P, ow, g.n, d_corr, d_conv, chunk_base);
+    if (order_w >= 0) osd_kernel<<<grid5, T5, OS.total, s>>>(g, d_synd, ws, L, P, OS, ow, method, order_w, rank, d_corr, d_pm, chunk_base);
+    osd_finish_kernel<<<grid5, 128, 0, s>>>(ws, L, P, ow, g.n, d_corr, d_conv, chunk_base, order_w < 0 ? 1 : 0);
     cudaMemsetAsync(in_list, 0, (size_t)B, s);
     osd_mark_list_kernel<<<64, 256, 0, s>>>(ws, in_list);
     osd_pm_kernel<<<(unsigned)((B + 7) / 8 < 1 ? 1 : ((B + 7) / 8 > 65535 ? 65535 : (B + 7) / 8)), 256, 0, s>>>(g.llr, g.n, d_corr, d_conv, B, d_pm, ow, chunk_base, in_list);

@@ -22,14 +22,30 @@ struct StreamWs {
     long long G;        // shots per tile = threads of the launch
 };
 
+// Memory-level parallelism is what this kernel lives on.  Both passes read the messages in a sequence that is known in
+// advance (check pass: CSR positions 0, 1, 2, ...; variable pass: cpos[0], cpos[1], ...), so every thread keeps SWD_SK
+// asynchronous 8-byte copies (cp.async, LDGSTS) in flight into its own ring of shared-memory slots, SWD_SK edges ahead of
+// the one it is working on: a warp has 16 coalesced 256-byte lines outstanding all the time instead of one batch per
+// variable node (ncu: first version 7 % of the HBM roof, register-batched loads 27 %).  A thread only ever reads the slots
+// it filled itself, so there is no barrier and no mbarrier - cp.async.wait_group orders each copy before its use.
+#define SWD_SK 16
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int DM>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
 pre_bp_stream_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, long long tile_base, int max_iter, double alpha,
                      StreamWs sw, int full_hist, u64 *stats) {
+    constexpr int K = SWD_SK;
     extern __shared__ __align__(16) unsigned char smem[];
     const int T = blockDim.x, tid = threadIdx.x;
-    const int m = g.m, n = g.n, MW = (m + 31) >> 5;
-    u32 *s_synd = (u32 *)smem;                 // [MW][T]
+    const int m = g.m, n = g.n, nnz = g.nnz, MW = (m + 31) >> 5;
+    double *ring = (double *)smem + tid;       // [K][T] doubles: slot s of this thread = ring[s * T]
+    u32 *s_synd = (u32 *)(smem + (size_t)8 * K * T);   // [MW][T]
     u32 *s_par = s_synd + (size_t)MW * T;      // [MW][T]
     const long long gid = (long long)blockIdx.x * T + tid;
     const long long shot = tile_base + gid;
@@ -50,69 +66,89 @@ pre_bp_stream_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, long 
     u64 edge_passes = 0;
     for (int it = 0; it < max_iter; it++) {
         if (__all_sync(FULLMASK, done)) break;
+        if (done) continue;
         // ---- check pass: min1 / min2 / argmin / parity (pyx:62-96); iteration 1 reads the priors (pyx:55-60)
-        if (!done) {
-            for (int r = 0; r < m; r++) {
-                const int p0 = __ldg(g.rp + r), p1 = __ldg(g.rp + r + 1);
-                double m1 = SWD_BIG, m2 = SWD_BIG; int arg = -1;
-                u32 par = (s_synd[(r >> 5) * T + tid] >> (r & 31)) & 1u;
-                u64 neg = 0;
-#pragma unroll 8
-                for (int p = p0; p < p1; p++) {
-                    const double b = (it == 0) ? __ldg(g.llr + __ldg(g.rc + p)) : msg[(size_t)p * G];
-                    double a = fabs(b);
-                    a = (a > SWD_CLIP) ? SWD_CLIP : a;
-                    const bool lt = a < m1;
-                    const double hi = lt ? m1 : a;
-                    m2 = (hi < m2) ? hi : m2;
-                    m1 = lt ? a : m1;
-                    arg = lt ? p : arg;
-                    const u32 ng = (u32)(b <= 0.0);
-                    par ^= ng;
-                    if (p - p0 < 64) neg |= (u64)ng << (p - p0);
+        if (it > 0) {
+#pragma unroll
+            for (int i = 0; i < K; i++) { if (i < nnz) cp_async8(ring + i * T, msg + (size_t)i * G); cp_async_commit(); }
+        }
+        for (int r = 0; r < m; r++) {
+            const int p0 = __ldg(g.rp + r), p1 = __ldg(g.rp + r + 1);
+            double m1 = SWD_BIG, m2 = SWD_BIG; int arg = -1;
+            u32 par = (s_synd[(r >> 5) * T + tid] >> (r & 31)) & 1u;
+            u64 neg = 0;
+#pragma unroll 4
+            for (int p = p0; p < p1; p++) {
+                double b;
+                if (it == 0) b = __ldg(g.llr + __ldg(g.rc + p));
+                else {
+                    cp_async_wait<K - 1>();
+                    b = ring[(p & (K - 1)) * T];
+                    if (p + K < nnz) cp_async8(ring + (p & (K - 1)) * T, msg + (size_t)(p + K) * G);
+                    cp_async_commit();
                 }
-                const double q1 = m1 * alpha, q2 = m2 * alpha;
-#pragma unroll 8
-                for (int p = p0; p < p1; p++) {
-                    u32 ng;
-                    if (p - p0 < 64) ng = (u32)((neg >> (p - p0)) & 1ull);
-                    else ng = (u32)(((it == 0) ? __ldg(g.llr + __ldg(g.rc + p)) : msg[(size_t)p * G]) <= 0.0);
-                    msg[(size_t)p * G] = flip_sign((p == arg) ? q2 : q1, par ^ ng);
-                }
+                double a = fabs(b);
+                a = (a > SWD_CLIP) ? SWD_CLIP : a;
+                const bool lt = a < m1;
+                const double hi = lt ? m1 : a;
+                m2 = (hi < m2) ? hi : m2;
+                m1 = lt ? a : m1;
+                arg = lt ? p : arg;
+                const u32 ng = (u32)(b <= 0.0);
+                par ^= ng;
+                if (p - p0 < 64) neg |= (u64)ng << (p - p0);
+            }
+            const double q1 = m1 * alpha, q2 = m2 * alpha;
+#pragma unroll 4
+            for (int p = p0; p < p1; p++) {
+                u32 ng;
+                if (p - p0 < 64) ng = (u32)((neg >> (p - p0)) & 1ull);
+                else ng = (u32)(((it == 0) ? __ldg(g.llr + __ldg(g.rc + p)) : msg[(size_t)p * G]) <= 0.0);   // rows longer than 64: re-read (not yet overwritten)
+                msg[(size_t)p * G] = flip_sign((p == arg) ? q2 : q1, par ^ ng);
             }
         }
+        cp_async_wait<0>();
         // ---- variable pass: ordered prefix / suffix sums (pyx:98-127), hard decisions, parity of H * e
-        if (!done) {
-            for (int w = 0; w < MW; w++) s_par[w * T + tid] = 0;
-            const bool keep = full_hist || (it >= max_iter - 4);
-            double *hs = sw.hs + ((size_t)(it & 3) * n) * G + gid;
-            u32 decw = 0;
-            for (int v = 0; v < n; v++) {
-                const int e0 = __ldg(g.cp + v), d = __ldg(g.cp + v + 1) - e0;
-                double cc[DM], pre[DM]; int pp[DM];
-                double t = __ldg(g.llr + v);
+        for (int w = 0; w < MW; w++) s_par[w * T + tid] = 0;
+        const bool keep = full_hist || (it >= max_iter - 4);
+        double *hs = sw.hs + ((size_t)(it & 3) * n) * G + gid;
+        u32 decw = 0;
 #pragma unroll
-                for (int k = 0; k < DM; k++) if (k < d) { pp[k] = __ldg(g.cpos + e0 + k); cc[k] = msg[(size_t)pp[k] * G]; }
+        for (int i = 0; i < K; i++) { if (i < nnz) cp_async8(ring + i * T, msg + (size_t)__ldg(g.cpos + i) * G); cp_async_commit(); }
+        for (int v = 0; v < n; v++) {
+            const int e0 = __ldg(g.cp + v), d = __ldg(g.cp + v + 1) - e0;
+            double cc[DM], pre[DM]; int pp[DM];
+            double t = __ldg(g.llr + v);
 #pragma unroll
-                for (int k = 0; k < DM; k++) if (k < d) { pre[k] = t; t += cc[k]; }
-                const u32 hard = (u32)(t <= 0.0);
-                decw |= hard << (v & 31);
-                if ((v & 31) == 31 || v == n - 1) { sw.decw[(size_t)(v >> 5) * G + gid] = decw; decw = 0; }
-                if (hard) {
-#pragma unroll 1
-                    for (int k = 0; k < d; k++) { const int r = __ldg(g.cr + e0 + k); s_par[(r >> 5) * T + tid] ^= 1u << (r & 31); }
+            for (int k = 0; k < DM; k++) {
+                if (k < d) {
+                    const int e = e0 + k;
+                    pp[k] = __ldg(g.cpos + e);
+                    cp_async_wait<K - 1>();
+                    cc[k] = ring[(e & (K - 1)) * T];
+                    if (e + K < nnz) cp_async8(ring + (e & (K - 1)) * T, msg + (size_t)__ldg(g.cpos + e + K) * G);
+                    cp_async_commit();
+                    pre[k] = t; t += cc[k];
                 }
-                double s = 0.0;
-#pragma unroll
-                for (int k = DM - 1; k >= 0; k--) if (k < d) { msg[(size_t)pp[k] * G] = pre[k] + s; s += cc[k]; }
-                if (keep) hs[(size_t)v * G] = t;
             }
-            iters = it + 1;
-            edge_passes++;
-            u32 mism = 0;
-            for (int w = 0; w < MW; w++) mism |= s_par[w * T + tid] ^ s_synd[w * T + tid];
-            if (!mism) { conv = 1; done = true; }
+            const u32 hard = (u32)(t <= 0.0);
+            decw |= hard << (v & 31);
+            if ((v & 31) == 31 || v == n - 1) { sw.decw[(size_t)(v >> 5) * G + gid] = decw; decw = 0; }
+            if (hard) {
+#pragma unroll 1
+                for (int k = 0; k < d; k++) { const int r = __ldg(g.cr + e0 + k); s_par[(r >> 5) * T + tid] ^= 1u << (r & 31); }
+            }
+            double s = 0.0;
+#pragma unroll
+            for (int k = DM - 1; k >= 0; k--) if (k < d) { msg[(size_t)pp[k] * G] = pre[k] + s; s += cc[k]; }
+            if (keep) hs[(size_t)v * G] = t;
         }
+        cp_async_wait<0>();
+        iters = it + 1;
+        edge_passes++;
+        u32 mism = 0;
+        for (int w = 0; w < MW; w++) mism |= s_par[w * T + tid] ^ s_synd[w * T + tid];
+        if (!mism) { conv = 1; done = true; }
     }
     if (live) { sw.itdone[gid] = iters; sw.conv[gid] = (u8)conv; }
     // work counter: edge-iterations (warp-reduced)

@@ -379,8 +379,9 @@ class bp4_osd:
         px, py, pz = kwargs.get("channel_probs_x"), kwargs.get("channel_probs_y"), kwargs.get("channel_probs_z")
         if px is None or py is None or pz is None:
             raise TypeError("channel_probs_x, channel_probs_y and channel_probs_z are required")
-        if len(px) != self.n:
+        if len(px) != self.n or len(py) != self.n or len(pz) != self.n:     # the reference checks px only (bp4_osd.pyx:40-42) and reads past py / pz
             raise ValueError(f"The length of the channel probability vector must be eqaul to the block length n={self.n}.")
+        self._device = int(kwargs.get("device", 0))
         osd_method = kwargs.get("osd_method", "osd_0")
         key = str(osd_method).lower()
         if key not in _OSD_METHODS:
@@ -457,6 +458,9 @@ class bp4_osd:
         sx = synd_x.to(torch.uint8).contiguous(); sz = synd_z.to(torch.uint8).contiguous()
         if sx.dim() != 2 or sz.dim() != 2 or sx.shape[1] != self.mx or sz.shape[1] != self.mz or sx.shape[0] != sz.shape[0]:
             raise ValueError(f"expected syndromes of shape [B, {self.mx}] and [B, {self.mz}]")
+        dev_index = getattr(self, "_device", 0)
+        if sx.device.index != dev_index or sz.device.index != dev_index:
+            raise ValueError(f"syndromes live on cuda:{sx.device.index} / cuda:{sz.device.index}, decoder on cuda:{dev_index}")
         B, n, dev = sx.shape[0], self.n, sx.device
         dec = torch.empty((B, 2, n), dtype=torch.uint8, device=dev); conv = torch.empty(B, dtype=torch.uint8, device=dev)
         lpr = torch.empty((B, n, 3), dtype=torch.float64, device=dev); it = torch.empty(B, dtype=torch.int32, device=dev)

@@ -133,6 +133,24 @@ def global144_section(bpgdg_decoder, osd_window, bpgd_decoder):
     save("g144_gdg_mt1", chk, pri, s[:24], kw, dec=d, conv=c)
 
 
+def noosd_section(osd_window):
+    """osd_order = -1 ("BP only", osd_window.pyx:86,192): a [[72,12,6]] (3,1) middle window with a short post-BP so that a
+    good part of the shots ends without convergence - decode() then returns bp_decoding with converge = 0."""
+    from slidingwindowdecoder_b200.codes import bb_code
+    from slidingwindowdecoder_b200.dem import bb_memory_circuit, detector_error_model, dem_to_check_matrices
+    from slidingwindowdecoder_b200.windows import build_windows
+    from slidingwindowdecoder_b200.sliding_window import sample_dem
+    code, A, B = bb_code(72)
+    chk, obs, pri = dem_to_check_matrices(detector_error_model(bb_memory_circuit(code, A, B, 0.005, 6, z_basis=True)))
+    plan = build_windows(chk, obs, pri, code.N, W=3, F=1, method=1)
+    det, ob, _ = sample_dem(plan.chk, plan.obs, plan.priors, 3000, np.random.default_rng(7272))
+    w = plan.windows[1]
+    s = det[:, w.row0:w.row1]
+    s = s[np.nonzero(s.any(axis=1))[0][:500]]
+    kw = dict(pre_max_iter=8, post_max_iter=12, ms_scaling_factor=1.0, osd_method="osd_cs", osd_order=-1)
+    save("c2_w1_osdw_noosd", w.mat, w.prior, s, kw, **run_osd(osd_window, w.mat, w.prior, s, kw))
+
+
 def c3_extra_section(bpgdg_decoder, bpgd_decoder):
     """More of the headline configuration's middle window (216 x 1728): single-thread GDG schedule and BPGD."""
     from slidingwindowdecoder_b200.codes import bb_code
@@ -234,6 +252,12 @@ def main():
         from src.osd_window import osd_window
         c4_section(bpgdg_decoder, osd_window)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "noosd":
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 2)
+        from src.osd_window import osd_window
+        noosd_section(osd_window)
+        return
     if len(sys.argv) > 1 and sys.argv[1] in ("g144", "c3x"):
         devnull = os.open(os.devnull, os.O_WRONLY)
         os.dup2(devnull, 2)
@@ -327,6 +351,7 @@ def main():
     c4_section(bpgdg_decoder, osd_window)
     c3_extra_section(bpgdg_decoder, bpgd_decoder)
     global144_section(bpgdg_decoder, osd_window, bpgd_decoder)
+    noosd_section(osd_window)
     bp4_section()
     camel_section()
 

@@ -1,4 +1,6 @@
 """The CPU oracle against golden vectors recorded from the real reference (tests/golden/make_golden.py)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -68,6 +70,17 @@ def test_osd_window_matches_reference(name, oracle_mod):
         r = orc.osd_window(g["synd"][i], **g["kwargs"])
         if r["bp_iteration"] >= 4:
             assert np.array_equal(r["log_prob_ratios"], g["lpr_first8"][i]), i
+
+
+def test_osd_window_bp_only_matches_reference(oracle_mod):
+    """osd_order = -1 (osd_window.pyx:86,192 "BP only"): no OSD stage, a non-converged shot returns bp_decoding, converge 0."""
+    g = load_golden("c2_w1_osdw_noosd")
+    assert g["kwargs"]["osd_order"] == -1 and 0 < g["conv"].sum() < len(g["conv"])
+    orc = oracle_mod.Oracle(g["mat"], g["priors"])
+    for i, s in enumerate(g["synd"]):
+        r = orc.osd_window(s, **g["kwargs"])
+        assert r["converge"] == g["conv"][i] and r["bp_iteration"] == g["bp_iteration"][i] and r["min_pm"] == g["min_pm"][i], i
+        assert np.array_equal(r["dec"].astype(np.uint8), g["dec"][i]) and np.array_equal(r["bp_decoding"].astype(np.uint8), g["bp_decoding"][i]), i
 
 
 def test_uniform_prior_statistics(oracle_mod):
@@ -158,3 +171,36 @@ def test_bp4_camel_decode_matches_reference(name, oracle_mod):
         assert o["min_pm"] == g["min_pm"][i]
         if i < 16:
             assert np.array_equal(o["log_prob_ratios"], g["lpr_first16"][i])
+
+
+def test_port_equals_compiled_reference_do_work_on_a_headline_window(oracle_mod):
+    """oracle/_ref (the reference's own bpgd.cpp / mod2sparse.c compiled in place: the REAL threaded
+    BPGD_main_thread::do_work, bpgd.cpp:591-688) against the C port on a [[144,12,12]] (3,1) window of the headline
+    configuration: same converge flags, same corrections except exact path-metric ties (thread timing decides those in the
+    reference).  Skipped where oracle/_ref is not built."""
+    import ctypes as C
+    if oracle_mod.ref_lib() is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    lib = oracle_mod.ref_lib()
+    g = load_golden("c3_w5_gdg_mt1")
+    orc = oracle_mod.Oracle(g["mat"], g["priors"])
+    synd = g["synd"][:200]
+    kw = dict(max_iter=8, max_iter_per_step=6, max_step=25, max_tree_depth=3, max_side_depth=10, max_tree_branch_step=10, max_side_branch_step=10)
+    lib.ref_gdg_create.restype = C.c_void_p
+    _p = oracle_mod._p
+    h = C.c_void_p(lib.ref_gdg_create(orc.m, orc.n, _p(orc.cp, C.c_int), _p(orc.cr, C.c_int), _p(orc.llr, C.c_double), kw["max_iter"],
+                                      C.c_double(1.0), kw["max_iter_per_step"], kw["max_step"], kw["max_tree_depth"], kw["max_side_depth"],
+                                      kw["max_tree_branch_step"], kw["max_side_branch_step"], C.c_double(1.0), 0, 0))
+    s8 = np.ascontiguousarray(synd.astype(np.int8))
+    dec = np.zeros((len(s8), orc.n), dtype=np.int8); conv = np.zeros(len(s8), dtype=np.int8)
+    devnull = os.open(os.devnull, os.O_WRONLY); saved = os.dup(2); os.dup2(devnull, 2)      # "Error setting thread affinity" on small hosts
+    try:
+        lib.ref_gdg_decode_batch(h, _p(s8, C.c_int8), C.c_longlong(len(s8)), _p(dec, C.c_int8), _p(conv, C.c_int8))
+    finally:
+        os.dup2(saved, 2); os.close(devnull); os.close(saved)
+    o_dec, o_conv, o_pm, _ = orc.bpgdg_batch(synd, multi_thread=True, **kw)
+    assert np.array_equal(conv.astype(np.uint8), o_conv.astype(np.uint8))
+    assert np.array_equal(conv.astype(np.uint8), g["conv"][:200])                     # and both equal the Cython-level golden
+    gg = dict(g); gg["dec"] = dec.astype(np.uint8); gg["synd"] = synd
+    bad = np.nonzero((o_dec.astype(np.uint8) != dec.astype(np.uint8)).any(axis=1))[0]
+    check_only_ties(gg, orc, o_dec, o_conv, o_pm, bad, "oracle/_ref vs port")
