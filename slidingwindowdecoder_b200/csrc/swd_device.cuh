@@ -507,6 +507,7 @@ struct Ctx {
     u8 *cn_deg, *flip;
     u32 *upar;
     double *red_d; int *red_i; int *misc;
+    int zslot;                          // index (relative to msg) of a shared-memory double that always holds +0.0
 };
 
 // ownership: slot (tid, i) -> sorted index; odd rounds run backwards so that every warp gets a mix of
@@ -714,14 +715,28 @@ __device__ __forceinline__ void check_update(Ctx &c, int p0, int len, int cm, do
 
 // one variable-node update (bpgd.cpp:151-182) for a VN of degree d <= DM: returns the posterior, writes the hard
 // decision, the parity contributions and the new bit-to-check messages
+#ifndef SWD_VNZ
+#define SWD_VNZ 0           /* measured -1.7 % (A/B r2): the select per edge costs more than the four predicated selects it removes */
+#endif
 template <int DM>
 __device__ __forceinline__ double vn_update(Ctx &c, const int j, const int e0, const int d, const int dw) {
     double cc[DM], pre[DM]; int pp[DM];
     double t = c.prior[j];
+#if SWD_VNZ
+    // The loop bound dw is the warp's largest degree; a VN of smaller degree reads a constant +0.0 slot for its missing
+    // edges: adding +0.0 changes no partial sum (bpgd.cpp:151-182 skips those edges), so the prefix sums need no
+    // per-edge predicate / select - only the store keeps one.
+    const int zslot = c.zslot;
+#pragma unroll
+    for (int k = 0; k < DM; k++) { if (k >= dw) break; const int p = c.vpos[e0 + k]; pp[k] = (k < d) ? p : zslot; cc[k] = c.msg[pp[k]]; }
+#pragma unroll
+    for (int k = 0; k < DM; k++) { if (k >= dw) break; pre[k] = t; t += cc[k]; }
+#else
 #pragma unroll
     for (int k = 0; k < DM; k++) { if (k >= dw) break; if (k < d) { pp[k] = c.vpos[e0 + k]; cc[k] = c.msg[pp[k]]; } }
 #pragma unroll
     for (int k = 0; k < DM; k++) { if (k >= dw) break; if (k < d) { pre[k] = t; t += cc[k]; } }
+#endif
     const int hard = (t <= 0.0);
     c.error[j] = (i8)hard;
     if (hard) {
@@ -750,7 +765,29 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
     //      aliases `dec`, which is only live inside select_vn.
     u16 *alist = (u16 *)c.dec;
     int na = 0;
-    {
+#ifndef SWD_ALIST1
+#define SWD_ALIST1 1
+#endif
+    if (SWD_ALIST1 && T == 128 && c.m <= 256) {
+        // small windows: every warp takes the ballots of all <= 8 words of ranks itself, so the offsets need no exchange
+        // through shared memory and the list is complete after ONE barrier (same order: rank-ascending)
+        const int lane = tid & 31, wid = tid >> 5;
+        u32 my0 = 0, my1 = 0; int off0 = 0, off1 = 0, run = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const int q = w * 32 + lane;
+            const bool act = (q < c.m) && (c.cn_mask[c.cperm[q]] >= 0);
+            const u32 b = __ballot_sync(FULLMASK, act);
+            if (w == wid) { my0 = b; off0 = run; }
+            if (w == 4 + wid) { my1 = b; off1 = run; }
+            run += __popc(b);
+        }
+        const u32 below = (1u << lane) - 1u;
+        if ((my0 >> lane) & 1u) alist[off0 + __popc(my0 & below)] = (u16)tid;
+        if ((my1 >> lane) & 1u) alist[off1 + __popc(my1 & below)] = (u16)(128 + tid);
+        na = run;
+        __syncthreads();
+    } else {
         const int lane = tid & 31, wid = tid >> 5, nw = (T + 31) >> 5;
         int *wcnt = (int *)c.red_d;                           // [SWD_CPT * nw] <= 128 ints = the 512 bytes of red_d
         u32 bal[SWD_CPT];
@@ -786,6 +823,14 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
         if (k < na) { const int q = alist[k]; my_cn++; my_slots += (u32)(c.coff[q + 1] - c.coff[q]); }
     }
     int it = 0, conv = 0;
+#ifndef SWD_MISM_SMEM
+#define SWD_MISM_SMEM 1
+#endif
+    // convergence flag of an iteration: a shared-memory word that any check thread with a mismatching row sets (cleared
+    // during the previous variable pass) instead of an OR-reduction barrier over a per-thread accumulator
+    // Two words, alternating by iteration parity: the word of iteration `it` is cleared by thread 0 after the barrier of
+    // iteration it + 1 - behind every read of it (those precede the variable pass of `it`) and ahead of every set of it + 2.
+    if (SWD_MISM_SMEM && tid == 0) { c.misc[5] = 0; c.misc[6] = 0; }     // published by the first barrier of the loop; the first set comes two barriers later
     for (;; it++) {
         // ---- check pass (+ convergence test of the previous iteration)
         int mism = 0;
@@ -800,7 +845,7 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
             if (it > 0) {
                 const int f = (c.upar[r] != (u32)cm);
                 c.flip[r] = (u8)f;
-                mism |= f;
+                if (SWD_MISM_SMEM) { if (f) c.misc[5 + (it & 1)] = 1; } else mism |= f;
             }
             c.upar[r] = 0;
             if (last) continue;
@@ -808,7 +853,11 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
         }
         if (it > 0) {
             // a check that lost all its columns at reset while its syndrome bit is 1 (bad_rows) can never be satisfied
-            if (!__syncthreads_or(mism) && !c.bad_rows) { conv = 1; break; }
+            if (SWD_MISM_SMEM) {
+                __syncthreads();
+                if (c.misc[5 + (it & 1)] == 0 && !c.bad_rows) { conv = 1; break; }
+                if (tid == 0) c.misc[5 + ((it & 1) ^ 1)] = 0;
+            } else if (!__syncthreads_or(mism) && !c.bad_rows) { conv = 1; break; }
         } else __syncthreads();
         if (last) break;
         // ---- variable pass: ordered prefix / suffix sums (bpgd.cpp:151-182); predicated straight-line code per slot.

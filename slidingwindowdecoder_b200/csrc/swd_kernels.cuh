@@ -484,6 +484,8 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
     c.cn_mask = pinned_smem<i8>(st + S.off_cnmask); c.cn_deg = st + S.off_cndeg; c.flip = pinned_smem<u8>(st + S.off_flip);
     c.upar = pinned_smem<u32>(st + S.off_upar);
     c.red_d = (double *)(st + S.off_red); c.red_i = (int *)(c.red_d + 64); c.misc = (int *)(st + S.off_misc);
+    c.zslot = (int)((double *)(st + S.off_misc + 48) - c.msg);      // misc[12..13]: the constant +0.0 of vn_update
+    if (threadIdx.x == 0) *(double *)(st + S.off_misc + 48) = 0.0;
 #if !SWD_DIET
     i8 *bvn = (i8 *)(st + S.off_bvn); i8 *bcn = (i8 *)(st + S.off_bcn); u8 *bdeg = st + S.off_bdeg;
 #endif
