@@ -392,10 +392,10 @@ static int setup_kernels(swd_decoder *d) {
         // messages streamed from HBM, one thread per shot (swd_stream.cuh); syndrome + parity bit words per thread in shared memory
         if (ps) { set_err("product-sum BP: window graph does not fit in shared memory (nnz too large)"); return SWD_ERR_UNSUPPORTED; }
         const int MW = (m + 31) / 32;
-        // shared memory per thread: the cp.async ring (SWD_SK doubles) + syndrome and parity bit words; two CTAs per SM
-        int ts = 256; while (ts > 32 && (size_t)(8 * MW + 8 * SWD_SK) * ts > 110 * 1024) ts -= 32;
-        if ((size_t)(8 * MW + 8 * SWD_SK) * ts > 110 * 1024) { set_err("window graph has too many checks for the streamed BP kernel"); return SWD_ERR_UNSUPPORTED; }
-        d->stream_mode = true; d->Ts = ts; d->stream_smem = (size_t)(8 * MW + 8 * SWD_SK) * ts;
+        // shared memory per thread: the cp.async ring (SWD_SK doubles) + parity bit words; two CTAs per SM
+        int ts = 256; while (ts > 32 && (size_t)(4 * MW + 8 * SWD_SK) * ts > (SWD_STREAM_MINB >= 3 ? 72 : 110) * 1024) ts -= 32;
+        if ((size_t)(4 * MW + 8 * SWD_SK) * ts > 110 * 1024) { set_err("window graph has too many checks for the streamed BP kernel"); return SWD_ERR_UNSUPPORTED; }
+        d->stream_mode = true; d->Ts = ts; d->stream_smem = (size_t)(4 * MW + 8 * SWD_SK) * ts;
         S1.total = 0;
     }
     // staged static graph info (per-slot records + CSC->CSR map) if it still fits next to the messages
@@ -605,8 +605,13 @@ static int stream_pre_bp(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_co
     const int Ts = d->Ts, n = d->n;
     size_t budget = (size_t)48 << 30;
     if (const char *e = getenv("SWD_STREAM_BYTES")) budget = (size_t)atoll(e);
-    const size_t per_shot = (size_t)8 * (d->nnz + 4 * (size_t)n) + 4 * (size_t)((n + 31) / 32) + 8;
-    long long Gmax = (long long)d->num_sm * Ts * 2;                               // two CTAs per SM
+    const size_t per_shot = (size_t)8 * (d->nnz + 4 * (size_t)n) + 4 * (size_t)((n + 31) / 32) + 4 * (size_t)((d->m + 31) / 32) + 8;
+    typedef void (*sfn_t)(GraphDev, const u8 *, long long, long long, int, double, StreamWs, int, u64 *);
+    sfn_t fn = d->max_col_deg <= 6 ? pre_bp_stream_kernel<6> : (d->max_col_deg <= 8 ? pre_bp_stream_kernel<8> : pre_bp_stream_kernel<16>);
+    int socc = 0;
+    { int st = occupancy(fn, Ts, d->stream_smem, &socc); if (st) return st; }
+    if (socc < 1) { set_err("pre_bp_stream_kernel does not fit"); return SWD_ERR_UNSUPPORTED; }
+    long long Gmax = (long long)d->num_sm * Ts * socc;                            // a tile = one resident wave
     Gmax = std::max<long long>(Ts, std::min<long long>(Gmax, (long long)(budget / per_shot) / Ts * Ts));
     const long long want = std::min<long long>(Gmax, (B + Ts - 1) / Ts * Ts);
     if (want > d->sw_G) {
@@ -617,17 +622,15 @@ static int stream_pre_bp(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_co
         const size_t o_msg = o; o += a256((size_t)8 * d->nnz * want);
         const size_t o_hs = o; o += a256((size_t)32 * n * want);
         const size_t o_dec = o; o += a256((size_t)4 * ((n + 31) / 32) * want);
+        const size_t o_sy = o; o += a256((size_t)4 * ((d->m + 31) / 32) * want);
         const size_t o_it = o; o += a256((size_t)4 * want);
         const size_t o_cv = o; o += a256((size_t)want);
         if (cudaMalloc(&d->sw_block, o) != cudaSuccess) { set_err("streamed-BP message buffer cudaMalloc failed"); return SWD_ERR_NOMEM; }
         unsigned char *b = (unsigned char *)d->sw_block;
         d->sw.msg = (double *)(b + o_msg); d->sw.hs = (double *)(b + o_hs); d->sw.decw = (u32 *)(b + o_dec);
-        d->sw.itdone = (int *)(b + o_it); d->sw.conv = b + o_cv;
+        d->sw.itdone = (int *)(b + o_it); d->sw.conv = b + o_cv; d->sw.syndw = (u32 *)(b + o_sy);
         d->sw_G = want;
     }
-    typedef void (*sfn_t)(GraphDev, const u8 *, long long, long long, int, double, StreamWs, int, u64 *);
-    sfn_t fn = d->max_col_deg <= 6 ? pre_bp_stream_kernel<6> : (d->max_col_deg <= 8 ? pre_bp_stream_kernel<8> : pre_bp_stream_kernel<16>);
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     for (long long t0 = 0; t0 < B; t0 += d->sw_G) {
         const long long nb = std::min<long long>(d->sw_G, B - t0);
         StreamWs sw = d->sw; sw.G = (nb + Ts - 1) / Ts * Ts;

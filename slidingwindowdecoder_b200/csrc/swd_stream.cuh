@@ -9,7 +9,7 @@
 // already converged (their lanes stop issuing loads and stores).  Per iteration and shot the kernel moves exactly the
 // algorithmic bytes of SURVEY 8(d): read E + write E in the check pass, read E + write E in the variable pass
 // (E * 32 bytes) plus 8 n bytes of posterior history - HBM is the roof that binds here.
-// The per-shot syndrome and the parity of the hard decisions are bit words in shared memory ([word][thread]).
+// The parity of the hard decisions is kept as bit words in shared memory ([word][thread]), the syndrome as bit words in HBM.
 #pragma once
 #include "swd_device.cuh"
 
@@ -17,6 +17,7 @@ struct StreamWs {
     double *msg;        // [nnz][G]
     double *hs;         // [4][n][G]   posterior ring (slot = iteration & 3)
     u32 *decw;          // [ceil(n/32)][G] hard decisions, bit v & 31 of word v >> 5
+    u32 *syndw;         // [ceil(m/32)][G] syndrome bit words
     int *itdone;        // [G] iterations executed
     u8 *conv;           // [G]
     long long G;        // shots per tile = threads of the launch
@@ -28,7 +29,12 @@ struct StreamWs {
 // the one it is working on: a warp has 16 coalesced 256-byte lines outstanding all the time instead of one batch per
 // variable node (ncu: first version 7 % of the HBM roof, register-batched loads 27 %).  A thread only ever reads the slots
 // it filled itself, so there is no barrier and no mbarrier - cp.async.wait_group orders each copy before its use.
-#define SWD_SK 16
+#ifndef SWD_SK
+#define SWD_SK 16          /* 32 measured 7 % slower: the ring is not what limits the lines in flight */
+#endif
+#ifndef SWD_STREAM_MINB
+#define SWD_STREAM_MINB 2
+#endif
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -37,7 +43,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int DM>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, SWD_STREAM_MINB)
 pre_bp_stream_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, long long tile_base, int max_iter, double alpha,
                      StreamWs sw, int full_hist, u64 *stats) {
     constexpr int K = SWD_SK;
@@ -45,13 +51,13 @@ pre_bp_stream_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, long 
     const int T = blockDim.x, tid = threadIdx.x;
     const int m = g.m, n = g.n, nnz = g.nnz, MW = (m + 31) >> 5;
     double *ring = (double *)smem + tid;       // [K][T] doubles: slot s of this thread = ring[s * T]
-    u32 *s_synd = (u32 *)(smem + (size_t)8 * K * T);   // [MW][T]
-    u32 *s_par = s_synd + (size_t)MW * T;      // [MW][T]
+    u32 *s_par = (u32 *)(smem + (size_t)8 * K * T);    // [MW][T] parity of H * e per check, bit words
     const long long gid = (long long)blockIdx.x * T + tid;
     const long long shot = tile_base + gid;
     const long long G = sw.G;
     const bool live = shot < B;
     double *msg = sw.msg + gid;
+    u32 *g_synd = sw.syndw + gid;              // [MW][G] syndrome bit words (HBM / L2: one coalesced word per 32 rows)
     // ---- syndrome bytes -> bit words
     for (int w = 0; w < MW; w++) {
         u32 word = 0;
@@ -59,7 +65,7 @@ pre_bp_stream_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, long 
             const int r1 = min(32, m - 32 * w);
             for (int b = 0; b < r1; b++) word |= (u32)(synd[shot * m + 32 * w + b] & 1u) << b;
         }
-        s_synd[w * T + tid] = word;
+        g_synd[(size_t)w * G] = word;
     }
     bool done = !live;
     int iters = 0, conv = 0;
@@ -72,10 +78,12 @@ pre_bp_stream_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, long 
 #pragma unroll
             for (int i = 0; i < K; i++) { if (i < nnz) cp_async8(ring + i * T, msg + (size_t)i * G); cp_async_commit(); }
         }
+        u32 sword = 0;
         for (int r = 0; r < m; r++) {
             const int p0 = __ldg(g.rp + r), p1 = __ldg(g.rp + r + 1);
             double m1 = SWD_BIG, m2 = SWD_BIG; int arg = -1;
-            u32 par = (s_synd[(r >> 5) * T + tid] >> (r & 31)) & 1u;
+            if ((r & 31) == 0) sword = g_synd[(size_t)(r >> 5) * G];
+            u32 par = (sword >> (r & 31)) & 1u;
             u64 neg = 0;
 #pragma unroll 4
             for (int p = p0; p < p1; p++) {
@@ -147,7 +155,7 @@ pre_bp_stream_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, long 
         iters = it + 1;
         edge_passes++;
         u32 mism = 0;
-        for (int w = 0; w < MW; w++) mism |= s_par[w * T + tid] ^ s_synd[w * T + tid];
+        for (int w = 0; w < MW; w++) mism |= s_par[w * T + tid] ^ g_synd[(size_t)w * G];
         if (!mism) { conv = 1; done = true; }
     }
     if (live) { sw.itdone[gid] = iters; sw.conv[gid] = (u8)conv; }
