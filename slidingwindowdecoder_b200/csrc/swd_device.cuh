@@ -152,6 +152,10 @@ __device__ __forceinline__ void mbar_wait(u64 *bar, u32 phase) {
             : "memory");
     }
 }
+// L2 prefetch of a global range (16-byte aligned, size % 16 == 0): warms the cache for a TMA load issued later
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, u32 bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // TMA 1-D bulk copy global -> shared (SASS: UBLKCP); dst/src 16-byte aligned, bytes % 16 == 0
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar) {

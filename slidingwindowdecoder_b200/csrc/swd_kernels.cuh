@@ -507,7 +507,7 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
     else if (phase == 0) { if (sT > 0) { l1 = 2 * sT + tier; l2 = 2 * sT + 2 + tier; } else l1 = tier; }
     else l1 = 2 * sT + 4 + tier;
     // list lengths live in shared memory (misc[8..10]): they are only needed once per item
-    if (tid == 0) {
+    if (tid == T - 1) {          // the thread that draws the tickets (it reads these back before the first barrier)
         const int n1 = ws.counters[SWD_WL_CNT + l1], n2 = (l2 >= 0) ? ws.counters[SWD_WL_CNT + l2] : 0;
         c.misc[8] = n1; c.misc[9] = npaths * n1; c.misc[10] = npaths * n1 + n2;
     }
@@ -515,15 +515,46 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
     u64 edge_iters = 0, bp_calls = 0, paths_run = 0, slot_iters = 0;
     u32 vn_iters = 0, cn_iters = 0;
 
+#ifndef SWD_CLAIM_AHEAD
+#define SWD_CLAIM_AHEAD 0     /* measured -3..4 % (A/B r2, as in round 1): kept for the record */
+#endif
+    // (SWD_CLAIM_AHEAD = 1, measured and rejected) One item ahead: while the CTA works on an item, its last thread has already drawn the next ticket, read that item
+    // (shared memory: misc[2] = ticket, misc[14..15] = item - no registers are held across the item) and asked L2 for the
+    // item's graph, parent messages and parent state, so the next set-up starts without a global round trip and its TMA
+    // copies come from L2 instead of HBM.
+    auto claim = [&]() {
+        const int ntk = atomicAdd(&ws.counters[ticket], 1);
+        c.misc[2] = ntk;
+        if (ntk >= c.misc[10]) return;
+        const int n1c = c.misc[8], t1c = c.misc[9];
+        const u64 it = (ntk < t1c) ? ws.wl[(size_t)l1 * ws.wl_stride + (npaths > 1 ? ntk % n1c : ntk)]
+                                   : ws.wl[(size_t)l2 * ws.wl_stride + (ntk - t1c)];
+        *(u64 *)&c.misc[14] = it;
+        if (SWD_CLAIM_AHEAD) {
+            const int nslot = (int)(it & 0xfffffffu), nes = (int)((it >> 28) & 0xffffu);
+            const int npath = (npaths > 1) ? ntk / n1c : (int)(it >> 48);
+            const unsigned char *nb = ws.blob + (size_t)nslot * LG.blob_bytes;
+            const u32 vb = (u32)((nes * 2 + 15) & ~15);
+            bulk_prefetch_l2(nb, (u32)L.fixed_bytes);
+            if (vb) { bulk_prefetch_l2(nb + LG.off_vrow, vb); bulk_prefetch_l2(nb + LG.off_vpos, vb); }
+            if (sT > 0 && (node_level > 0 || phase == 0)) {
+                const int plevel = (node_level > 0) ? node_level - 1 : sT - 1;
+                const unsigned char *pn = ws.node + ((size_t)nslot * P.n_nodes + ((1 << plevel) - 1) + (npath >> 1)) * P.node_stride;
+                bulk_prefetch_l2(pn, (u32)P.node_off_msg);                                   // header + masks
+                bulk_prefetch_l2(pn + P.node_off_msg, (u32)((nes * 8 + 15) & ~15));             // messages
+                bulk_prefetch_l2(pn + P.node_off_hist, (u32)(8 * 16 * T));                     // posterior history
+            }
+        }
+    };
+    if (SWD_CLAIM_AHEAD && tid == T - 1) claim();
     for (;;) {
         __syncthreads();
-        if (tid == 0) c.misc[2] = atomicAdd(&ws.counters[ticket], 1);
-        __syncthreads();
+        if (!SWD_CLAIM_AHEAD) { if (tid == T - 1) claim(); __syncthreads(); }
         const int tk = c.misc[2];
         if (tk >= c.misc[10]) break;
-        const int n1 = c.misc[8], total1 = c.misc[9];
-        const u64 item = (tk < total1) ? ws.wl[(size_t)l1 * ws.wl_stride + (npaths > 1 ? tk % n1 : tk)]
-                                       : ws.wl[(size_t)l2 * ws.wl_stride + (tk - total1)];
+        const int n1 = c.misc[8];
+        const u64 item = *(const u64 *)&c.misc[14];
+        if (SWD_CLAIM_AHEAD) { __syncthreads(); if (tid == T - 1) claim(); }       // everyone holds the current item: draw the next
         const int slot = (int)(item & 0xfffffffu), es = (int)((item >> 28) & 0xffffu);
         const int path = (npaths > 1) ? tk / n1 : (int)(item >> 48);
         const unsigned char *gblob = ws.blob + (size_t)slot * LG.blob_bytes;
