@@ -67,13 +67,16 @@ WORKLOADS = {
                      name="[[144,12,12]] circuit-level p=0.004, 12 rounds, un-windowed DEM 936 x 8784 (IBM.ipynb), BP+OSD-CS10 on the whole DEM",
                      decoder_name="osd_window(pre_max_iter=16, post_max_iter=1000, osd_cs, order 10)"),
 }
-WL = WORKLOADS["c3_gdg"]
+WL = dict(WORKLOADS["c3_gdg"], _key="c3_gdg")
 METRIC = {"gdg": "decoded shots/sec (sliding-window GDG)", "osd": "decoded shots/sec (sliding-window BP+OSD)"}
 
 
-def select_workload(key):
+def select_workload(key, p=None):
     global WL
-    WL = WORKLOADS[key]
+    WL = dict(WORKLOADS[key], _key=key)
+    if p is not None:
+        WL["name"] = WL["name"].replace(f"p={WL['p']}", f"p={p}")
+        WL["p"] = p
 
 
 def build_plan():
@@ -109,11 +112,11 @@ def build_plan():
 _CPU = {}
 
 
-def _cpu_init(plan_blob, use_ref=False, wl_key="c3_gdg"):
+def _cpu_init(plan_blob, use_ref=False, wl_key="c3_gdg", wl_p=None):
     """use_ref: decode with oracle/_ref (the reference's own bpgd.cpp, 15 std::threads per shot) instead of the C port."""
     import ctypes as C
     from oracle.oracle import Oracle, ref_lib, _p
-    select_workload(wl_key)
+    select_workload(wl_key, wl_p)
     _CPU["plan"] = plan_blob
     _CPU["orc"] = [Oracle(w.mat, w.prior) for w in plan_blob.windows]
     _CPU["chkT"] = plan_blob.chk.T.tocsr()
@@ -182,8 +185,7 @@ class CpuArm:
         self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         self.procs = procs or self.cores
         self.plan = plan
-        key = next(k for k, v in WORKLOADS.items() if v is WL)
-        self.pool = mp.get_context("fork").Pool(self.procs, initializer=_cpu_init, initargs=(plan, use_ref, key))
+        self.pool = mp.get_context("fork").Pool(self.procs, initializer=_cpu_init, initargs=(plan, use_ref, WL.get("_key", "c3_gdg"), WL["p"]))
 
     def run(self, det, obs):
         B = det.shape[0]
@@ -668,6 +670,7 @@ def main():
     ap.add_argument("--workload", default="c3_gdg", choices=sorted(WORKLOADS), help="default: BASELINE.json configs[2], the metric's configuration")
     ap.add_argument("--streams", type=int, default=3, help="concurrent sub-batches per GPU (fills kernel tails)")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: do not time the CPU baseline")
+    ap.add_argument("--p", type=float, default=None, help="override the workload's physical error rate (BASELINE configs[4]: p sweep 1e-3 .. 5e-3)")
     ap.add_argument("--total-shots", type=int, default=0, help="strong scaling: decode ONE job of this many shots (configs[2]: 10000000), sharded over the GPUs; "
                                                             "sampling inside the clock; prints wall seconds")
     ap.add_argument("--ref-seconds", type=float, default=90.0, help="--impl reference: CPU seconds spent on warm-up + timed steps together")
@@ -679,7 +682,7 @@ def main():
     sys.stdout.flush()
     _STDOUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
-    select_workload(args.workload)
+    select_workload(args.workload, args.p)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -27,3 +27,24 @@ out = d.camel_decode_batch(g["synd_x"][:n], g["synd_z"][:n])
 print("c1_bp4_camel_tied", "ok", bool(np.array_equal(out["converge"], g["conv"][:n])), int(out["converge"].sum()))
 out = d.decode_batch(g["synd_x"][:n], g["synd_z"][:n])
 print("c1_bp4 decode (tied)", "ok", int(out["converge"].sum()))
+
+# round 2: the large-graph paths forced on small windows (HBM-streamed BP with its cp.async rings, big radix select, large-T OSD
+# layout), the bit-packed entry point, and a few shots of the un-windowed [[144,12,12]] DEM itself
+from slidingwindowdecoder_b200.decoders import pack_bits, unpack_bits
+for env in ("SWD_FORCE_STREAM", "SWD_FORCE_BIG_SORT", "SWD_FORCE_BIG_OSD"):
+    os.environ[env] = "1"
+g = load_golden("c2_w1_osdw_cs10")
+d = osd_window(g["mat"], channel_probs=g["priors"], **g["kwargs"])
+pc, conv = d.decode_batch_packed(pack_bits(g["synd"][:n]))
+print("c2_w1_osdw_cs10 forced stream / big sort / big osd, packed", "ok", bool(np.array_equal(unpack_bits(pc, d.n), g["dec"][:n])), int(conv.sum()))
+g = load_golden("c2_w1_gdg_mt1")
+d = bpgdg_decoder(g["mat"], channel_probs=g["priors"], **g["kwargs"])
+corr, conv = d.decode_batch(g["synd"][:n])
+print("c2_w1_gdg_mt1 forced stream / big sort", "ok", int(conv.sum()))
+for env in ("SWD_FORCE_STREAM", "SWD_FORCE_BIG_SORT", "SWD_FORCE_BIG_OSD"):
+    del os.environ[env]
+if os.environ.get("SANITIZE_G144", "1") == "1":
+    g = load_golden("g144_osdw_cs10")
+    d = osd_window(g["mat"], channel_probs=g["priors"], **g["kwargs"])
+    corr, conv = d.decode_batch(g["synd"][:3])
+    print("g144_osdw_cs10", "ok", bool(np.array_equal(corr, g["dec"][:3])), int(conv.sum()))
