@@ -58,6 +58,8 @@ struct swd_decoder {
     SubLayout L{}, LsA{}, LsB{};
     PathSmem PS{}, PSB{};
     int es_capA = 0, grid3B = 0;
+    // latency configuration (tiny batches): a branch path spread over one VN per thread
+    path_fn_t path_fn_lat = nullptr; int T3lat = 0, grid3lat = 0;
     PreSmem PRE{};
     // graphs whose messages exceed one SM's shared memory: HBM-streamed full-window BP (swd_stream.cuh)
     bool stream_mode = false; int Ts = 256; size_t stream_smem = 0; StreamWs sw{}; void *sw_block = nullptr; long long sw_G = 0;
@@ -512,6 +514,18 @@ static int setup_kernels(swd_decoder *d) {
     d->grid3 = d->num_sm * occ;
     if ((st = occupancy(d->path_fn, d->T3, smemB, &occ))) return st;
     d->grid3B = d->num_sm * std::max(1, occ);
+    // Latency configuration: with a handful of shots every branch path has an SM to itself, and what counts is the length of
+    // one min-sum iteration on one CTA (tools/latency_probe.py: ~5 us with 128 threads, 97 % of the window latency is kernel
+    // execution).  One VN per thread (one variable round instead of four, one check round) shortens it several times.
+    d->T3lat = 0;
+    if (c.kind != SWD_KIND_OSD_WINDOW && !getenv("SWD_NO_LATENCY_MODE")) {
+        const int tl = std::min(1024, std::max(d->T3, r32up(nn)));
+        if (tl > d->T3) {
+            path_fn_t f = pick_path_kernel(d->dmax, tl);
+            int occl = 0;
+            if (occupancy(f, tl, smemB, &occl) == SWD_OK && occl >= 1) { d->path_fn_lat = f; d->T3lat = tl; d->grid3lat = d->num_sm * occl; }
+        }
+    }
     // shared-prefix tree (multi-thread GDG): depths 0..T-1 are computed once per decision prefix
     if (c.kind == SWD_KIND_BPGDG && c.multi_thread && P.T >= 1 && P.T <= 6 && P.max_step >= P.T && !getenv("SWD_NO_SHARED_PREFIX")) {
         P.shared_T = P.T; P.n_nodes = (1 << P.T) - 1;
@@ -522,7 +536,7 @@ static int setup_kernels(swd_decoder *d) {
         q += m; q = r16(q); P.node_off_flip = q;
         q += m; q = r16(q); P.node_off_msg = q;
         q += 8 * es_slots; q = r16(q); P.node_off_hist = q;
-        q += 8 * 16 * d->T3; q = r16(q);
+        q += 8 * 16 * std::max(d->T3, d->T3lat); q = r16(q);
         P.node_stride = q;
     }
     // ---- K5 (OSD)
@@ -671,7 +685,8 @@ static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_cor
     const int g2 = (int)std::min<long long>(B, d->grid2);
     // Latency mode: with so few shots that every work item gets its own CTA even at the worst-case footprint, run one
     // tier (worst-case shared memory) instead of two - five launches less per window (p50 per-window latency at batch 1).
-    const bool one_tier = (d->es_capA < d->L.es_max) && (B * (long long)std::max(1, d->P.n_rec) <= (long long)d->grid3B);
+    const bool lat = d->T3lat > 0 && (B * (long long)std::max(1, d->P.n_rec) <= (long long)d->grid3lat / 2);
+    const bool one_tier = lat || ((d->es_capA < d->L.es_max) && (B * (long long)std::max(1, d->P.n_rec) <= (long long)d->grid3B));
     const int capA = one_tier ? d->L.es_max : d->es_capA;
     const SubLayout &LsA = one_tier ? d->LsB : d->LsA;
     const PathSmem &PSA = one_tier ? d->PSB : d->PS;
@@ -681,7 +696,9 @@ static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_cor
     const size_t smem3 = (size_t)LsA.blob_bytes + PSA.total;
     const size_t smem3B = (size_t)d->LsB.blob_bytes + d->PSB.total;
     const bool two_tier = capA < d->L.es_max;
-    const int g3 = one_tier ? d->grid3B : d->grid3;
+    int g3 = one_tier ? d->grid3B : d->grid3;
+    path_fn_t pfn = d->path_fn; int T3 = d->T3;
+    if (lat) { pfn = d->path_fn_lat; T3 = d->T3lat; g3 = d->grid3lat; }
     const int phases = (c.kind == SWD_KIND_BPGDG && c.multi_thread && d->P.n_side > 0) ? 2 : 1;
     if (c.kind == SWD_KIND_OSD_WINDOW) {
         for (int stage = 0; stage < 2; stage++) {
@@ -694,7 +711,7 @@ static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_cor
     } else {
         for (int lv = 0; lv < d->P.shared_T; lv++) {       // shared-prefix nodes, level by level
             KTimer kt(d, s, SWD_K_PATH_TRUNK);
-            d->path_fn<<<g3, d->T3, smem3, s>>>(d->ws, d->L, LsA, PSA, d->P, 2 + lv, 0, capA);
+            pfn<<<g3, T3, smem3, s>>>(d->ws, d->L, LsA, PSA, d->P, 2 + lv, 0, capA);
             d->ctr.kernel_launches++;
             if (two_tier) {
                 d->path_fn<<<d->grid3B, d->T3, smem3B, s>>>(d->ws, d->L, d->LsB, d->PSB, d->P, 2 + lv, 1, capA);
@@ -703,7 +720,7 @@ static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_cor
         }
         for (int ph = 0; ph < phases; ph++) {
             KTimer kt(d, s, ph == 0 ? SWD_K_PATH_MAIN : SWD_K_PATH_SIDE);
-            d->path_fn<<<g3, d->T3, smem3, s>>>(d->ws, d->L, LsA, PSA, d->P, ph, 0, capA);
+            pfn<<<g3, T3, smem3, s>>>(d->ws, d->L, LsA, PSA, d->P, ph, 0, capA);
             d->ctr.kernel_launches++;
             if (two_tier) {      // shots whose shortened graph exceeds tier A (rare): same kernel, worst-case footprint
                 d->path_fn<<<d->grid3B, d->T3, smem3B, s>>>(d->ws, d->L, d->LsB, d->PSB, d->P, ph, 1, capA);

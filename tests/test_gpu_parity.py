@@ -62,6 +62,25 @@ def test_single_shot_api(oracle_mod):
         dec.decode(np.zeros(5, dtype=np.uint8))
 
 
+@pytest.mark.parametrize("name", ["c3_w5_gdg_mt1", "c3_w5_gdg_mt0", "c3_w5_bpgd", "c5_w4_gdg_mt1"])
+def test_latency_configuration_equals_throughput_configuration(name):
+    """Tiny batches run the branch paths in the latency configuration (one VN per thread: 448 instead of 128 threads per path on a
+    [[144,12,12]] window) and one worst-case shared-memory tier: the corrections of shots decoded one, two and three at a time must
+    equal those of the same shots decoded in one large batch (and the reference's goldens for the single-thread kinds)."""
+    from slidingwindowdecoder_b200 import bpgdg_decoder, bpgd_decoder
+    g = load_golden(name)
+    cls = bpgd_decoder if name.endswith("bpgd") else bpgdg_decoder
+    dec = cls(g["mat"], channel_probs=g["priors"], **g["kwargs"])
+    synd = g["synd"][:240]
+    big, bconv, bpm = dec.decode_batch(synd, return_pm=True)
+    for step in (1, 2, 3):
+        for i in range(0, 60, step):
+            c, v, pm = dec.decode_batch(synd[i:i + step], return_pm=True)
+            assert np.array_equal(c, big[i:i + step]) and np.array_equal(v, bconv[i:i + step]) and np.array_equal(pm, bpm[i:i + step]), (step, i)
+    if not name.endswith("mt1"):
+        assert np.array_equal(big, g["dec"][:240])
+
+
 def test_edge_cases(oracle_mod):
     g = load_golden("c1_gdg_default_mt1")
     dec = _gdg_cls()(g["mat"], channel_probs=g["priors"], **g["kwargs"])
