@@ -37,7 +37,10 @@ static path_fn_t pick_path_kernel(int dmax, int T) {
 #define SWD_MINB (SWD_DIET ? 8 : 7)
 #endif
         if (T <= 128) return path_kernel<4, 6, 128, SWD_MINB>;
-        if (T <= 320) return path_kernel<4, 6, 320, 2>;          // e.g. 576 x 4896 windows (new_n = 1152): two CTAs per SM
+#ifndef SWD_MINB320
+#define SWD_MINB320 3      /* 64 registers, three CTAs per SM: C4 post-BP -4.5 % (A/B r2) */
+#endif
+        if (T <= 320) return path_kernel<4, 6, 320, SWD_MINB320>;          // e.g. 576 x 4896 windows (new_n = 1152): two CTAs per SM
         if (T <= 512) return path_kernel<4, 6, 512, 1>;
         return path_kernel<4, 6, 1024, 1>;
     }

@@ -577,7 +577,10 @@ typedef void (*post_fn_t)(Workspace, SubLayout, SubLayout, PathSmem, GdgDev, int
 static inline post_fn_t pick_post_kernel(int dmax, int T) {
     if (dmax == 6) {
         if (T <= 128) return post_bp_kernel<4, 6, 128, 5>;
-        if (T <= 320) return post_bp_kernel<4, 6, 320, 2>;
+#ifndef SWD_MINB320
+#define SWD_MINB320 3      /* 64 registers, three CTAs per SM: C4 post-BP -4.5 % (A/B r2) */
+#endif
+        if (T <= 320) return post_bp_kernel<4, 6, 320, SWD_MINB320>;
         if (T <= 512) return post_bp_kernel<4, 6, 512, 1>;
         return post_bp_kernel<4, 6, 1024, 1>;
     }
