@@ -309,6 +309,65 @@ def test_heavy_columns_long_rows(kind, oracle_mod):
     assert len(bad) == 0, f"shots {bad[:10]}"
 
 
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_random_graphs_all_kinds_all_paths(seed, oracle_mod, monkeypatch):
+    """Fuzz: random sparse check matrices of ragged shapes (m from 5 to 150, n not a multiple of anything, column weights 1..9, a few
+    no empty rows: the reference requires deg > 0, random new_n, scaling factors, tree depths, OSD orders), random syndromes - some of them not in the
+    column space of H -, every decoder kind, and on odd seeds the large-graph code paths forced (HBM-streamed BP, big radix select,
+    large-T OSD layout).  Bit-exact vs the CPU oracle: corrections, converge flags, path metrics."""
+    from slidingwindowdecoder_b200 import bpgdg_decoder, bpgd_decoder, osd_window
+    rng = np.random.default_rng(1000 + seed)
+    m = int(rng.integers(5, 150)); n = int(rng.integers(m + 3, 6 * m + 40))
+    wmax = int(rng.integers(2, 10))
+    H = _random_pcm(m, n, rng, 1, min(wmax, m))
+    for r in np.nonzero(H.sum(axis=1) == 0)[0]:          # the reference requires every check to have a column (osd_window.pyx:117)
+        H[r, int(rng.integers(0, n))] = 1
+    pri = 10 ** rng.uniform(-3, -1.2, size=n)
+    B = 96
+    err = (rng.random((B, n)) < pri * rng.uniform(0.5, 3.0)).astype(np.int64)
+    synd = (err @ H.T % 2).astype(np.uint8)
+    synd[::7] ^= (rng.random((len(synd[::7]), m)) < 0.05).astype(np.uint8)          # not necessarily a syndrome of anything
+    if seed % 2:
+        for k in ("SWD_FORCE_STREAM", "SWD_FORCE_BIG_SORT", "SWD_FORCE_BIG_OSD"):
+            monkeypatch.setenv(k, "1")
+    orc = oracle_mod.Oracle(H, pri)
+    new_n = None if seed % 3 else int(rng.integers(max(2, m // 2), n + 1))
+    f = float(rng.choice([1.0, 0.9, 0.625]))
+    # multi-thread / single-thread GDG
+    for mt in (True, False):
+        kw = dict(max_iter=int(rng.integers(0, 12)), ms_scaling_factor=f, gdg_factor=f, max_iter_per_step=int(rng.integers(2, 8)),
+                  max_step=int(rng.integers(3, 20)), max_tree_depth=int(rng.integers(1, 4)), max_side_depth=int(rng.integers(4, 9)),
+                  max_tree_branch_step=int(rng.integers(2, 8)), max_side_branch_step=int(rng.integers(2, 8)), multi_thread=mt,
+                  low_error_mode=bool(seed & 4), new_n=new_n)
+        kw["max_step"] = max(kw["max_step"], kw["max_tree_depth"])
+        corr, conv, pm = bpgdg_decoder(H, channel_probs=pri, **kw).decode_batch(synd, return_pm=True)
+        o_dec, o_conv, o_pm, _ = orc.bpgdg_batch(synd, **kw)
+        assert np.array_equal(conv, o_conv.astype(np.uint8)), (seed, mt)
+        assert np.array_equal(corr, o_dec.astype(np.uint8)), (seed, mt)
+        if mt:
+            assert np.array_equal(pm[pm < 9999.0], o_pm[pm < 9999.0])
+    # BPGD
+    kw = dict(max_iter=int(rng.integers(1, 10)), ms_scaling_factor=f, max_iter_per_step=int(rng.integers(2, 8)), max_step=int(rng.integers(3, 30)),
+              gd_factor=f, new_n=new_n)
+    corr, conv = bpgd_decoder(H, channel_probs=pri, **kw).decode_batch(synd)
+    o = [orc.bpgd(x, **kw) for x in synd]
+    assert np.array_equal(conv, np.array([x[1] for x in o]).astype(np.uint8)) and np.array_equal(corr, np.array([x[0] for x in o]).astype(np.uint8)), seed
+    # osd_window: OSD-0 / CS / E / BP only
+    for meth, order in (("osd_0", 0), ("osd_cs", int(rng.integers(0, 6))), ("osd_e", int(rng.integers(0, 4))), ("osd_cs", -1)):
+        kw = dict(pre_max_iter=int(rng.integers(0, 10)), post_max_iter=int(rng.integers(0, 40)), ms_scaling_factor=f, osd_method=meth,
+                  osd_order=order, new_n=new_n)
+        try:
+            dec = osd_window(H, channel_probs=pri, **kw)
+        except ValueError as e:                      # osd_order > new_n - rank (the reference raises the same way)
+            assert "OSD order" in str(e)
+            continue
+        corr, conv, pm = dec.decode_batch(synd, return_pm=True)
+        o_dec, o_conv, o_pm, _ = orc.osd_window_batch(synd, **kw)
+        assert np.array_equal(conv, np.asarray(o_conv).astype(np.uint8)), (seed, meth, order)
+        assert np.array_equal(corr, np.asarray(o_dec).astype(np.uint8)), (seed, meth, order)
+        assert np.array_equal(pm, o_pm), (seed, meth, order)
+
+
 def test_chunked_workspace_gives_identical_results(monkeypatch):
     """Batches larger than the workspace capacity are decoded in chunks (SWD_WS_BYTES caps the workspace)."""
     from slidingwindowdecoder_b200 import bpgdg_decoder, osd_window
