@@ -69,6 +69,7 @@ struct swd_decoder {
     SortSmem SS{};
     OsdSmem OS{};
     GdgDev P{};
+    GdgDev Plat{};            // the same with the node-snapshot stride of the latency configuration (T3lat threads of history)
     int T1 = 0, T2 = 0, T3 = 0, T5 = 0, dmax = 8;
     int grid1 = 0, grid2 = 0, grid3 = 0, grid5 = 0;
     // workspace
@@ -529,6 +530,7 @@ static int setup_kernels(swd_decoder *d) {
             if (occupancy(f, tl, smemB, &occl) == SWD_OK && occl >= 1) { d->path_fn_lat = f; d->T3lat = tl; d->grid3lat = d->num_sm * occl; }
         }
     }
+    d->Plat = P;
     // shared-prefix tree (multi-thread GDG): depths 0..T-1 are computed once per decision prefix
     if (c.kind == SWD_KIND_BPGDG && c.multi_thread && P.T >= 1 && P.T <= 6 && P.max_step >= P.T && !getenv("SWD_NO_SHARED_PREFIX")) {
         P.shared_T = P.T; P.n_nodes = (1 << P.T) - 1;
@@ -539,8 +541,11 @@ static int setup_kernels(swd_decoder *d) {
         q += m; q = r16(q); P.node_off_flip = q;
         q += m; q = r16(q); P.node_off_msg = q;
         q += 8 * es_slots; q = r16(q); P.node_off_hist = q;
-        q += 8 * 16 * std::max(d->T3, d->T3lat); q = r16(q);
+        const int q_hist = q;
+        q += 8 * 16 * d->T3; q = r16(q);
         P.node_stride = q;
+        d->Plat = P;
+        d->Plat.node_stride = r16(q_hist + 8 * 16 * std::max(d->T3, d->T3lat));
     }
     // ---- K5 (OSD)
     if (c.kind == SWD_KIND_OSD_WINDOW) {
@@ -581,7 +586,8 @@ static int alloc_workspace(swd_decoder *d, long long want, cudaStream_t s) {
     size_t o_blob = o; o += a256((size_t)cap * d->L.blob_bytes);
     size_t o_rec = o; o += a256((size_t)cap * d->P.n_rec * d->P.rec_stride);
     size_t o_side = o; o += a256((size_t)cap * std::max(1, d->P.n_side) * d->P.side_stride);
-    size_t o_node = o; o += a256((size_t)cap * std::max(1, d->P.n_nodes) * d->P.node_stride);
+    size_t o_node = o; o += a256(std::max((size_t)cap * std::max(1, d->P.n_nodes) * d->P.node_stride,
+                                          (size_t)std::min<long long>(cap, 8) * std::max(1, d->P.n_nodes) * d->Plat.node_stride));
     size_t o_osd = o; if (osd) o += a256((size_t)cap * osd_bytes_per_shot(d->m, n));
     const long long wl_stride = cap * std::max(1, std::max(d->P.n_tree + 1, d->P.n_side));
     size_t o_bak = o; o += a256((size_t)cap * std::max(1, d->P.n_tree) * d->P.bak_stride);
@@ -688,13 +694,13 @@ static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_cor
     const int g2 = (int)std::min<long long>(B, d->grid2);
     // Latency mode: with so few shots that every work item gets its own CTA even at the worst-case footprint, run one
     // tier (worst-case shared memory) instead of two - five launches less per window (p50 per-window latency at batch 1).
-    const bool lat = d->T3lat > 0 && (B * (long long)std::max(1, d->P.n_rec) <= (long long)d->grid3lat / 2);
+    const bool lat = d->T3lat > 0 && B <= 8 && (B * (long long)std::max(1, d->P.n_rec) <= (long long)d->grid3lat / 2);     // <= 8: the node region holds 8 slots at the latency stride
     const bool one_tier = lat || ((d->es_capA < d->L.es_max) && (B * (long long)std::max(1, d->P.n_rec) <= (long long)d->grid3B));
     const int capA = one_tier ? d->L.es_max : d->es_capA;
     const SubLayout &LsA = one_tier ? d->LsB : d->LsA;
     const PathSmem &PSA = one_tier ? d->PSB : d->PS;
     { KTimer kt(d, s, SWD_K_SORT_RESET);
-      sort_reset_kernel<<<g2, d->T2, d->SS.total, s>>>(d->g, d_synd, d->ws, d->L, d->P, d->SS, d_corr, capA); }
+      sort_reset_kernel<<<g2, d->T2, d->SS.total, s>>>(d->g, d_synd, d->ws, d->L, lat ? d->Plat : d->P, d->SS, d_corr, capA); }
     d->ctr.kernel_launches++;
     const size_t smem3 = (size_t)LsA.blob_bytes + PSA.total;
     const size_t smem3B = (size_t)d->LsB.blob_bytes + d->PSB.total;
@@ -714,7 +720,7 @@ static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_cor
     } else {
         for (int lv = 0; lv < d->P.shared_T; lv++) {       // shared-prefix nodes, level by level
             KTimer kt(d, s, SWD_K_PATH_TRUNK);
-            pfn<<<g3, T3, smem3, s>>>(d->ws, d->L, LsA, PSA, d->P, 2 + lv, 0, capA);
+            pfn<<<g3, T3, smem3, s>>>(d->ws, d->L, LsA, PSA, lat ? d->Plat : d->P, 2 + lv, 0, capA);
             d->ctr.kernel_launches++;
             if (two_tier) {
                 d->path_fn<<<d->grid3B, d->T3, smem3B, s>>>(d->ws, d->L, d->LsB, d->PSB, d->P, 2 + lv, 1, capA);
@@ -723,7 +729,7 @@ static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_cor
         }
         for (int ph = 0; ph < phases; ph++) {
             KTimer kt(d, s, ph == 0 ? SWD_K_PATH_MAIN : SWD_K_PATH_SIDE);
-            pfn<<<g3, T3, smem3, s>>>(d->ws, d->L, LsA, PSA, d->P, ph, 0, capA);
+            pfn<<<g3, T3, smem3, s>>>(d->ws, d->L, LsA, PSA, lat ? d->Plat : d->P, ph, 0, capA);
             d->ctr.kernel_launches++;
             if (two_tier) {      // shots whose shortened graph exceeds tier A (rare): same kernel, worst-case footprint
                 d->path_fn<<<d->grid3B, d->T3, smem3B, s>>>(d->ws, d->L, d->LsB, d->PSB, d->P, ph, 1, capA);
@@ -731,7 +737,7 @@ static int launch_chunk(swd_decoder *d, const u8 *d_synd, long long B, u8 *d_cor
             }
         }
         { KTimer kt(d, s, SWD_K_SELECT);
-          select_kernel<<<std::max(1, std::min<int>((int)B, d->num_sm * 8)), 128, 0, s>>>(d->ws, d->L, d->P, d->n, d_corr, d_conv, d_pm); }
+          select_kernel<<<std::max(1, std::min<int>((int)B, d->num_sm * 8)), 128, 0, s>>>(d->ws, d->L, lat ? d->Plat : d->P, d->n, d_corr, d_conv, d_pm); }
         d->ctr.kernel_launches++;
     }
     CK(cudaGetLastError());
