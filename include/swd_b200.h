@@ -138,6 +138,13 @@ int  swd_pack_bits(int device, const uint8_t *d_bytes, int64_t B, int nbits, uin
 int  swd_unpack_bits(int device, const uint64_t *d_packed, int64_t B, int nbits, uint8_t *d_bytes, void *stream);
 /* 1 if the full-window BP of this decoder streams its messages from HBM (graph beyond one SM's shared memory), else 0 */
 int  swd_is_streamed(swd_decoder *d);
+/* Host-only diagnostic (no CUDA call): the shared-memory message layout swd_create chooses for the full-window BP kernel of
+ * this graph (static per decoder: row starts on distinct banks, slot order inside a row chosen so that both passes of
+ * bp_decode_llr, bp_guessing_decoder.pyx:62-127, are bank-conflict free).  slot_of_entry [nnz] (per CSC entry, rows ascending
+ * inside a column), row_start [m + 1], stats[3] = {slots incl. pads, extra variable-pass wavefronts of the plain CSR order,
+ * of the chosen layout}; any pointer may be NULL.  optimize = 0: the plain CSR order. */
+int  swd_pre_bp_layout(int m, int n, const int32_t *colptr, const int32_t *rowidx, int optimize,
+                       int32_t *slot_of_entry, int32_t *row_start, int64_t *stats);
 
 /* osd_window read-only properties of the LAST batch (osd_window.pyx:487-517), host copies.
  * Any pointer may be NULL.  bp_dec/osd0/osdw: [B*n]; log_prob_ratios: [B*n*4]; bp_iteration: [B]. */

@@ -34,7 +34,7 @@ KERNEL_CLASSES = ["pre_bp", "sort_reset", "path_main", "path_side", "select", "o
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4
 
 EXPORTS = ["swd_create", "swd_destroy", "swd_decode_batch_host", "swd_decode_batch_device", "swd_decode_batch_host_packed",
-           "swd_decode_batch_device_packed", "swd_pack_bits", "swd_unpack_bits", "swd_is_streamed", "swd_osd_last_outputs",
+           "swd_decode_batch_device_packed", "swd_pack_bits", "swd_unpack_bits", "swd_is_streamed", "swd_pre_bp_layout", "swd_osd_last_outputs",
            "swd_set_profiling", "swd_get_kernel_times", "swd_get_counters", "swd_reset_counters", "swd_rank", "swd_new_n", "swd_window_create", "swd_window_destroy",
            "swd_window_extract", "swd_window_commit", "swd_window_count_failures", "swd_window_set_priors", "swd_window_sample", "swd_bp4_create", "swd_bp4_destroy", "swd_bp4_rank", "swd_bp4_decode_batch_host", "swd_bp4_camel_decode_batch_host", "swd_bp4_decode_batch_device", "swd_bp4_camel_decode_batch_device", "swd_strerror", "swd_last_error",
            "swd_version"]
@@ -70,6 +70,8 @@ def load():
     lib.swd_unpack_bits.restype = C.c_int
     lib.swd_is_streamed.argtypes = [vp]
     lib.swd_is_streamed.restype = C.c_int
+    lib.swd_pre_bp_layout.argtypes = [C.c_int, C.c_int, i32p, i32p, C.c_int, vp, vp, vp]
+    lib.swd_pre_bp_layout.restype = C.c_int
     lib.swd_osd_last_outputs.argtypes = [vp, C.c_int64, u8p, u8p, u8p, dp, vp]
     lib.swd_osd_last_outputs.restype = C.c_int
     lib.swd_get_counters.argtypes = [vp, C.POINTER(SwdCounters)]

@@ -57,7 +57,8 @@ struct swd_decoder {
     bool osd_only = false;
     int device = 0, num_sm = 0;
     GraphDev g{};
-    void *d_graph[11] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *d_graph[13] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int nphys = 0;              // message slots of the pre-BP kernel's physical layout (>= nnz)
     SubLayout L{}, LsA{}, LsB{};
     PathSmem PS{}, PSB{};
     int es_capA = 0, grid3B = 0;
@@ -157,6 +158,90 @@ extern "C" int swd_create(const swd_config *cfg, int m, int n, const int32_t *co
     return create_impl(cfg, m, n, colptr, rowidx, channel_llr, out, false);
 }
 
+// Physical message layout of the pre-BP kernel (GraphDev::prow / cpj / c2b1 / rowof).  Static graph -> solved once per decoder:
+//  * row starts: inside every aligned group of 16 rows (the rows a half-warp of the check pass owns) the starts fall on 16
+//    distinct 8-byte banks - a few pad slots between rows;
+//  * slot order inside a row (free: the check update does not depend on it): local search (pair swaps inside a row, non-worsening
+//    moves accepted) on the number of extra shared-memory wavefronts of the variable pass, where the 16 ownership slots of a
+//    half-warp touch their k-th edges together.  [[144,12,12]] (3,1) window: 3040 -> ~1570 wavefronts per iteration (ideal 1538).
+// optimize = false: slots in CSR order without pads (SWD_PRE_NO_LAYOUT=1, for A/B runs).
+struct PreLayout { int nphys = 0; std::vector<int> pstart, phys; int jb[17]; std::vector<u16> cpj; long long excess0 = 0, excess = 0; };
+static void pre_layout(int m, int n, int nnz, const std::vector<int> &cp, const std::vector<int> &cr, const std::vector<int> &rp,
+                       const std::vector<int> &cpos, const std::vector<u16> &vord, bool optimize, PreLayout &L) {
+    L.pstart.assign(m + 1, 0); L.phys.assign(std::max(nnz, 1), 0);
+    {
+        int pos = 0; unsigned used = 0;
+        for (int r = 0; r < m; r++) {
+            if ((r & 15) == 0) used = 0;
+            if (optimize) while (used & (1u << (pos & 15))) pos++;
+            used |= 1u << (pos & 15);
+            L.pstart[r] = pos; pos += rp[r + 1] - rp[r];
+        }
+        L.pstart[m] = pos; L.nphys = pos;
+    }
+    if (L.nphys > 65535) {      // 16-bit slots: fall back to the unpadded order
+        optimize = false;
+        for (int r = 0; r <= m; r++) L.pstart[r] = rp[r];
+        L.nphys = nnz;
+    }
+    std::vector<int> deg(n), gid(std::max(nnz, 1)), tpos(std::max(nnz, 1)), epos(std::max(nnz, 1));
+    for (int sl = 0; sl < n; sl++) deg[sl] = cp[vord[sl] + 1] - cp[vord[sl]];            // descending
+    int ng = 0;
+    for (int h = 0; h * 16 < n; h++) {
+        const int gb = ng; ng += deg[h * 16];
+        for (int sl = h * 16; sl < std::min(n, h * 16 + 16); sl++) for (int k = 0; k < deg[sl]; k++) gid[cp[vord[sl]] + k] = gb + k;
+    }
+    for (int e = 0; e < nnz; e++) { epos[cpos[e]] = e; tpos[e] = cpos[e] - rp[cr[e]]; }
+    std::vector<unsigned char> cnt((size_t)std::max(ng, 1) * 16, 0);
+    for (int e = 0; e < nnz; e++) cnt[(size_t)gid[e] * 16 + ((L.pstart[cr[e]] + tpos[e]) & 15)]++;
+    auto excess = [&]() { long long x = 0; for (unsigned char c : cnt) x += c > 1 ? c - 1 : 0; return x; };
+    L.excess0 = L.excess = excess();
+    if (optimize) {
+        unsigned long long rng = 0x9e3779b97f4a7c15ull;
+        long long best = L.excess0; int stale = 0;
+        for (int sweep = 0; sweep < 64 && best > 0 && stale < 6; sweep++) {
+            for (int r = 0; r < m; r++) {
+                const int S = L.pstart[r], len = rp[r + 1] - rp[r];
+                const int *E = &epos[rp[r]];
+                for (int i = 0; i < len; i++) {
+                    const int e = E[i], b = (S + tpos[e]) & 15, g = gid[e];
+                    if (cnt[(size_t)g * 16 + b] <= 1) continue;
+                    int bf_best = -1, bestd = 1, nzero = 0;
+                    for (int j = 0; j < len; j++) {
+                        const int f = E[j], bf = (S + tpos[f]) & 15, gf = gid[f];
+                        if (bf == b || gf == g) continue;
+                        const int d = -1 + (cnt[(size_t)g * 16 + bf] >= 1) - (cnt[(size_t)gf * 16 + bf] > 1) + (cnt[(size_t)gf * 16 + b] >= 1);
+                        if (d < 0) { if (d < bestd) { bestd = d; bf_best = j; } }
+                        else if (d == 0 && bestd >= 0) {            // no improving swap so far: keep one of the neutral ones at random
+                            rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                            if ((rng >> 33) % (unsigned)(++nzero) == 0) { bestd = 0; bf_best = j; }
+                        }
+                    }
+                    if (bf_best >= 0 && bestd <= 0) {
+                        const int f = E[bf_best], bf = (S + tpos[f]) & 15, gf = gid[f];
+                        cnt[(size_t)g * 16 + b]--; cnt[(size_t)g * 16 + bf]++; cnt[(size_t)gf * 16 + bf]--; cnt[(size_t)gf * 16 + b]++;
+                        std::swap(tpos[e], tpos[f]);
+                    }
+                }
+            }
+            const long long x = excess();
+            if (x < best) { best = x; stale = 0; } else stale++;
+        }
+        L.excess = best;
+    }
+    for (int e = 0; e < nnz; e++) L.phys[e] = L.pstart[cr[e]] + tpos[e];
+    // jagged-diagonal map in ownership-slot order
+    L.cpj.assign(std::max(nnz, 1), 0);
+    int o = 0;
+    for (int k = 0; k < 17; k++) {
+        L.jb[k] = o;
+        if (k == 16) break;
+        for (int sl = 0; sl < n && deg[sl] > k; sl++) L.cpj[o + sl] = (u16)L.phys[cp[vord[sl]] + k];
+        int nk = 0; while (nk < n && deg[nk] > k) nk++;
+        o += nk;
+    }
+}
+
 // osd_only: the graph is used by osd_kernel alone (bp4_osd runs its own BP kernel) - no pre-BP / sort / path set-up and no
 // column- or row-weight limit (CAMEL codes tie every check to the last qubit)
 static int create_impl(const swd_config *cfg, int m, int n, const int32_t *colptr, const int32_t *rowidx,
@@ -229,7 +314,16 @@ static int create_impl(const swd_config *cfg, int m, int n, const int32_t *colpt
         vrec[sl] = (u32)cp[v] | ((u32)(cp[v + 1] - cp[v]) << 16);
         llr_s[sl] = llr[v];
     }
+    PreLayout PL;
+    std::vector<u32> prow(std::max(m, 1));
+    if (!osd_only) {
+        pre_layout(m, n, nnz, cp, cr, rp, cpos, vord, !getenv("SWD_PRE_NO_LAYOUT"), PL);
+        for (int r = 0; r < m; r++) prow[r] = (u32)PL.pstart[r] | ((u32)(rp[r + 1] - rp[r]) << 16);
+        if (getenv("SWD_DEBUG")) fprintf(stderr, "[swd] pre-BP layout: nnz=%d slots=%d extra VN-pass wavefronts %lld -> %lld\n", nnz, PL.nphys, PL.excess0, PL.excess);
+    } else { PL.nphys = nnz; PL.cpj.assign(std::max(nnz, 1), 0); for (int k = 0; k < 17; k++) PL.jb[k] = 0; }
+    d->nphys = PL.nphys;
     int st;
+    if ((st = upload(prow, &d->d_graph[11])) || (st = upload(PL.cpj, &d->d_graph[12]))) { swd_destroy(d); return st; }
     if ((st = upload(rp, &d->d_graph[0])) || (st = upload(rc16, &d->d_graph[1])) || (st = upload(cp, &d->d_graph[2])) ||
         (st = upload(cr16, &d->d_graph[3])) || (st = upload(cpos16, &d->d_graph[4])) || (st = upload(llr, &d->d_graph[5])) ||
         (st = upload(vord, &d->d_graph[6])) || (st = upload(vrec, &d->d_graph[7])) || (st = upload(llr_s, &d->d_graph[8]))) {
@@ -238,7 +332,9 @@ static int create_impl(const swd_config *cfg, int m, int n, const int32_t *colpt
     d->g.c2b1 = nullptr; d->g.rowof = nullptr;
     if (!osd_only && cfg->bp_method == SWD_BP_MIN_SUM && !getenv("SWD_NO_FIRST_PASS_TABLE")) {
         // the check pass of iteration 1 for syndrome 0, with the kernel's own arithmetic (osd / bpgd pyx:62-96)
-        std::vector<double> t(std::max(nnz, 1)); std::vector<u16> ro(std::max(nnz, 1));
+        std::vector<double> t(std::max(PL.nphys, 1), 0.0); std::vector<u16> ro(std::max(PL.nphys, 1), 0);     // physical slot order
+        std::vector<int> physof(std::max(nnz, 1));                                                          // CSR position -> physical slot
+        for (int e = 0; e < nnz; e++) physof[cpos[e]] = PL.phys[e];
         const double alpha = cfg->ms_scaling_factor;
         for (int r = 0; r < m; r++) {
             double m1 = SWD_BIG, m2 = SWD_BIG; int arg = -1; unsigned par = 0;
@@ -253,14 +349,16 @@ static int create_impl(const swd_config *cfg, int m, int n, const int32_t *colpt
             for (int p = rp[r]; p < rp[r + 1]; p++) {
                 const double b = llr[rc[p]];
                 const double q = (p == arg) ? q2 : q1;
-                t[p] = ((par ^ (unsigned)(b <= 0.0)) & 1u) ? -q : q;
-                ro[p] = (u16)r;
+                t[physof[p]] = ((par ^ (unsigned)(b <= 0.0)) & 1u) ? -q : q;
+                ro[physof[p]] = (u16)r;
             }
         }
         if ((st = upload(t, &d->d_graph[9])) || (st = upload(ro, &d->d_graph[10]))) { swd_destroy(d); return st; }
         d->g.c2b1 = (const double *)d->d_graph[9]; d->g.rowof = (const u16 *)d->d_graph[10];
     }
     d->g.m = m; d->g.n = n; d->g.nnz = nnz;
+    d->g.nphys = PL.nphys; d->g.prow = (const u32 *)d->d_graph[11]; d->g.cpj = (const u16 *)d->d_graph[12];
+    for (int k = 0; k < 17; k++) d->g.jb[k] = PL.jb[k];
     d->g.rp = (const int *)d->d_graph[0]; d->g.rc = (const u16 *)d->d_graph[1]; d->g.cp = (const int *)d->d_graph[2];
     d->g.cr = (const u16 *)d->d_graph[3]; d->g.cpos = (const u16 *)d->d_graph[4]; d->g.llr = (const double *)d->d_graph[5];
     d->g.vord = (const u16 *)d->d_graph[6]; d->g.vrec = (const u32 *)d->d_graph[7]; d->g.llr_s = (const double *)d->d_graph[8];
@@ -385,15 +483,15 @@ static int setup_kernels(swd_decoder *d) {
     d->T1 = std::min(256, std::max(64, r32up((n + 3) / 4)));
     if (const char *e = getenv("SWD_T1")) d->T1 = std::min(256, std::max(32, r32up(atoi(e))));
     PreSmem &S1 = d->PRE;
-    int o = 0; S1.off_msg = o; o += 8 * std::max(d->nnz, 1); o = r16(o);
+    int o = 0; S1.off_msg = o; o += 8 * std::max(d->nphys, 1); o = r16(o);
     S1.off_upar = o; o += 4 * m; o = r16(o);
     S1.off_synd = o; o += m; o = r16(o);
     S1.off_dec = o; o += n; o = r16(o);
     S1.off_misc = o; o += 64;
     S1.off_fwd = o;
     const bool ps = (c.bp_method == SWD_BP_PRODUCT_SUM);
-    if (ps) { o = r16(o); S1.off_fwd = o; o += 8 * std::max(d->nnz, 1); }
-    S1.total = o; S1.off_vrec = o; S1.off_cpos = o;
+    if (ps) { o = r16(o); S1.off_fwd = o; o += 8 * std::max(d->nphys, 1); }
+    S1.total = o; S1.off_vrec = o; S1.off_cpos = o; S1.off_prow = o;
     if (S1.total > 227 * 1024 || getenv("SWD_FORCE_STREAM")) {
         // messages streamed from HBM, one thread per shot (swd_stream.cuh); syndrome + parity bit words per thread in shared memory
         if (ps) { set_err("product-sum BP: window graph does not fit in shared memory (nnz too large)"); return SWD_ERR_UNSUPPORTED; }
@@ -408,9 +506,10 @@ static int setup_kernels(swd_decoder *d) {
     bool staged = false;
     {
         int q = r16(o); const int ov = q; q += 4 * n; q = r16(q); const int oc = q; q += 2 * std::max(d->nnz, 1); q = r16(q);
+        const int opr = q; q += 4 * m; q = r16(q);
         // staging must not cost occupancy: 256-thread CTAs are register limited to 3 per SM, so compare at that count
         const int occ_unstaged = std::min(3, (int)(233472 / (S1.total + 1024))), occ_staged = std::min(3, (int)(233472 / (q + 1024)));
-        if (q <= 227 * 1024 && occ_staged >= occ_unstaged && !getenv("SWD_PRE_UNSTAGED")) { staged = true; S1.off_vrec = ov; S1.off_cpos = oc; S1.total = q; }
+        if (q <= 227 * 1024 && occ_staged >= occ_unstaged && !getenv("SWD_PRE_UNSTAGED")) { staged = true; S1.off_vrec = ov; S1.off_cpos = oc; S1.off_prow = opr; S1.total = q; }
     }
     int occ = 0, st;
     if (!d->stream_mode) {
@@ -855,6 +954,36 @@ extern "C" int swd_decode_batch_host_packed(swd_decoder *d, const uint64_t *synd
 }
 
 extern "C" int swd_is_streamed(swd_decoder *d) { return d ? (d->stream_mode ? 1 : 0) : -1; }
+
+// Host-only diagnostic (no CUDA call): the physical message layout swd_create picks for the pre-BP kernel of this graph.
+extern "C" int swd_pre_bp_layout(int m, int n, const int32_t *colptr, const int32_t *rowidx, int optimize,
+                                 int32_t *slot_of_entry, int32_t *row_start, int64_t *stats) {
+    if (!colptr || !rowidx || m <= 0 || n <= 0 || colptr[0] != 0) { set_err("swd_pre_bp_layout: bad argument"); return SWD_ERR_INVALID; }
+    const int nnz = colptr[n];
+    if (n > 65534 || m > 65534 || nnz > 65535 || nnz < 0) { set_err("swd_pre_bp_layout: graph too large for 16-bit indices"); return SWD_ERR_UNSUPPORTED; }
+    std::vector<int> cp(colptr, colptr + n + 1), cr(std::max(nnz, 1)), rp(m + 1, 0), cpos(std::max(nnz, 1));
+    for (int c = 0; c < n; c++) {
+        if (cp[c + 1] < cp[c]) { set_err("swd_pre_bp_layout: colptr not monotone"); return SWD_ERR_INVALID; }
+        std::vector<int> rows(rowidx + cp[c], rowidx + cp[c + 1]);
+        std::sort(rows.begin(), rows.end());
+        for (size_t k = 0; k < rows.size(); k++) {
+            if (rows[k] < 0 || rows[k] >= m || (k && rows[k] == rows[k - 1])) { set_err("swd_pre_bp_layout: bad row index"); return SWD_ERR_INVALID; }
+            cr[cp[c] + k] = rows[k]; rp[rows[k] + 1]++;
+        }
+    }
+    for (int r = 0; r < m; r++) rp[r + 1] += rp[r];
+    { std::vector<int> fill(rp.begin(), rp.end() - 1); for (int c = 0; c < n; c++) for (int e = cp[c]; e < cp[c + 1]; e++) cpos[e] = fill[cr[e]]++; }
+    std::vector<u16> vord(n);
+    { std::vector<int> idx(n); for (int c = 0; c < n; c++) idx[c] = c;
+      std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return cp[a + 1] - cp[a] > cp[b + 1] - cp[b]; });
+      for (int c = 0; c < n; c++) vord[c] = (u16)idx[c]; }
+    PreLayout L;
+    pre_layout(m, n, nnz, cp, cr, rp, cpos, vord, optimize != 0, L);
+    if (slot_of_entry) for (int e = 0; e < nnz; e++) slot_of_entry[e] = L.phys[e];     // CSC entry (rows ascending inside a column) -> slot
+    if (row_start) for (int r = 0; r <= m; r++) row_start[r] = L.pstart[r];
+    if (stats) { stats[0] = L.nphys; stats[1] = L.excess0; stats[2] = L.excess; }
+    return SWD_OK;
+}
 
 extern "C" int swd_osd_last_outputs(swd_decoder *d, int64_t B, uint8_t *bp_dec, uint8_t *osd0, uint8_t *osdw,
                                     double *lpr, int32_t *bp_iteration) {

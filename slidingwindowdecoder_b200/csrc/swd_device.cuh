@@ -74,8 +74,18 @@ struct GraphDev {               // static window graph (device pointers)
     // first check pass of the full-window min-sum BP for an all-zero syndrome: in iteration 1 every bit-to-check message
     // is its column's prior (pyx:55-60), so the check-to-bit magnitudes do not depend on the shot and a syndrome bit
     // only flips the sign of its row.  nullptr: not available (product-sum, osd-only graphs).
-    const double *c2b1;         // [nnz]  CSR order
-    const u16 *rowof;           // [nnz]  CSR position -> row
+    const double *c2b1;         // [nphys]  physical slot order of the pre-BP kernel (pads: 0)
+    const u16 *rowof;           // [nphys]  physical slot -> row (pads: 0)
+    // Physical message layout of the pre-BP kernel (swd_api.cu: pre_layout).  The graph is the same for every shot, so the
+    // slot of every edge is chosen once on the host such that BOTH passes are (nearly) bank-conflict free: rows start on
+    // distinct 8-byte banks within every 16 consecutive rows (check pass: thread r reads prow[r] + k), and the order of the
+    // slots inside a row - free, ties between equal magnitudes give q1 = q2 - is picked so that the 16 edges a half-warp of
+    // the variable pass touches in step k fall on 16 distinct banks.
+    int nphys;                  // message slots incl. the few pad slots between rows
+    const u32 *prow;            // [m]    first physical slot | row length << 16
+    const u16 *cpj;             // [nnz]  jagged-diagonal map: cpj[jb[k] + sl] = physical slot of the k-th edge of the column at
+                                //        ownership slot sl (sl < number of columns of degree > k): lane-contiguous 16-bit loads
+    int jb[17];
 };
 
 struct GdgDev {                 // parameters of the decimation tree

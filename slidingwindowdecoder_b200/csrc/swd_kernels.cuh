@@ -18,7 +18,7 @@
 // ----------------------------------------------------------------------------------------------
 // K1: full-window BP
 // ----------------------------------------------------------------------------------------------
-struct PreSmem { int off_msg, off_upar, off_synd, off_dec, off_misc, total; int off_fwd; int off_vrec, off_cpos; };
+struct PreSmem { int off_msg, off_upar, off_synd, off_dec, off_misc, total; int off_fwd; int off_vrec, off_cpos, off_prow; };
 // off_fwd: product-sum forward products; off_vrec / off_cpos: staged copies of the static per-slot records and CSC->CSR map
 
 #ifndef SWD_PRE_MINB
@@ -27,12 +27,12 @@ struct PreSmem { int off_msg, off_upar, off_synd, off_dec, off_misc, total; int 
 // one variable-node update of the full-window BP (bp_guessing_decoder.pyx:98-127): ordered prefix / suffix sums; the
 // hard decision goes to s_dec[sl] (ownership-slot order), parity contributions to upar
 template <int DM>
-__device__ __forceinline__ double pre_vn_update(double *msg, u32 *upar, const u16 *cpos, const u16 *__restrict__ cr, const double prior,
-                                                const int e0, const int d, const int dw, u8 *dec_slot) {
+__device__ __forceinline__ double pre_vn_update(double *msg, u32 *upar, const u16 *cpj_sl, const int (&jb)[17], const u16 *__restrict__ cr,
+                                                const double prior, const int e0, const int d, const int dw, u8 *dec_slot) {
     double cc[DM], pre[DM]; int pp[DM];
     double t = prior;
 #pragma unroll
-    for (int k = 0; k < DM; k++) { if (k >= dw) break; if (k < d) { pp[k] = cpos[e0 + k]; cc[k] = msg[pp[k]]; } }
+    for (int k = 0; k < DM; k++) { if (k >= dw) break; if (k < d) { pp[k] = cpj_sl[jb[k]]; cc[k] = msg[pp[k]]; } }
 #pragma unroll
     for (int k = 0; k < DM; k++) { if (k >= dw) break; if (k < d) { pre[k] = t; t += cc[k]; } }
     const int hard = (t <= 0.0);
@@ -69,12 +69,14 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
     double *hs = hscratch + (size_t)blockIdx.x * 4 * n;           // last four posteriors, ownership-slot order (coalesced)
     const double fpos = alpha;
     u64 edge_iters = 0;
-    const u32 *vrec = g.vrec; const u16 *cpos = g.cpos;
+    const u32 *vrec = g.vrec; const u16 *cpj = g.cpj; const u32 *prow = g.prow;
     if (STAGED) {
         u32 *sv = pinned_smem<u32>(smem + S.off_vrec); u16 *sc = pinned_smem<u16>(smem + S.off_cpos);
+        u32 *sr = pinned_smem<u32>(smem + S.off_prow);
         for (int i = tid; i < n; i += T) sv[i] = g.vrec[i];
-        for (int i = tid; i < g.nnz; i += T) sc[i] = g.cpos[i];
-        vrec = sv; cpos = sc;
+        for (int i = tid; i < g.nnz; i += T) sc[i] = g.cpj[i];
+        for (int i = tid; i < m; i += T) sr[i] = g.prow[i];
+        vrec = sv; cpj = sc; prow = sr;
         __syncthreads();
     }
 
@@ -85,15 +87,15 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
             __syncthreads();
             for (int r = tid; r < m; r += T) upar[r] = 0;
 #pragma unroll 4
-            for (int p = tid; p < g.nnz; p += T) msg[p] = flip_sign(g.c2b1[p], (u32)s_synd[g.rowof[p]]);
+            for (int p = tid; p < g.nphys; p += T) msg[p] = flip_sign(g.c2b1[p], (u32)s_synd[g.rowof[p]]);
             for (int sl = tid; sl < n; sl += T) s_dec[sl] = 0;
         } else
         for (int sl = tid; sl < n; sl += T) {                  // pyx:55-60
             const u32 vr = vrec[sl];
-            const int e0 = (int)(vr & 0xffffu), d = (int)(vr >> 16);
+            const int d = (int)(vr >> 16);
             const double l = g.llr_s[sl];
 #pragma unroll 1
-            for (int k = 0; k < d; k++) msg[cpos[e0 + k]] = l;
+            for (int k = 0; k < d; k++) msg[cpj[g.jb[k] + sl]] = l;
             s_dec[sl] = 0;
         }
         __syncthreads();
@@ -108,7 +110,8 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
                 const double PMAX = 1.0 - 2.220446049250313e-16;
                 for (int r = tid; r < m; r += T) {
                     upar[r] = 0;
-                    const int p0 = g.rp[r], p1 = g.rp[r + 1];
+                    const u32 pr = prow[r];
+                    const int p0 = (int)(pr & 0xffffu), p1 = p0 + (int)(pr >> 16);
                     double tmp = 1.0;
                     for (int p = p0; p < p1; p++) { fwd[p] = tmp; tmp *= tanh(msg[p] * 0.5); }
                     tmp = 1.0;
@@ -124,7 +127,8 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
             } else
             for (int r = tid; r < m; r += T) {
                 upar[r] = 0;
-                const int p0 = g.rp[r], p1 = g.rp[r + 1];
+                const u32 pr = prow[r];
+                const int p0 = (int)(pr & 0xffffu), p1 = p0 + (int)(pr >> 16);
                 double m1 = SWD_BIG, m2 = SWD_BIG; int arg = -1; u32 par = s_synd[r];
                 for (int p = p0; p < p1; p++) {
                     const double b = msg[p];
@@ -152,7 +156,7 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
                 if (sl < n) { const u32 vr = vrec[sl]; e0 = (int)(vr & 0xffffu); d = (int)(vr >> 16); }
                 const int dw = __reduce_max_sync(FULLMASK, d);
                 if (sl < n) {
-                    const double t = pre_vn_update<DMAX>(msg, upar, cpos, g.cr, g.llr_s[sl], e0, d, dw, s_dec + sl);
+                    const double t = pre_vn_update<DMAX>(msg, upar, cpj + sl, g.jb, g.cr, g.llr_s[sl], e0, d, dw, s_dec + sl);
                     if (keep) hs[(size_t)(it & 3) * n + sl] = t;
                 }
             }

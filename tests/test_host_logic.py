@@ -176,3 +176,46 @@ def test_bench_reference_arm_prints_one_contract_line():
     import argparse, bench
     assert d["config"] == bench.config_block(argparse.Namespace(batch=32768, streams=3))     # the product arm's config, verbatim
     assert "modes_shots_per_s" in d["cpu_baseline"] and d["cpu_baseline"]["nproc"] >= 1
+
+
+@pytest.mark.parametrize("name", ["c1_gdg_sim_mt1", "c3_w5_gdg_mt1", "c5_w0_gdg_mt1"])
+def test_pre_bp_message_layout_is_valid_and_nearly_conflict_free(name):
+    """The static shared-memory layout swd_create picks for the full-window BP kernel (host code, no CUDA call): every edge
+    gets its own slot inside its row's range, the rows of a half-warp of the check pass start on distinct 8-byte banks, and
+    the variable pass is left with a small fraction of the extra wavefronts of the plain CSR order."""
+    from conftest import load_golden
+    from slidingwindowdecoder_b200 import _lib
+    lib = _lib.load()
+    mat = load_golden(name)["mat"].tocsc()
+    mat.sort_indices()
+    m, n = mat.shape
+    cp, ri = mat.indptr.astype(np.int32), mat.indices.astype(np.int32)
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    res = {}
+    for opt in (0, 1):
+        slot, rs, st = np.zeros(mat.nnz, np.int32), np.zeros(m + 1, np.int32), np.zeros(3, np.int64)
+        assert lib.swd_pre_bp_layout(m, n, cp.ctypes.data_as(i32p), ri.ctypes.data_as(i32p), opt, slot.ctypes.data, rs.ctypes.data, st.ctypes.data) == 0
+        rl = np.bincount(ri, minlength=m)
+        assert len(np.unique(slot)) == mat.nnz and slot.max() < st[0]
+        assert np.all(slot >= rs[ri]) and np.all(slot < rs[ri] + rl[ri])
+        assert np.all(rs[1:] >= rs[:-1] + rl)                          # rows do not overlap
+        res[opt] = (slot, rs, st)
+    slot0, rs0, st0 = res[0]
+    assert st0[0] == mat.nnz and np.array_equal(rs0, np.concatenate([[0], np.cumsum(np.bincount(ri, minlength=m))]))
+    slot1, rs1, st1 = res[1]
+    for g0 in range(0, m, 16):                                         # check pass: distinct banks inside a half-warp's rows
+        b = rs1[g0:min(g0 + 16, m)] & 15
+        assert len(np.unique(b)) == len(b)
+    assert st1[0] - mat.nnz <= 16 * ((m + 15) // 16)
+    assert st1[2] * 5 <= st0[2]                                        # at least 5x fewer conflicting accesses (measured: 50-100x)
+    # independent recount of the extra variable-pass wavefronts from the returned slots
+    deg = np.diff(cp)
+    vord = np.argsort(-deg, kind="stable")
+    extra = 0
+    for h0 in range(0, n, 16):
+        vs = vord[h0:h0 + 16]
+        for k in range(int(deg[vs[0]])):
+            banks = [int(slot1[cp[v] + k]) & 15 for v in vs if deg[v] > k]
+            c = np.bincount(banks, minlength=16)
+            extra += int(np.maximum(c - 1, 0).sum())
+    assert extra == st1[2]
