@@ -542,6 +542,12 @@ def run_ours(args):
                      "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
                      "kernels": {k: v for k, v in blocks.items() if k != dom},
                      "kernel_ms": kernel_ms, "kernel_ms_steps": Kp, "single_stream_ms_per_step": round(ms_prof / Kp, 3)})
+    # minimal-I/O figure: a design that keeps everything else on chip moves (m + n) / 8 + 1 bytes per shot-window
+    # (bit-packed syndrome in, correction + converge flag out) through HBM
+    mio = float(np.mean([(w.mat.shape[0] + w.mat.shape[1]) / 8.0 + 1.0 for w in plan.windows]))
+    roofline["minimal_io"] = {"bytes_per_shot_window": round(mio, 1),
+                              "gbs_at_value": round(value / world * n_win * mio / 1e9, 4),
+                              "frac_of_hbm_peak": round(value / world * n_win * mio / 1e9 / hbm_peak, 6)}
     # ---- CPU baseline on a bounded sample (rank 0, at every N)
     cpu_baseline = None if args.skip_cpu else cpu_baseline_block(plan, 12.0)
     launches = ctr_timed["kernel_launches"] + K * args.streams * (2 * len(plan.windows) + 1)
