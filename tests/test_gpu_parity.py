@@ -880,6 +880,33 @@ def test_streamed_bp_equals_shared_memory_bp(name, force, monkeypatch):
     assert b.counters()["pre_bp_edge_iters"] == a.counters()["pre_bp_edge_iters"]
 
 
+@pytest.mark.parametrize("name", ["c1_osdw_osd_cs10", "c3_w5_osdw_cs10", "c5_w4_gdg_mt1", "c4_w7_osdw_cs10"])
+def test_pre_bp_static_layout_equals_csr_order(name, monkeypatch):
+    """The full-window BP kernel with its host-chosen message layout (padded row starts, permuted slots inside a row, jagged
+    edge map; swd_api.cu pre_layout) against the same kernel with the slots in plain CSR order (SWD_PRE_NO_LAYOUT=1): the
+    check update does not depend on the order of the slots of a row, so corrections, flags, path metrics, BP decisions,
+    iteration counts and the whole posterior history must be bit-identical - and equal to the reference's goldens."""
+    from slidingwindowdecoder_b200 import bpgdg_decoder, osd_window
+    g = load_golden(name)
+    cls = osd_window if "osdw" in name else bpgdg_decoder
+    nshot = min(len(g["synd"]), 200)
+    a = cls(g["mat"], channel_probs=g["priors"], **g["kwargs"])
+    ra = a.decode_batch(g["synd"][:nshot], return_pm=True)
+    oa = a.last_outputs() if cls is osd_window else None
+    monkeypatch.setenv("SWD_PRE_NO_LAYOUT", "1")
+    b = cls(g["mat"], channel_probs=g["priors"], **g["kwargs"])
+    rb = b.decode_batch(g["synd"][:nshot], return_pm=True)
+    for x, y in zip(ra, rb):
+        assert np.array_equal(x, y)
+    assert np.array_equal(ra[1], g["conv"][:nshot])
+    if oa is not None:
+        ob = b.last_outputs()
+        for k in oa:
+            assert np.array_equal(oa[k], ob[k]), k
+        assert np.array_equal(ra[0], g["dec"][:nshot])
+    assert b.counters()["pre_bp_edge_iters"] == a.counters()["pre_bp_edge_iters"]
+
+
 def test_unwindowed_144_limits_lifted():
     """the un-windowed [[144,12,12]] DEM (936 x 8784, 30672 edges; IBM.ipynb:122-123) used to be rejected with
     SWD_ERR_UNSUPPORTED because its messages exceed one SM's shared memory.  It now constructs for all three kinds and a
