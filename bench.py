@@ -570,6 +570,10 @@ def run_ours(args):
         "results": {"shots": int(total_shots), "flagged": int(counts_res[0]), "failed": int(counts_res[1]),
                     "gdg_fraction": round(ctr["gdg_shots"] / max(1, ctr["shots"]), 4)},
         "counters": ctr_timed,
+        # the min-sum work counters (edge / VN / CN / slot iterations) only accumulate while profiling is on (counting them costs
+        # 1.7 % of the shots/s): these are the ones of the `kernel_ms_steps` profiled single-stream steps the roofline is computed from
+        "work_counters_profiled_steps": {k: int(ctr[k]) for k in ("shots", "gdg_shots", "paths_run", "bp_calls", "path_edge_iters", "path_vn_iters",
+                                                                   "path_cn_iters", "path_slot_iters", "pre_bp_edge_iters") if k in ctr},
     }
     print(json.dumps(line), file=_STDOUT, flush=True)
     if world > 1:

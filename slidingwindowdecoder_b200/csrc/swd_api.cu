@@ -466,7 +466,7 @@ static int setup_kernels(swd_decoder *d) {
     if (c.kind == SWD_KIND_OSD_WINDOW) { P.factor = c.ms_scaling_factor; P.low_error = 0; }
     P.rec_stride = r16((int)sizeof(RecHeader) + 4 * ((nn + 31) / 32));
     P.side_stride = r16((int)sizeof(SideHeader) + nn + 2 * m);
-    P.shared_T = 0; P.n_nodes = 0; P.node_stride = 16;
+    P.shared_T = 0; P.n_nodes = 0; P.node_stride = 16; P.count_work = d->profiling ? 1 : 0;
     P.bak_stride = SWD_DIET ? r16(nn) + 2 * r16(m) : 16;
     // ---- blob layouts: global (worst case), shared-memory tier A (typical shots), tier B (worst case)
     const int lcap = std::min(255, d->max_row_deg);
@@ -1003,6 +1003,7 @@ extern "C" int swd_osd_last_outputs(swd_decoder *d, int64_t B, uint8_t *bp_dec, 
 extern "C" int swd_set_profiling(swd_decoder *d, int enable) {
     if (!d) return SWD_ERR_INVALID;
     d->profiling = enable != 0;
+    d->P.count_work = d->Plat.count_work = d->profiling ? 1 : 0;      // the work counters of the min-sum calls (swd_get_counters)
     return SWD_OK;
 }
 extern "C" int swd_get_kernel_times(swd_decoder *d, double *ms, uint64_t *launches) {

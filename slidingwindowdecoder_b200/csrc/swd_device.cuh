@@ -100,6 +100,7 @@ struct GdgDev {                 // parameters of the decimation tree
     // prefix of favour/flip decisions, so they are computed once per prefix ("nodes") instead of once per path
     int shared_T, n_nodes, node_stride;
     int bak_stride;             // bytes per tree-path backup (vn_mask, cn_mask, cn_deg)
+    int count_work;             // 1 while profiling is enabled (swd_set_profiling): the min-sum calls count their work
     int node_off_err, node_off_cn, node_off_deg, node_off_flip, node_off_msg, node_off_hist;
 };
 
@@ -521,6 +522,7 @@ struct Ctx {
     u8 *cn_deg, *flip;
     u32 *upar;
     double *red_d; int *red_i; int *misc;
+    int count_work;                     // accumulate the per-call work counters (edge / VN / CN / slot iterations)
     int zslot;                          // index (relative to msg) of a shared-memory double that always holds +0.0
 };
 
@@ -824,18 +826,6 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
         na = run;
         __syncthreads();
     }
-    // work counters: the active sets do not change inside a call, so count them once (not per iteration)
-    u32 my_vn = 0, my_edges = 0, my_cn = 0;
-#pragma unroll
-    for (int i = 0; i < VPT; i++) {
-        const int sl = own_slot(i, tid, T);
-        if (sl < c.nn) { const int j = c.vperm[sl]; if (c.vn_mask[j] < 0) { my_vn++; my_edges += (u32)(c.voff[j + 1] - c.voff[j]); } }
-    }
-    u32 my_slots = 0;                                       // message slots (live + dead + pad) of the owned active rows
-    for (int i = 0; i * T < na; i++) {
-        const int k = own_slot(i, tid, T);
-        if (k < na) { const int q = alist[k]; my_cn++; my_slots += (u32)(c.coff[q + 1] - c.coff[q]); }
-    }
     int it = 0, conv = 0;
 #ifndef SWD_MISM_SMEM
 #define SWD_MISM_SMEM 1
@@ -893,8 +883,26 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
     }
     // `it` variable passes were executed; check updates: one per variable pass, plus one more when the call converged
     // before the last iteration (the messages of that extra pass are never used)
+    // work counters: the active sets do not change inside a call, so count them once (not per iteration) - and after the
+    // loop, so that they do not occupy registers inside it
+    u32 my_vn = 0, my_edges = 0, my_cn = 0;
+    // (only while profiling is on, swd_set_profiling: the counting costs 1.7 % of the shots/s - A/B r2b)
+    if (c.count_work)
+#pragma unroll
+    for (int i = 0; i < VPT; i++) {
+        const int sl = own_slot(i, tid, T);
+        if (sl < c.nn) { const int j = c.vperm[sl]; if (c.vn_mask[j] < 0) { my_vn++; my_edges += (u32)(c.voff[j + 1] - c.voff[j]); } }
+    }
+    u32 my_slots = 0;                                       // message slots (live + dead + pad) of the owned active rows
+    if (c.count_work)
+    for (int i = 0; i * T < na; i++) {
+        const int k = own_slot(i, tid, T);
+        if (k < na) { const int q = alist[k]; my_cn++; my_slots += (u32)(c.coff[q + 1] - c.coff[q]); }
+    }
+    if (c.count_work) {
     const u32 vp = (u32)it, cp = (u32)(conv ? (it < num_iter ? it + 1 : it) : it);
     edge_iters += (u64)my_edges * vp; vn_iters += my_vn * vp; cn_iters += my_cn * cp; slot_iters += (u64)my_slots * cp;
+    }
     if (iters_done) *iters_done = conv ? it : (num_iter > 0 ? num_iter : 0);
     return conv;
 }

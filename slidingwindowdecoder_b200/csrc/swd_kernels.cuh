@@ -476,7 +476,7 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
     unsigned char *blob = smem;
     unsigned char *st = smem + L.blob_bytes;
     Ctx c;
-    c.m = L.m; c.nn = L.nn; c.factor = P.factor; c.low_error = P.low_error;
+    c.m = L.m; c.nn = L.nn; c.factor = P.factor; c.low_error = P.low_error; c.count_work = P.count_work;
     c.prior = pinned_smem<const double>(blob + L.off_prior);
     c.voff = pinned_smem<const u16>(blob + L.off_voff); c.coff = pinned_smem<const u16>(blob + L.off_coff);
     c.crank = (const u16 *)(blob + L.off_crank);

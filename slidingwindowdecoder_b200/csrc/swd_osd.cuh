@@ -68,7 +68,7 @@ post_bp_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, in
     unsigned char *blob = smem;
     unsigned char *st = smem + L.blob_bytes;
     Ctx c;
-    c.m = L.m; c.nn = L.nn; c.factor = P.factor; c.low_error = 0;
+    c.m = L.m; c.nn = L.nn; c.factor = P.factor; c.low_error = 0; c.count_work = P.count_work;
     c.prior = (const double *)(blob + L.off_prior);
     c.voff = (const u16 *)(blob + L.off_voff); c.coff = (const u16 *)(blob + L.off_coff);
     c.crank = (const u16 *)(blob + L.off_crank);
