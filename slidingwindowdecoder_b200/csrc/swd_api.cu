@@ -519,6 +519,14 @@ static int setup_kernels(swd_decoder *d) {
     else d->pre_fn = d->max_col_deg <= 6 ? SWD_PRE_PICK(6, 256, SWD_PRE_MINB) : (d->max_col_deg <= 8 ? SWD_PRE_PICK(8, 256, SWD_PRE_MINB) : SWD_PRE_PICK(16, 256, 2));
     st = occupancy(d->pre_fn, d->T1, S1.total, &occ);
     if (st) return st;
+    if (!ps && d->max_col_deg <= 8 && (int)(233472 / (S1.total + 1024)) > occ && !getenv("SWD_T1")) {
+        // small windows: shared memory would allow more CTAs than the 3-per-SM register budget (85) of the default instantiation -
+        // take the 64-register one when it raises the number of resident warps ([[72,12,6]] windows: 4 instead of 3 CTAs of 224 threads)
+        pre_fn_t f4 = d->max_col_deg <= 6 ? SWD_PRE_PICK(6, 256, 4) : SWD_PRE_PICK(8, 256, 4);
+        int occ4 = 0;
+        if ((st = occupancy(f4, d->T1, S1.total, &occ4))) return st;
+        if (occ4 > occ) { d->pre_fn = f4; occ = occ4; }
+    }
     if (occ * d->T1 < 512 && !getenv("SWD_T1")) {
         // shared memory allows fewer than 16 warps per SM with 256-thread CTAs: use one large CTA per SM instead
         const int want = std::min(1024, std::max(256, r32up(std::max((n + 3) / 4, m))));

@@ -47,6 +47,37 @@ __device__ __forceinline__ double pre_vn_update(double *msg, u32 *upar, const u1
     return t;
 }
 
+// The same update for a warp whose 32 columns all have degree K (the columns are owned in degree order, so that is nearly every
+// warp): no per-edge predicates, selects or loop tests - load, K-term prefix chain, store.  Same sums in the same order.
+template <int K>
+__device__ __forceinline__ double pre_vn_uniform(double *msg, const u16 *cpj_sl, const int (&jb)[17], const double prior, double (&b2c)[K], int (&pp)[K]) {
+    double cc[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { pp[k] = cpj_sl[jb[k]]; cc[k] = msg[pp[k]]; }
+    double t = prior;
+#pragma unroll
+    for (int k = 0; k < K; k++) { b2c[k] = t; t += cc[k]; }
+    double s = 0.0;
+#pragma unroll
+    for (int k = K - 1; k >= 0; k--) { b2c[k] = b2c[k] + s; s += cc[k]; }
+    return t;
+}
+template <int K>
+__device__ __forceinline__ double pre_vn_uniform_apply(double *msg, u32 *upar, const u16 *cpj_sl, const int (&jb)[17], const u16 *__restrict__ cr,
+                                                       const double prior, const int e0, u8 *dec_slot) {
+    double b2c[K]; int pp[K];
+    const double t = pre_vn_uniform<K>(msg, cpj_sl, jb, prior, b2c, pp);
+    const int hard = (t <= 0.0);
+    *dec_slot = (u8)hard;
+    if (hard) {
+#pragma unroll 1
+        for (int k = 0; k < K; k++) atomicXor(&upar[cr[e0 + k]], 1u);
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) msg[pp[k]] = b2c[k];
+    return t;
+}
+
 // MAXT = 256: several CTAs per SM (small windows).  MAXT = 1024: windows whose messages leave room for one CTA per
 // SM only (e.g. 576 x 4896, 136 KB) get one large CTA instead of eight warps per SM.
 // PS = true: product-sum check update (tanh products, forward / backward) instead of normalised min-sum.
@@ -149,15 +180,33 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
             }
             __syncthreads();
             const bool keep = full_hist || (it >= max_iter - 4);
+            double *hs_it = hs + (size_t)(it & 3) * n;
             // ---- variable pass: columns are owned in degree order, so a warp's loop bound is uniform
             for (int base = 0; base < n; base += T) {
                 const int sl = base + tid;
                 int e0 = 0, d = 0;
                 if (sl < n) { const u32 vr = vrec[sl]; e0 = (int)(vr & 0xffffu); d = (int)(vr >> 16); }
                 const int dw = __reduce_max_sync(FULLMASK, d);
+#ifndef SWD_PRE_UNIFORM
+#define SWD_PRE_UNIFORM 1
+#endif
+                const bool uni = SWD_PRE_UNIFORM && dw >= 1 && dw <= 6 && __all_sync(FULLMASK, d == dw);     // implies sl < n in every lane
+                if (uni) {
+                    double t;
+                    const double pr = g.llr_s[sl];
+                    switch (dw) {
+                        case 1: t = pre_vn_uniform_apply<1>(msg, upar, cpj + sl, g.jb, g.cr, pr, e0, s_dec + sl); break;
+                        case 2: t = pre_vn_uniform_apply<2>(msg, upar, cpj + sl, g.jb, g.cr, pr, e0, s_dec + sl); break;
+                        case 3: t = pre_vn_uniform_apply<3>(msg, upar, cpj + sl, g.jb, g.cr, pr, e0, s_dec + sl); break;
+                        case 4: t = pre_vn_uniform_apply<4>(msg, upar, cpj + sl, g.jb, g.cr, pr, e0, s_dec + sl); break;
+                        case 5: t = pre_vn_uniform_apply<5>(msg, upar, cpj + sl, g.jb, g.cr, pr, e0, s_dec + sl); break;
+                        default: t = pre_vn_uniform_apply<6>(msg, upar, cpj + sl, g.jb, g.cr, pr, e0, s_dec + sl); break;
+                    }
+                    if (keep) hs_it[sl] = t;
+                } else
                 if (sl < n) {
                     const double t = pre_vn_update<DMAX>(msg, upar, cpj + sl, g.jb, g.cr, g.llr_s[sl], e0, d, dw, s_dec + sl);
-                    if (keep) hs[(size_t)(it & 3) * n + sl] = t;
+                    if (keep) hs_it[sl] = t;
                 }
             }
             edge_iters += 1;
