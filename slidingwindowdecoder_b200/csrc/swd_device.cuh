@@ -765,6 +765,31 @@ __device__ __forceinline__ double vn_update(Ctx &c, const int j, const int e0, c
     return t;
 }
 
+// The same update when every active lane of the warp holds a VN of degree K (VNs are owned in degree order): no per-edge
+// predicates, selects or loop tests.  Same sums in the same order as vn_update.
+#ifndef SWD_VN_UNIFORM
+#define SWD_VN_UNIFORM 1
+#endif
+template <int K>
+__device__ __forceinline__ double vn_uniform(Ctx &c, const int j, const int e0) {
+    double cc[K], b[K]; int pp[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { pp[k] = c.vpos[e0 + k]; cc[k] = c.msg[pp[k]]; }
+    double t = c.prior[j];
+#pragma unroll
+    for (int k = 0; k < K; k++) { b[k] = t; t += cc[k]; }
+    const int hard = (t <= 0.0);
+    c.error[j] = (i8)hard;
+    if (hard) {
+#pragma unroll 1
+        for (int k = 0; k < K; k++) atomicXor(&c.upar[c.vrow[e0 + k]], 1u);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = K - 1; k >= 0; k--) { c.msg[pp[k]] = b[k] + s; s += cc[k]; }
+    return t;
+}
+
 // BPGD::min_sum_log (bpgd.cpp:97-197) on the shortened graph, whole CTA.
 // h[i][s]: posterior history of the VN owned as slot i, ring slot s = iteration % 4.
 // Two barriers per iteration: the H*error == syndrome test of iteration `it` (bpgd.cpp:185-194;
@@ -867,14 +892,21 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
         // ---- variable pass: ordered prefix / suffix sums (bpgd.cpp:151-182); predicated straight-line code per slot.
         //      VNs are owned in degree order, so most warps only hold VNs of degree <= 3 and take the short body.
         const int ring = it & 3;
-#pragma unroll
-        for (int i = 0; i < VPT; i++) {
+#pragma unroll 1
+        for (int i = 0; i < VPT; i++) {      // rolled: one copy of the update bodies (instruction-cache footprint of the iteration)
             const int sl = own_slot(i, tid, T);
             int j = -1, e0 = 0, d = 0;
             if (sl < c.nn) { j = c.vperm[sl]; if (c.vn_mask[j] < 0) { e0 = c.voff[j]; d = c.voff[j + 1] - e0; } else j = -1; }
             const int dw = __reduce_max_sync(FULLMASK, d);
+            const bool uni = SWD_VN_UNIFORM && dw <= 3 && __all_sync(FULLMASK, j < 0 || d == dw);
             if (j >= 0) {
-                const double t = vn_update<DMAX>(c, j, e0, d, dw);     // dw: warp-uniform loop bound (VNs are owned in degree order)
+                double t;
+                if (uni) {
+                    if (dw == 3) t = vn_uniform<3>(c, j, e0);
+                    else if (dw == 2) t = vn_uniform<2>(c, j, e0);
+                    else t = vn_uniform<1>(c, j, e0);
+                } else
+                t = vn_update<DMAX>(c, j, e0, d, dw);     // dw: warp-uniform loop bound (VNs are owned in degree order)
                 h[i][ring] = t;      // dynamic ring index: the history lives in (L1/L2-backed) local memory, written once per
                                      // iteration and read once per call by select_vn - it does not occupy 32 registers
             }
