@@ -173,6 +173,19 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
                     par ^= (u32)(b <= 0.0);
                 }
                 const double q1 = m1 * fpos, q2 = m2 * fpos;
+#ifndef SWD_PRE_SWEEP2
+#define SWD_PRE_SWEEP2 1
+#endif
+                if (SWD_PRE_SWEEP2 && m1 != 0.0) {
+                    // no message of the row is an exact zero, so "b <= 0" is the sign bit: every slot gets +-q1 (only the sign bit of
+                    // the old message is used), then the argmin slot is patched with +-q2 of the sign just written
+                    const int q1lo = __double2loint(q1), q1hi = __double2hiint(q1) ^ (int)(par << 31);
+                    for (int p = p0; p < p1; p++) msg[p] = __hiloint2double(q1hi ^ (__double2hiint(msg[p]) & (int)0x80000000), q1lo);
+                    if (arg >= 0) {
+                        const int x = (__double2hiint(msg[arg]) ^ __double2hiint(q1)) & (int)0x80000000;
+                        msg[arg] = __hiloint2double(__double2hiint(q2) ^ x, __double2loint(q2));
+                    }
+                } else
                 for (int p = p0; p < p1; p++) {
                     const double b = msg[p];
                     msg[p] = flip_sign((p == arg) ? q2 : q1, par ^ (u32)(b <= 0.0));
