@@ -920,7 +920,7 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
     u32 my_vn = 0, my_edges = 0, my_cn = 0;
     // (only while profiling is on, swd_set_profiling: the counting costs 1.7 % of the shots/s - A/B r2b)
     if (c.count_work)
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < VPT; i++) {
         const int sl = own_slot(i, tid, T);
         if (sl < c.nn) { const int j = c.vperm[sl]; if (c.vn_mask[j] < 0) { my_vn++; my_edges += (u32)(c.voff[j + 1] - c.voff[j]); } }
@@ -949,7 +949,7 @@ __device__ __forceinline__ int select_vn(Ctx &c, const double (&h)[VPT][4], int 
     double best = SWD_MAX_PM, bestn = SWD_MAX_PM; int bi = 0x7fffffff, bni = 0x7fffffff;
     int any_dec = 0;
     if (tid == 0) c.misc[0] = 0x7fffffff;                    // failpos
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < VPT; i++) {
         const int sl = own_slot(i, tid, T);
         if (sl < c.nn) {
@@ -989,7 +989,7 @@ __device__ __forceinline__ int select_vn(Ctx &c, const double (&h)[VPT][4], int 
         // (1 | value << 8) to their checks' parity words - `upar` is zero for every active check between two min-sum
         // calls (the check pass clears it, bp_run) and is cleared again by the next call's first check pass - so no
         // thread scans whole rows here (and `cvn` is only touched on the contradiction path below).
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < VPT; i++) {
             const int sl = own_slot(i, tid, T);
             if (sl < c.nn) {
@@ -1031,7 +1031,7 @@ __device__ __forceinline__ int select_vn(Ctx &c, const double (&h)[VPT][4], int 
         __syncthreads();
         const int failpos = c.misc[0];
         if (failpos != 0x7fffffff) {                         // contradiction: branch is dead
-#pragma unroll
+#pragma unroll 1
             for (int i = 0; i < VPT; i++) {
                 const int sl = own_slot(i, tid, T);
                 if (sl < c.nn) {
@@ -1048,7 +1048,7 @@ __device__ __forceinline__ int select_vn(Ctx &c, const double (&h)[VPT][4], int 
             const int q = own_slot(i, tid, T);
             if (q < c.m && ndg[i] >= 0) { const int r = c.cperm[q]; c.cn_deg[r] = (u8)ndg[i]; c.cn_mask[r] = (i8)nmk[i]; }
         }
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < VPT; i++) {
             const int sl = own_slot(i, tid, T);
             if (sl < c.nn) {
