@@ -851,6 +851,16 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
         na = run;
         __syncthreads();
     }
+#ifndef SWD_VN_JPACK
+#define SWD_VN_JPACK 1
+#endif
+    u32 jj01 = 0xffffffffu, jj23 = 0xffffffffu;
+    if (SWD_VN_JPACK && VPT == 4) {
+        const int s0 = own_slot(0, tid, T), s1 = own_slot(1, tid, T), s2 = own_slot(2, tid, T), s3 = own_slot(3, tid, T);
+        const u32 j0 = s0 < c.nn ? c.vperm[s0] : 0xffffu, j1 = s1 < c.nn ? c.vperm[s1] : 0xffffu;
+        const u32 j2 = s2 < c.nn ? c.vperm[s2] : 0xffffu, j3 = s3 < c.nn ? c.vperm[s3] : 0xffffu;
+        jj01 = j0 | (j1 << 16); jj23 = j2 | (j3 << 16);
+    }
     int it = 0, conv = 0;
 #ifndef SWD_MISM_SMEM
 #define SWD_MISM_SMEM 1
@@ -894,9 +904,16 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
         const int ring = it & 3;
 #pragma unroll 1
         for (int i = 0; i < VPT; i++) {      // rolled: one copy of the update bodies (instruction-cache footprint of the iteration)
-            const int sl = own_slot(i, tid, T);
             int j = -1, e0 = 0, d = 0;
+            if (SWD_VN_JPACK && VPT == 4) {
+                // the thread's four VNs, packed once per call: no ownership arithmetic / vperm load per round
+                const u32 w = (i < 2) ? jj01 : jj23;
+                j = (int)((w >> ((i & 1) << 4)) & 0xffffu);
+                if (j != 0xffff && c.vn_mask[j] < 0) { e0 = c.voff[j]; d = c.voff[j + 1] - e0; } else j = -1;
+            } else {
+            const int sl = own_slot(i, tid, T);
             if (sl < c.nn) { j = c.vperm[sl]; if (c.vn_mask[j] < 0) { e0 = c.voff[j]; d = c.voff[j + 1] - e0; } else j = -1; }
+            }
             const int dw = __reduce_max_sync(FULLMASK, d);
             const bool uni = SWD_VN_UNIFORM && dw <= 3 && __all_sync(FULLMASK, j < 0 || d == dw);
             if (j >= 0) {
