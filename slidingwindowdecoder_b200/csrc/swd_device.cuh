@@ -653,11 +653,17 @@ __device__ __forceinline__ double flip_sign(double x, u32 flip) {
 // do they enter min1 / min2.  The masks are shifted in most-significant-first (one funnel shift each): after S slots,
 // slot k sits at bit S - 1 - k.  neg: the sign bit (an exact +0.0, which also counts as "<= 0", bpgd.cpp:124, is caught by
 // the caller: it makes min1 zero).  dead: exponent field all ones <=> (|hi| + 0x00100000) carries into bit 31.
+#ifndef SWD_LATE_CLIP
+#define SWD_LATE_CLIP 1
+#endif
+// CLIPPED = false: the +-50 clip of bpgd.cpp:119-121 is left to the caller - clipping is monotone, so the two smallest clipped
+// magnitudes are the clipped two smallest magnitudes (check_update applies it to min1 / min2 once per row).
+template <bool CLIPPED = true>
 __device__ __forceinline__ void check_slot(const double b, const int k, double &m1, double &m2, int &arg, u32 &neg, u32 &dead) {
     const u32 hi = (u32)__double2hiint(b);
     const u32 ahi = hi & 0x7fffffffu;
     double a = __hiloint2double((int)ahi, __double2loint(b));
-    a = (a > SWD_CLIP) ? SWD_CLIP : a;                           // bpgd.cpp:119-121
+    if (CLIPPED) a = (a > SWD_CLIP) ? SWD_CLIP : a;              // bpgd.cpp:119-121
     const bool lt = a < m1;
     const double h = lt ? m1 : a;                                // max(m1, a); NaN stays NaN
     m2 = (h < m2) ? h : m2;
@@ -704,12 +710,18 @@ __device__ __forceinline__ void check_update(Ctx &c, int p0, int len, int cm, do
     double m1 = SWD_BIG, m2 = SWD_BIG; int arg = -1;
     u32 neg = 0, dead = 0;
     // rows have an odd number of slots (pad): the first one alone, then two per trip
-    check_slot(row[0], 0, m1, m2, arg, neg, dead);
+    check_slot<!SWD_LATE_CLIP>(row[0], 0, m1, m2, arg, neg, dead);
 #pragma unroll 1
     for (int k = 1; k < len; k += 2) {
         const double b0 = row[k], b1 = row[k + 1];
-        check_slot(b0, k, m1, m2, arg, neg, dead);
-        check_slot(b1, k + 1, m1, m2, arg, neg, dead);
+        check_slot<!SWD_LATE_CLIP>(b0, k, m1, m2, arg, neg, dead);
+        check_slot<!SWD_LATE_CLIP>(b1, k + 1, m1, m2, arg, neg, dead);
+    }
+    if (SWD_LATE_CLIP) {
+        // fewer than two live magnitudes below the 1e308 sentinel (a check of degree 1, or magnitudes that overflowed): the exact
+        // slot-by-slot path; else clip the two minima (min of clipped values = clipped min, for both order statistics)
+        if (!(m2 < SWD_BIG)) { check_update_long(row, len, cm, fpos, fneg); return; }
+        m1 = (m1 > SWD_CLIP) ? SWD_CLIP : m1; m2 = (m2 > SWD_CLIP) ? SWD_CLIP : m2;
     }
     if (m1 == 0.0) neg = check_neg_mask_exact(row, len);
     const u32 par = (u32)cm ^ (__popc(neg) & 1u);

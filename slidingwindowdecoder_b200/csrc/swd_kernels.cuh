@@ -161,16 +161,32 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
                 const u32 pr = prow[r];
                 const int p0 = (int)(pr & 0xffffu), p1 = p0 + (int)(pr >> 16);
                 double m1 = SWD_BIG, m2 = SWD_BIG; int arg = -1; u32 par = s_synd[r];
+                // the +-50 clip (pyx:74-76) is monotone: the two smallest clipped magnitudes are the clipped two smallest
+                // magnitudes, so it is applied to min1 / min2 once per row ...
                 for (int p = p0; p < p1; p++) {
                     const double b = msg[p];
-                    double a = fabs(b);
-                    a = (a > SWD_CLIP) ? SWD_CLIP : a;
+                    const double a = fabs(b);
                     const bool lt = a < m1;
                     const double hi = lt ? m1 : a;
                     m2 = (hi < m2) ? hi : m2;
                     m1 = lt ? a : m1;
                     arg = lt ? p : arg;
                     par ^= (u32)(b <= 0.0);
+                }
+                if (m2 < SWD_BIG) { m1 = (m1 > SWD_CLIP) ? SWD_CLIP : m1; m2 = (m2 > SWD_CLIP) ? SWD_CLIP : m2; }
+                else {
+                    // ... unless fewer than two magnitudes lie below the 1e308 sentinel (a row of weight 1, or sums that
+                    // overflowed): slot-by-slot clip as the reference writes it
+                    m1 = SWD_BIG; m2 = SWD_BIG; arg = -1;
+                    for (int p = p0; p < p1; p++) {
+                        double a = fabs(msg[p]);
+                        a = (a > SWD_CLIP) ? SWD_CLIP : a;
+                        const bool lt = a < m1;
+                        const double hi = lt ? m1 : a;
+                        m2 = (hi < m2) ? hi : m2;
+                        m1 = lt ? a : m1;
+                        arg = lt ? p : arg;
+                    }
                 }
                 const double q1 = m1 * fpos, q2 = m2 * fpos;
 #ifndef SWD_PRE_SWEEP2
