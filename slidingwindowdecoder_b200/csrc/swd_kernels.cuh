@@ -546,6 +546,13 @@ __device__ __forceinline__ void record_result(Ctx &c, u8 *rec, int converged, co
     }
 }
 
+// 16-byte vector copy of a small state array (both sides 16-byte aligned, allocations padded to 16 bytes)
+__device__ __forceinline__ void copy_vec16(void *dst, const void *src, int nbytes, int tid, int T) {
+    const int nv = (nbytes + 15) >> 4;
+#pragma unroll 1
+    for (int i = tid; i < nv; i += T) ((uint4 *)dst)[i] = ((const uint4 *)src)[i];
+}
+
 template <int VPT, int DMAX, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int phase, int tier, int capA) {
@@ -685,10 +692,8 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
             const i8 *ncn = (const i8 *)(pnode + P.node_off_cn);
             const u8 *ndg = pnode + P.node_off_deg, *nfl = pnode + P.node_off_flip;
             const double *nh = (const double *)(pnode + P.node_off_hist);
-#pragma unroll 1
-            for (int j = tid; j < c.nn; j += T) { c.vn_mask[j] = nvn[j]; c.error[j] = ner[j]; }
-#pragma unroll 1
-            for (int r = tid; r < c.m; r += T) { c.cn_mask[r] = ncn[r]; c.cn_deg[r] = ndg[r]; c.flip[r] = nfl[r]; }
+            copy_vec16(c.vn_mask, nvn, c.nn, tid, T); copy_vec16(c.error, ner, c.nn, tid, T);
+            copy_vec16(c.cn_mask, ncn, c.m, tid, T); copy_vec16(c.cn_deg, ndg, c.m, tid, T); copy_vec16(c.flip, nfl, c.m, tid, T);
 #pragma unroll
             for (int i = 0; i < VPT; i++)
 #pragma unroll
@@ -909,12 +914,9 @@ path_kernel(Workspace ws, SubLayout LG, SubLayout L, PathSmem S, GdgDev P, int p
             u8 *ndg = nd + P.node_off_deg, *nfl = nd + P.node_off_flip;
             double *nm = (double *)(nd + P.node_off_msg), *nh = (double *)(nd + P.node_off_hist);
             __syncthreads();
-#pragma unroll 1
-            for (int j = tid; j < c.nn; j += T) { nvn[j] = c.vn_mask[j]; ner[j] = c.error[j]; }
-#pragma unroll 1
-            for (int r = tid; r < c.m; r += T) { ncn[r] = c.cn_mask[r]; ndg[r] = c.cn_deg[r]; nfl[r] = c.flip[r]; }
-#pragma unroll 1
-            for (int p = tid; p < c.es; p += T) nm[p] = c.msg[p];
+            copy_vec16(nvn, c.vn_mask, c.nn, tid, T); copy_vec16(ner, c.error, c.nn, tid, T);
+            copy_vec16(ncn, c.cn_mask, c.m, tid, T); copy_vec16(ndg, c.cn_deg, c.m, tid, T); copy_vec16(nfl, c.flip, c.m, tid, T);
+            copy_vec16(nm, c.msg, 8 * c.es, tid, T);
 #pragma unroll
             for (int i = 0; i < VPT; i++)
 #pragma unroll
