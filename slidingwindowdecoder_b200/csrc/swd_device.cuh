@@ -864,9 +864,21 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
         __syncthreads();
     }
 #ifndef SWD_VN_JPACK
-#define SWD_VN_JPACK 1
+#define SWD_VN_JPACK 2      /* 2: (index, first edge, degree) records; 1: indices only; 0: ownership arithmetic per round */
 #endif
     u32 jj01 = 0xffffffffu, jj23 = 0xffffffffu;
+    u32 vr0 = 0, vr1 = 0, vr2 = 0, vr3 = 0;
+    if (SWD_VN_JPACK == 2 && VPT == 4) {
+        auto rec = [&](int i) -> u32 {
+            const int sl = own_slot(i, tid, T);
+            if (sl >= c.nn) return 0u;
+            const int j = c.vperm[sl];
+            if (c.vn_mask[j] >= 0) return 0u;
+            const int e0 = c.voff[j], d = c.voff[j + 1] - e0;
+            return (u32)j | ((u32)e0 << 12) | ((u32)d << 27);
+        };
+        vr0 = rec(0); vr1 = rec(1); vr2 = rec(2); vr3 = rec(3);
+    } else
     if (SWD_VN_JPACK && VPT == 4) {
         const int s0 = own_slot(0, tid, T), s1 = own_slot(1, tid, T), s2 = own_slot(2, tid, T), s3 = own_slot(3, tid, T);
         const u32 j0 = s0 < c.nn ? c.vperm[s0] : 0xffffu, j1 = s1 < c.nn ? c.vperm[s1] : 0xffffu;
@@ -917,7 +929,13 @@ __device__ __forceinline__ int bp_run(Ctx &c, double (&h)[VPT][4], int num_iter,
 #pragma unroll 1
         for (int i = 0; i < VPT; i++) {      // rolled: one copy of the update bodies (instruction-cache footprint of the iteration)
             int j = -1, e0 = 0, d = 0;
-            if (SWD_VN_JPACK && VPT == 4) {
+            if (SWD_VN_JPACK == 2 && VPT == 4) {
+                // the thread's four VNs as packed records (index | first edge << 12 | degree << 27; degree 0: decided or none), built
+                // once per call - the masks do not change inside a call; the four registers rotate, the current one is vr0
+                const u32 w = vr0; vr0 = vr1; vr1 = vr2; vr2 = vr3; vr3 = w;
+                d = (int)(w >> 27);
+                if (d) { j = (int)(w & 0xfffu); e0 = (int)((w >> 12) & 0x7fffu); }
+            } else if (SWD_VN_JPACK && VPT == 4) {
                 // the thread's four VNs, packed once per call: no ownership arithmetic / vperm load per round
                 const u32 w = (i < 2) ? jj01 : jj23;
                 j = (int)((w >> ((i & 1) << 4)) & 0xffffu);
