@@ -163,7 +163,7 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
                 double m1 = SWD_BIG, m2 = SWD_BIG; int arg = -1; u32 par = s_synd[r];
                 // the +-50 clip (pyx:74-76) is monotone: the two smallest clipped magnitudes are the clipped two smallest
                 // magnitudes, so it is applied to min1 / min2 once per row ...
-#pragma unroll 2
+#pragma unroll 4
                 for (int p = p0; p < p1; p++) {
                     const double b = msg[p];
                     const double a = fabs(b);
@@ -197,7 +197,7 @@ pre_bp_kernel(GraphDev g, const u8 *__restrict__ synd, long long B, int max_iter
                     // no message of the row is an exact zero, so "b <= 0" is the sign bit: every slot gets +-q1 (only the sign bit of
                     // the old message is used), then the argmin slot is patched with +-q2 of the sign just written
                     const int q1lo = __double2loint(q1), q1hi = __double2hiint(q1) ^ (int)(par << 31);
-#pragma unroll 4
+#pragma unroll 8
                     for (int p = p0; p < p1; p++) msg[p] = __hiloint2double(q1hi ^ (__double2hiint(msg[p]) & (int)0x80000000), q1lo);
                     if (arg >= 0) {
                         const int x = (__double2hiint(msg[arg]) ^ __double2hiint(q1)) & (int)0x80000000;
