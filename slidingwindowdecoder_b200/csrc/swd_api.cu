@@ -619,6 +619,9 @@ static int setup_kernels(swd_decoder *d) {
                                      (size_t)d->LsA.blob_bytes + d->PS.total, (size_t)d->LsB.blob_bytes + d->PSB.total);
     const size_t smemB = (size_t)d->LsB.blob_bytes + d->PSB.total;
     if (smemB > 227 * 1024) { set_err("shortened graph does not fit in shared memory"); return SWD_ERR_UNSUPPORTED; }
+    // the per-call VN records of bp_run pack (index < 4096, first edge < 32768, degree < 32) into one word; the shared-memory bound above
+    // keeps es_slots far below that, this only states the invariant
+    if (es_slots > 32767 || nn > 4096) { set_err("shortened graph too large for the packed VN records"); return SWD_ERR_UNSUPPORTED; }
     const size_t smemA = (size_t)d->LsA.blob_bytes + d->PS.total;
     if ((st = occupancy(d->path_fn, d->T3, smemA, &occ))) return st;
     if (occ < 1) { set_err("path_kernel does not fit"); return SWD_ERR_UNSUPPORTED; }
